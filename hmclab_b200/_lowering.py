@@ -1,0 +1,284 @@
+"""Lowering of a distribution object tree to the flat plan the CUDA engine consumes.
+
+``describe`` walks either ``hmclab_b200`` objects or genuine ``hmclab`` objects (it
+dispatches on the class *name* and reads the reference's attribute names, so a
+reference user's posterior can be handed over unchanged) and returns a tree of
+plain dicts holding float64 numpy arrays.  ``flatten`` turns that tree into
+
+* elementwise prior terms on coordinate ranges (Normal-diagonal, Laplace),
+* bound checks (every object with bounds contributes ``+inf`` to the misfit and,
+  for the priors/containers, to the gradient on its range; base.py:361-374,
+  564-570, 703-710, 786, 867-898, 1036-1054),
+* the reflection bounds the trajectory uses (base.py:239-270, 913-978, 1111-1142),
+* at most one coupled likelihood (dense / CSR LinearMatrix, SourceLocation3D).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+
+LIKELIHOOD_KINDS = ("linear_dense", "linear_csr", "srcloc3d")
+
+
+def _vec(x, n: int, what: str) -> np.ndarray:
+    """Scalar or (n,1)/(n,) -> contiguous float64 (n,)."""
+    a = np.asarray(x, dtype=np.float64)
+    if a.ndim == 0:
+        return np.full(n, float(a))
+    if a.size != n:
+        raise ValueError(f"{what}: expected {n} values, got shape {a.shape}")
+    return np.ascontiguousarray(a.reshape(n))
+
+
+def _bounds(obj, n: int):
+    lb = getattr(obj, "lower_bounds", None)
+    ub = getattr(obj, "upper_bounds", None)
+    return (
+        None if lb is None else _vec(lb, n, "lower_bounds"),
+        None if ub is None else _vec(ub, n, "upper_bounds"),
+    )
+
+
+def _csr_arrays(mat):
+    import scipy.sparse as sp
+
+    m = sp.csr_matrix(mat)
+    m.sum_duplicates()
+    m.sort_indices()
+    return (
+        np.ascontiguousarray(m.indptr, dtype=np.int32),
+        np.ascontiguousarray(m.indices, dtype=np.int32),
+        np.ascontiguousarray(m.data, dtype=np.float64),
+    )
+
+
+def describe(dist) -> Dict[str, Any]:
+    """Distribution object -> tree of plain dicts (see module docstring)."""
+    cls = type(dist).__name__
+    n = int(dist.dimensions)
+    lb, ub = _bounds(dist, n)
+    node: Dict[str, Any] = {"dims": n, "lb": lb, "ub": ub}
+
+    if cls == "Normal":
+        if not getattr(dist, "diagonal", True):
+            raise NotImplementedError("Normal with full covariance is not lowered.")
+        node.update(
+            kind="normal",
+            means=_vec(dist.means, n, "means"),
+            inv_cov=_vec(dist.inverse_covariance, n, "inverse_covariance"),
+            const=float(dist.normalization_constant),
+        )
+    elif cls == "Laplace":
+        node.update(
+            kind="laplace",
+            means=_vec(dist.means, n, "means"),
+            inv_disp=_vec(dist.inverse_dispersions, n, "inverse_dispersions"),
+            const=float(dist.normalization_constant),
+        )
+    elif cls == "Uniform":
+        node.update(kind="uniform")
+    elif cls in ("AdditiveDistribution", "BayesRule"):
+        node.update(
+            kind="additive", children=[describe(c) for c in dist.separate_distributions]
+        )
+    elif cls == "CompositeDistribution":
+        node.update(
+            kind="composite", children=[describe(c) for c in dist.separate_distributions]
+        )
+    elif cls == "LinearMatrix":
+        inner = describe(dist.Distribution)
+        # wrapper adds its own misfit_bounds on top of the inner ones (LinearMatrix.py:114-116)
+        inner["wrapper_lb"], inner["wrapper_ub"] = lb, ub
+        return inner
+    elif cls == "_LinearMatrix_dense_forward_simple_covariance":
+        node.update(kind="linear_dense", premult=bool(dist.premultiplication))
+        if dist.premultiplication:
+            node.update(
+                GtG=np.ascontiguousarray(dist.GtG, dtype=np.float64),
+                Gtd0=_vec(dist.Gtd0, n, "Gtd0"),
+                dtd=float(dist.dtd),
+            )
+        else:
+            N = int(dist.G.shape[0])
+            G = np.ascontiguousarray(dist.G, dtype=np.float64)
+            Gt = np.ascontiguousarray(dist.Gt, dtype=np.float64)
+            node.update(
+                N=N,
+                G=G,
+                Gt=None if np.array_equal(Gt, G.T) else Gt,
+                d=_vec(dist.d, N, "d"),
+                var=_vec(dist.data_variance, N, "data_variance"),
+                sigma=_vec(dist.data_sigma, N, "data_sigma"),
+            )
+    elif cls == "_LinearMatrix_sparse_forward_simple_covariance":
+        node.update(kind="linear_csr", premult=bool(dist.premultiplication))
+        if dist.premultiplication:
+            indptr, indices, data = _csr_arrays(dist.GtG)
+            node.update(
+                N=n,
+                indptr=indptr,
+                indices=indices,
+                data=data,
+                Gtd0=_vec(dist.Gtd0, n, "Gtd0"),
+                dtd=float(dist.dtd),
+            )
+        else:
+            N = int(dist.G.shape[0])
+            indptr, indices, data = _csr_arrays(dist.G)
+            t_indptr, t_indices, t_data = _csr_arrays(dist.Gt)
+            node.update(
+                N=N,
+                indptr=indptr,
+                indices=indices,
+                data=data,
+                t_indptr=t_indptr,
+                t_indices=t_indices,
+                t_data=t_data,
+                d=_vec(dist.d, N, "d"),
+                var=_vec(dist.data_variance, N, "data_variance"),
+                sigma=_vec(dist.data_sigma, N, "data_sigma"),
+            )
+    elif cls == "SourceLocation3D":
+        E, S = int(dist.number_of_events), int(dist.number_of_stations)
+        node.update(
+            kind="srcloc3d",
+            events=E,
+            stations=S,
+            rx=_vec(dist.receiver_array_x, S, "receiver_array_x"),
+            ry=_vec(dist.receiver_array_y, S, "receiver_array_y"),
+            rz=_vec(dist.receiver_array_z, S, "receiver_array_z"),
+            tobs=np.ascontiguousarray(dist.observed_data, dtype=np.float64).reshape(E, S),
+            std=np.ascontiguousarray(dist.data_std, dtype=np.float64).reshape(E, S),
+            infer_velocity=bool(dist.infer_velocity),
+            velocity=(
+                float("nan")
+                if dist.infer_velocity
+                else float(np.asarray(dist.medium_velocity).reshape(-1)[0])
+            ),
+        )
+    else:
+        raise NotImplementedError(
+            f"Distribution type `{cls}` is not on the batched B200 path "
+            "(supported: Normal (diagonal), Laplace, Uniform, CompositeDistribution, "
+            "AdditiveDistribution/BayesRule, LinearMatrix with scalar/vector variance, "
+            "SourceLocation3D)."
+        )
+    return node
+
+
+def describe_mass(mass) -> Dict[str, Any]:
+    cls = type(mass).__name__
+    n = int(mass.dimensions)
+    if cls == "Unit":
+        return {"kind": "unit", "dims": n}
+    if cls == "Diagonal":
+        return {
+            "kind": "diagonal",
+            "dims": n,
+            "diagonal": _vec(mass.diagonal, n, "diagonal"),
+            "inverse_diagonal": _vec(mass.inverse_diagonal, n, "inverse_diagonal"),
+        }
+    raise NotImplementedError(
+        f"Mass matrix `{cls}` is not on the batched B200 path (Unit, Diagonal)."
+    )
+
+
+# --------------------------------------------------------------------------------------
+def _reflection(tree) -> (Optional[np.ndarray], Optional[np.ndarray]):
+    """Bounds the *top-level* object's ``corrector`` reflects on."""
+    n = tree["dims"]
+    lb, ub = tree["lb"], tree["ub"]
+    if tree["kind"] in LIKELIHOOD_KINDS and "wrapper_lb" in tree:
+        lb, ub = tree["wrapper_lb"], tree["wrapper_ub"]
+    if tree["kind"] == "composite" and lb is None and ub is None:
+        # base.py:946-978: falls through to the direct children's own bounds
+        lo = np.full(n, -np.inf)
+        hi = np.full(n, np.inf)
+        any_lo = any_hi = False
+        off = 0
+        for child in tree["children"]:
+            c_lb, c_ub = child["lb"], child["ub"]
+            if child["kind"] in LIKELIHOOD_KINDS and "wrapper_lb" in child:
+                c_lb, c_ub = child["wrapper_lb"], child["wrapper_ub"]
+            if c_lb is not None:
+                lo[off : off + child["dims"]] = c_lb
+                any_lo = True
+            if c_ub is not None:
+                hi[off : off + child["dims"]] = c_ub
+                any_hi = True
+            off += child["dims"]
+        return (lo if any_lo else None), (hi if any_hi else None)
+    return lb, ub
+
+
+def flatten(tree) -> Dict[str, Any]:
+    """Tree from ``describe`` -> flat engine plan."""
+    plan: Dict[str, Any] = {
+        "dims": tree["dims"],
+        "terms": [],
+        "checks": [],
+        "likelihood": None,
+    }
+
+    def add_check(offset, n, lb, ub, in_gradient):
+        if lb is None and ub is None:
+            return
+        for chk in plan["checks"]:
+            same = (
+                chk["offset"] == offset
+                and chk["len"] == n
+                and (chk["lb"] is None) == (lb is None)
+                and (chk["ub"] is None) == (ub is None)
+                and (lb is None or np.array_equal(chk["lb"], lb))
+                and (ub is None or np.array_equal(chk["ub"], ub))
+            )
+            if same:
+                chk["in_gradient"] = chk["in_gradient"] or in_gradient
+                return
+        plan["checks"].append(
+            {"offset": offset, "len": n, "lb": lb, "ub": ub, "in_gradient": in_gradient}
+        )
+
+    def visit(node, offset):
+        kind, n = node["kind"], node["dims"]
+        if kind in LIKELIHOOD_KINDS:
+            if plan["likelihood"] is not None:
+                raise NotImplementedError("Only one coupled likelihood per posterior.")
+            if offset != 0 or n != tree["dims"]:
+                raise NotImplementedError(
+                    "A coupled likelihood must span all coordinates of the posterior."
+                )
+            plan["likelihood"] = node
+            add_check(offset, n, node["lb"], node["ub"], False)
+            add_check(offset, n, node.get("wrapper_lb"), node.get("wrapper_ub"), False)
+            return
+        add_check(offset, n, node["lb"], node["ub"], True)
+        if kind == "normal":
+            plan["terms"].append(
+                {"kind": "normal", "offset": offset, "len": n, "a": node["means"],
+                 "b": node["inv_cov"], "const": node["const"]}
+            )
+        elif kind == "laplace":
+            plan["terms"].append(
+                {"kind": "laplace", "offset": offset, "len": n, "a": node["means"],
+                 "b": node["inv_disp"], "const": node["const"]}
+            )
+        elif kind == "uniform":
+            pass
+        elif kind == "additive":
+            for child in node["children"]:
+                if child["dims"] != n:
+                    raise ValueError("Additive children must share dimensions.")
+                visit(child, offset)
+        elif kind == "composite":
+            off = offset
+            for child in node["children"]:
+                visit(child, off)
+                off += child["dims"]
+        else:  # pragma: no cover
+            raise NotImplementedError(kind)
+
+    visit(tree, 0)
+    plan["reflect_lb"], plan["reflect_ub"] = _reflection(tree)
+    return plan

@@ -1,0 +1,50 @@
+"""Pins oracle/hmc_oracle.py (and the mirror constructors + lowering that feed it) to
+outputs of the unmodified reference stored in tests/golden/*.npz."""
+import numpy as np
+import pytest
+
+import cases
+from helpers import build_mirror, load_golden, rel_err
+from hmclab_b200._lowering import describe, describe_mass
+from oracle import hmc_oracle as oracle
+
+TOL = 1e-13  # same numpy/BLAS calls in the same order: agreement is at rounding level
+
+
+@pytest.mark.parametrize("name", cases.CASES)
+def test_oracle_reproduces_reference(name):
+    inp, ref = load_golden(name)
+    s = cases.SETTINGS[name]
+    post, mass = build_mirror(name, inp)
+    tree, mtree = describe(post), describe_mass(mass)
+    with np.errstate(all="ignore"):
+        got = oracle.run_chains(
+            tree, mtree, q0=inp["q0"], z=inp["z"], u_step=inp["u_step"],
+            u_acc=inp["u_acc"], integrator=s["integrator"], steps=s["steps"],
+            stepsize=s["stepsize"], randomize=s["randomize"], record_trace=True)
+    assert np.array_equal(got["accept"], ref["accept"]), "accept/reject sequence differs"
+    for key in ("H0", "H1", "q_prop", "p_prop", "samples", "trace_q", "trace_g"):
+        assert rel_err(got[key], ref[key]) < TOL, key
+
+
+@pytest.mark.parametrize("name", cases.CASES)
+def test_oracle_misfit_gradient_contract(name):
+    inp, ref = load_golden(name)
+    post, _ = build_mirror(name, inp)
+    tree = describe(post)
+    d = tree["dims"]
+    with np.errstate(all="ignore"):
+        for i, point in enumerate(ref["probe_points"]):
+            m = point.reshape(d, 1).copy()
+            assert rel_err(oracle.misfit(tree, m), ref["probe_misfit"][i]) < TOL
+            assert rel_err(oracle.gradient(tree, m)[:, 0], ref["probe_gradient"][i]) < TOL
+
+
+def test_golden_cases_exercise_both_decisions_and_bounds():
+    mixed = 0
+    nonfinite = 0
+    for name in cases.CASES:
+        _, ref = load_golden(name)
+        mixed += 0 < ref["accept"].mean() < 1
+        nonfinite += (~np.isfinite(ref["H1"])).any()
+    assert mixed >= 10 and nonfinite >= 2
