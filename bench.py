@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Throughput of the batched HMC hot path: gradient evaluations per second
+(chains x leapfrog steps), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one block of ``--block`` HMC proposals for every chain of the workload
+(momentum draw on the device, full trajectory, energies, Metropolis decision, sample
+rows written).  Default workload: BASELINE.json configs[1] (1000-dim standard normal,
+4096 chains, leapfrog L=10, Unit mass).  Under torchrun every rank owns its own
+``chains`` chains (weak scaling, chain ids keyed by rank, no collective in the step; one
+NCCL all-gather of the acceptance counters per block).
+
+One JSON line on stdout (rank 0).  ``value`` is timed with CUDA events around every step
+(inputs resident in HBM, L2 flushed between steps); ``e2e`` is the same metric through
+``hmcb_sample_host`` with pinned HOST buffers, copies inside the timed region.
+``--impl reference`` times the CPU restatement of the reference's path (oracle/, one
+process per host core) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gradient evals/s (chains x leapfrog steps)"
+UNIT = "grad_evals/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# fp64 peak is not in MEASURED_PEAKS.json; profiles/fp64_peak_r01.json holds this pool's
+# measured cuBLAS DGEMM / DFMA numbers once measured, else the datasheet value is used.
+def fp64_peak_tflops():
+    path = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["dgemm_tflops"]), "measured cuBLAS DGEMM (profiles/fp64_peak_r01.json)"
+    return 37.0, "datasheet (unmeasured)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes_per_step(w, block, thinning):
+    """HBM bytes one step must move with the trajectory fused on chip:
+    q read + q write + stored sample rows + per-chain scalars."""
+    C, d = w.chains, w.dims
+    rows = block // thinning
+    return 8.0 * C * d * 2 + 8.0 * C * (d + 1) * rows + 8.0 * C * 2 + 4.0 * C
+
+
+def cpu_oracle_rate(w, seconds, seed=0):
+    """grad evals/s of the numpy restatement (one chain, one core) on a bounded sample."""
+    from hmclab_b200._lowering import describe, describe_mass
+    from oracle import hmc_oracle as oracle
+
+    tree, mtree = describe(w.posterior), describe_mass(w.mass_matrix)
+    draws = oracle.GeneratorDraws(seed)
+    q0 = w.initial_models[0]
+    done, t0 = 0, time.perf_counter()
+    chunk = 1
+    with np.errstate(all="ignore"):
+        while True:
+            res = oracle.run_chain(tree, mtree, integrator=w.integrator, steps=w.amount_of_steps,
+                                   stepsize=w.stepsize, randomize=True, q0=q0, proposals=chunk,
+                                   draws=draws)
+            q0 = res["final_q"]
+            done += chunk
+            el = time.perf_counter() - t0
+            if el >= seconds:
+                break
+            chunk = max(1, min(4 * chunk, int(chunk * (seconds - el) / max(el, 1e-3) * 0.5) or 1))
+    return done * w.grads_per_proposal / el, done, el
+
+
+def _reference_worker(args):
+    name, kwargs, proposals, seed, chain = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from hmclab_b200 import workloads
+    from hmclab_b200._lowering import describe, describe_mass
+    from oracle import hmc_oracle as oracle
+
+    w = _WORKLOAD_CACHE.get(name)
+    if w is None:
+        w = workloads.BUILDERS[name](**kwargs)
+        _WORKLOAD_CACHE[name] = w
+    tree, mtree = describe(w.posterior), describe_mass(w.mass_matrix)
+    with np.errstate(all="ignore"):
+        res = oracle.run_chain(tree, mtree, integrator=w.integrator, steps=w.amount_of_steps,
+                               stepsize=w.stepsize, randomize=True,
+                               q0=w.initial_models[chain % w.chains], proposals=proposals,
+                               draws=oracle.GeneratorDraws(seed))
+    return int(res["accept"].sum())
+
+
+_WORKLOAD_CACHE = {}
+
+
+def run_reference(args, w, name, kwargs):
+    """CPU arm: the oracle port of the reference's path, one process per host core (the
+    reference's ParallelSampleSMP layout: one OS process per chain)."""
+    import multiprocessing as mp
+
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
+    cores = os.cpu_count() or 1
+    # size a step: about (150 s / (steps + warmup)) of work per core, bounded
+    rate1, _, _ = cpu_oracle_rate(w, 3.0)
+    budget = max(1.0, min(20.0, 150.0 / (args.steps + args.warmup)))
+    proposals = max(1, int(rate1 * budget / w.grads_per_proposal))
+    _WORKLOAD_CACHE[name] = w
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            jobs = [(name, kwargs, proposals if it >= args.warmup else max(1, proposals // 10),
+                     1000 * it + c, c) for c in range(cores)]
+            t0 = time.perf_counter()
+            pool.map(_reference_worker, jobs)
+            if it >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    evals = cores * proposals * w.grads_per_proposal * args.steps
+    value = evals / total
+    sample = (f"{cores} processes x 1 chain x {proposals} proposals per step "
+              f"(oracle/hmc_oracle.py, numpy {np.__version__}, 1 BLAS thread each)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": w.description, "chains_per_step": cores,
+                                        "proposals_per_step": proposals},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="normal_iid")
+    ap.add_argument("--block", type=int, default=10, help="proposals per step")
+    ap.add_argument("--thinning", type=int, default=1)
+    ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == "reference" or os.environ.get("HMCB_BENCH_ALLOW_SHORT"), \
+        "timing rules: at least 3 warm-up steps"
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from hmclab_b200 import workloads
+
+    kwargs = {"chains": args.chains} if args.chains else {}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w = workloads.BUILDERS[args.workload](**kwargs)
+        run_reference(args, w, args.workload, kwargs)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; hmclab_b200 has no CPU path to time")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from hmclab_b200._engine import Engine
+    from hmclab_b200._lowering import describe, describe_mass, flatten
+
+    w = workloads.BUILDERS[args.workload](**kwargs)
+    C, d, B, thin = w.chains, w.dims, args.block, args.thinning
+    assert B % thin == 0
+    eng = Engine(flatten(describe(w.posterior)), describe_mass(w.mass_matrix), C,
+                 integrator=w.integrator, amount_of_steps=w.amount_of_steps, device=local_rank)
+    dev = torch.device("cuda", local_rank)
+    q = torch.as_tensor(w.initial_models, dtype=torch.float64).to(dev).contiguous()
+    x = eng.misfit(q)
+    rows = B // thin
+    samples = torch.empty(rows, C, d + 1, dtype=torch.float64, device=dev)
+    accepted = torch.zeros(C, dtype=torch.int32, device=dev)
+    gathered = torch.zeros(world * C, dtype=torch.int32, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    chain_offset = rank * C
+
+    def step(k):
+        eng.run_block(q, x, B, stepsize=w.stepsize, randomize_stepsize=True, thinning=thin,
+                      proposal_offset=k * B, chain_offset=chain_offset, seed=2026,
+                      out_samples=samples, accepted_total=accepted)
+        if world > 1:  # diagnostics gather, once per sample block
+            dist.all_gather_into_tensor(gathered, accepted)
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)           # evict the previous step's lines from L2 (untimed)
+        starts[i].record()
+        step(args.warmup + i)
+        ends[i].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    if world > 1:
+        dist.barrier()
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    evals_per_step = world * C * B * w.grads_per_proposal
+    value = evals_per_step * args.steps / (total_ms * 1e-3)
+    acc_rate = float(accepted.double().mean().item()) / ((args.warmup + args.steps) * B)
+
+    # ---- end to end: host buffers, copies inside the timed region -----------------------
+    e2e = None
+    if not args.no_e2e:
+        q0_host = torch.as_tensor(w.initial_models, dtype=torch.float64).contiguous().pin_memory()
+        out_host = torch.empty(rows, C, d + 1, dtype=torch.float64).pin_memory()
+        acc_host = torch.empty(C, dtype=torch.int32).pin_memory()
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(2):
+            eng.sample_host(q0_host, B, stepsize=w.stepsize, thinning=thin, block_proposals=B,
+                            seed=7, chain_offset=chain_offset, samples=out_host, accepted=acc_host)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            eng.sample_host(q0_host, B, stepsize=w.stepsize, thinning=thin, block_proposals=B,
+                            seed=8 + i, chain_offset=chain_offset, samples=out_host, accepted=acc_host)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        te = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        el = float(te.item())
+        e2e = {"value": evals_per_step * n_e2e / el, "unit": UNIT,
+               "h2d_bytes_per_step": int(q0_host.numel() * 8),
+               "d2h_bytes_per_step": int(out_host.numel() * 8 + acc_host.numel() * 4),
+               "steps": n_e2e, "api": "hmcb_sample_host (C ABI, pinned host buffers)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------
+    peaks = measured_peaks()
+    ms_per_step = total_ms / args.steps
+    if eng.path in ("fused_priors", "fused_srcloc"):
+        abytes = algorithmic_bytes_per_step(w, B, thin)
+        achieved = abytes / (ms_per_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                    "kernel": "hmc_fused_priors_kernel" if eng.path == "fused_priors" else "hmc_fused_srcloc_kernel",
+                    "algorithmic_bytes_per_launch": abytes, "peak_source": peaks["source"],
+                    "note": "one launch per step; fp64 SIMT pipe, not HBM, limits this kernel (see DESIGN.md)"}
+    else:
+        peak, src = fp64_peak_tflops()
+        flops = w.extra.get("flops_per_grad")
+        if flops is None and "nnz" in w.extra:
+            flops = 4.0 * w.extra["nnz"]
+        achieved = flops * value / world / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "kernel": "dmma_gemm_kernel / csr_spmm_kernel (whole step time attributed)",
+                    "algorithmic_flops_per_grad_eval": flops, "peak_source": src}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, n_prop, el = cpu_oracle_rate(w, args.cpu_seconds)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"1 chain x {n_prop} proposals of the same workload in {el:.1f} s "
+                         f"(oracle/hmc_oracle.py numpy restatement, host cores available: {os.cpu_count()})"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w.description, "chains_per_gpu": C, "dims": d,
+                   "proposals_per_step": B, "online_thinning": thin, "integrator": w.integrator,
+                   "amount_of_steps": w.amount_of_steps, "path": eng.path, "rng": "on-device Philox4x32-10",
+                   "l2": "256 MiB flush write between timed steps"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "cpu_baseline": cpu, "acceptance_rate": acc_rate, "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

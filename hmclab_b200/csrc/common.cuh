@@ -1,0 +1,281 @@
+// common.cuh -- device-side building blocks shared by every HMC kernel.
+//
+//  * DevTarget: flattened target distribution (elementwise priors, bound checks,
+//    reflection bounds, mass matrix) passed by value to kernels.
+//  * Elementwise arithmetic follows the reference's operation order and is written with
+//    __dmul_rn/__dadd_rn/__dsub_rn so that nvcc never contracts it into FMAs: on separable
+//    targets a trajectory is bit-identical to numpy's.
+//  * Philox4x32-10 counter RNG keyed by (seed; chain, proposal, pair, stream) so that the
+//    draws do not depend on how chains are distributed over GPUs or thread blocks.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#define HMCB_MAX_PRIORS 8
+#define HMCB_MAX_CHECKS 8
+
+namespace hmcb {
+
+struct PriorTerm {
+  int kind;    // HMCB_PRIOR_NORMAL / HMCB_PRIOR_LAPLACE
+  int offset;  // first coordinate
+  int len;
+  const double* a;  // means            (indexed j - offset)
+  const double* b;  // inverse variance / inverse dispersion
+};
+
+struct BoundCheck {
+  int offset;
+  int len;
+  int in_gradient;
+  const double* lb;  // may be null (indexed j - offset)
+  const double* ub;  // may be null
+};
+
+struct DevTarget {
+  int dims;
+  int n_priors;
+  int n_checks;
+  unsigned grad_check_mask;  // bit k set: check k adds +inf to the gradient on its range
+  double const_sum;          // sum of the priors' normalisation constants
+  PriorTerm prior[HMCB_MAX_PRIORS];
+  BoundCheck check[HMCB_MAX_CHECKS];
+  const double* refl_lb;  // [dims] or null
+  const double* refl_ub;  // [dims] or null
+  const double* invm;     // [dims] 1/diagonal, null = unit mass
+  const double* sqrtm;    // [dims] sqrt(diagonal), null = unit mass
+};
+
+// ---------------------------------------------------------------- elementwise pieces ---
+
+__device__ __forceinline__ double sign_np(double v) {
+  // numpy.sign: -1, 0, +1, nan
+  return (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : ((v == 0.0) ? 0.0 : v));
+}
+
+// Sum over prior terms of d(chi)/dq_j at coordinate j (base.py:564-570, 703-710), plus
+// +inf when a gradient-visible bound check of this chain has fired (oob_mask).
+__device__ __forceinline__ double prior_gradient(const DevTarget& T, int j, double q,
+                                                 unsigned oob_mask) {
+  double g = 0.0;
+#pragma unroll 1
+  for (int t = 0; t < T.n_priors; ++t) {
+    const PriorTerm& P = T.prior[t];
+    const unsigned r = (unsigned)(j - P.offset);
+    if (r < (unsigned)P.len) {
+      const double a = __ldg(P.a + r), b = __ldg(P.b + r);
+      double term;
+      if (P.kind == 0) term = __dmul_rn(-b, __dsub_rn(a, q));          // -icov * (mu - q)
+      else             term = __dmul_rn(sign_np(__dsub_rn(q, a)), b);  // sign(q - mu) * idisp
+      g = __dadd_rn(g, term);
+    }
+  }
+  oob_mask &= T.grad_check_mask;
+  if (oob_mask) {
+#pragma unroll 1
+    for (int k = 0; k < T.n_checks; ++k)
+      if (((oob_mask >> k) & 1u) && (unsigned)(j - T.check[k].offset) < (unsigned)T.check[k].len)
+        g = __dadd_rn(g, CUDART_INF);
+  }
+  return g;
+}
+
+// Contribution of coordinate j to the prior misfit, constants excluded (base.py:539-550,
+// 689-700): Normal 0.5*r*(icov*r), Laplace |q-mu|*idisp.
+__device__ __forceinline__ double prior_misfit(const DevTarget& T, int j, double q) {
+  double s = 0.0;
+#pragma unroll 1
+  for (int t = 0; t < T.n_priors; ++t) {
+    const PriorTerm& P = T.prior[t];
+    const unsigned r = (unsigned)(j - P.offset);
+    if (r < (unsigned)P.len) {
+      const double a = __ldg(P.a + r), b = __ldg(P.b + r);
+      if (P.kind == 0) {
+        const double d = __dsub_rn(a, q);
+        s = __dadd_rn(s, __dmul_rn(0.5, __dmul_rn(d, __dmul_rn(b, d))));
+      } else {
+        s = __dadd_rn(s, __dmul_rn(fabs(__dsub_rn(q, a)), b));
+      }
+    }
+  }
+  return s;
+}
+
+// Bit k set iff coordinate j violates bound check k (misfit_bounds, base.py:361-374).
+__device__ __forceinline__ unsigned bound_violations(const DevTarget& T, int j, double q) {
+  unsigned m = 0;
+#pragma unroll 1
+  for (int k = 0; k < T.n_checks; ++k) {
+    const BoundCheck& B = T.check[k];
+    const unsigned r = (unsigned)(j - B.offset);
+    if (r < (unsigned)B.len) {
+      const bool low = B.lb && (q < __ldg(B.lb + r));
+      const bool high = B.ub && (q > __ldg(B.ub + r));
+      if (low || high) m |= (1u << k);
+    }
+  }
+  return m;
+}
+
+// One-shot mirror reflection (base.py:258-270): the upper test sees the corrected q.
+__device__ __forceinline__ void reflect(const DevTarget& T, int j, double& q, double& p) {
+  if (T.refl_lb) {
+    const double lb = __ldg(T.refl_lb + j);
+    if (q < lb) { q = __dadd_rn(q, __dmul_rn(2.0, __dsub_rn(lb, q))); p = -p; }
+  }
+  if (T.refl_ub) {
+    const double ub = __ldg(T.refl_ub + j);
+    if (q > ub) { q = __dadd_rn(q, __dmul_rn(2.0, __dsub_rn(ub, q))); p = -p; }
+  }
+}
+
+// dK/dp_j (MassMatrices.py:116-133, 201-218)
+__device__ __forceinline__ double kinetic_gradient(const DevTarget& T, int j, double p) {
+  return T.invm ? __dmul_rn(__ldg(T.invm + j), p) : p;
+}
+// p_j * dK/dp_j ; K = 0.5 * sum (MassMatrices.py:100-114, 185-199)
+__device__ __forceinline__ double kinetic_term(const DevTarget& T, int j, double p) {
+  return __dmul_rn(p, kinetic_gradient(T, j, p));
+}
+// q += coeff * dK/dp ; reflect
+__device__ __forceinline__ void position_update(const DevTarget& T, int j, double coeff,
+                                                double& q, double& p) {
+  q = __dadd_rn(q, __dmul_rn(coeff, kinetic_gradient(T, j, p)));
+  reflect(T, j, q, p);
+}
+// p -= coeff * g
+__device__ __forceinline__ void momentum_update(double coeff, double g, double& p) {
+  p = __dsub_rn(p, __dmul_rn(coeff, g));
+}
+
+// Metropolis test (Samplers.py:1481-1486): exp(H0 - H1) > u, NaN compares false.
+__device__ __forceinline__ bool metropolis_accept(double h0, double h1, double u) {
+  return exp(__dsub_rn(h0, h1)) > u;
+}
+
+// -------------------------------------------------------------------------- Philox ---
+
+struct Philox4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                 uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+  // top 53 bits of the 64-bit word (hi:lo) -> [0,1)
+  const uint64_t w = ((uint64_t)hi << 32) | lo;
+  return (double)(w >> 11) * 1.1102230246251565e-16;  // 2^-53
+}
+
+enum : uint32_t { STREAM_NORMAL = 0u, STREAM_UNIFORM = 1u };
+
+// Standard normals for coordinates (2*pair, 2*pair+1) of `chain` at `proposal`.
+__device__ __forceinline__ void normal_pair(uint64_t seed, uint32_t chain, uint32_t proposal,
+                                            uint32_t pair, double& z0, double& z1) {
+  const Philox4 r = philox4x32_10(chain, proposal, pair, STREAM_NORMAL, (uint32_t)seed,
+                                  (uint32_t)(seed >> 32));
+  const double u1 = 1.0 - u53(r.x, r.y);  // (0,1]
+  const double u2 = u53(r.z, r.w);        // [0,1)
+  const double rad = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  z0 = rad * c;
+  z1 = rad * s;
+}
+
+// (step-size factor in [0.5,1.5), acceptance uniform in [0,1)) of `chain` at `proposal`.
+__device__ __forceinline__ void uniform_pair(uint64_t seed, uint32_t chain, uint32_t proposal,
+                                             double& u_step, double& u_acc) {
+  const Philox4 r = philox4x32_10(chain, proposal, 0u, STREAM_UNIFORM, (uint32_t)seed,
+                                  (uint32_t)(seed >> 32));
+  u_step = 0.5 + u53(r.x, r.y);
+  u_acc = u53(r.z, r.w);
+}
+
+// ---------------------------------------------------------------- chain reductions ---
+// A chain is owned by TPC consecutive threads (TPC a power of two).  TPC <= 32: the group
+// lives inside one warp and reduces with xor-shuffles (every lane ends with the same
+// bits because each butterfly level adds the same two numbers on both partners).
+// TPC > 32: TPC == blockDim.x (one chain per block); warps reduce, then every thread
+// sums the per-warp partials in warp order.  Summation order is fixed => deterministic.
+
+template <int TPC>
+struct ChainReduce {
+  static constexpr int kWarps = (TPC + 31) / 32;
+  double* scratch;  // >= 3 * kWarps doubles of shared memory (TPC > 32 only)
+
+  __device__ __forceinline__ void sum3(double& a, double& b, double& c) const {
+    constexpr int W = TPC < 32 ? TPC : 32;
+#pragma unroll
+    for (int off = W / 2; off > 0; off >>= 1) {
+      a = __dadd_rn(a, __shfl_xor_sync(0xffffffffu, a, off));
+      b = __dadd_rn(b, __shfl_xor_sync(0xffffffffu, b, off));
+      c = __dadd_rn(c, __shfl_xor_sync(0xffffffffu, c, off));
+    }
+    if constexpr (TPC > 32) {
+      const int warp = threadIdx.x >> 5;
+      if ((threadIdx.x & 31) == 0) {
+        scratch[warp] = a; scratch[kWarps + warp] = b; scratch[2 * kWarps + warp] = c;
+      }
+      __syncthreads();
+      a = 0.0; b = 0.0; c = 0.0;
+#pragma unroll 4
+      for (int w = 0; w < kWarps; ++w) {
+        a = __dadd_rn(a, scratch[w]);
+        b = __dadd_rn(b, scratch[kWarps + w]);
+        c = __dadd_rn(c, scratch[2 * kWarps + w]);
+      }
+      __syncthreads();
+    }
+  }
+
+  __device__ __forceinline__ unsigned any_bits(unsigned m) const {
+    constexpr int W = TPC < 32 ? TPC : 32;
+#pragma unroll
+    for (int off = W / 2; off > 0; off >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, off);
+    if constexpr (TPC > 32) {
+      unsigned* s = reinterpret_cast<unsigned*>(scratch);
+      const int warp = threadIdx.x >> 5;
+      if ((threadIdx.x & 31) == 0) s[warp] = m;
+      __syncthreads();
+      m = 0;
+      for (int w = 0; w < kWarps; ++w) m |= s[w];
+      __syncthreads();
+    }
+    return m;
+  }
+};
+
+// ------------------------------------------------------------ integrator schedule ---
+// A trajectory is: [lone position update]* then pairs (momentum update, position update);
+// every momentum sub-step of lf/3s/4s is followed by a position sub-step
+// (Samplers.py:1524-1584, 1586-1661, 1663-1726).  Coefficients are multiples of the
+// chain's step size eps.
+
+struct StageOp {
+  double b;   // momentum coefficient multiplier (used iff has_b)
+  double a;   // position coefficient multiplier
+  int has_b;  // 1: gradient + momentum update + position update; 0: position update only
+  int pad;
+};
+
+struct Schedule {
+  int n_pre, n_body, reps, n_post;
+  int grads_per_proposal;
+  int pad;
+  StageOp pre[2];
+  StageOp body[6];
+  StageOp post[2];
+};
+
+}  // namespace hmcb

@@ -1,0 +1,313 @@
+// fused.cuh -- whole-proposal fused HMC kernels for targets whose gradient does not couple
+// chains through a matrix product: (a) elementwise priors only, (b) SourceLocation3D.
+//
+// One launch advances every chain by B proposals: momentum draw, kinetic energy, the full
+// leapfrog / 3-stage / 4-stage trajectory with bounds reflection, misfit, Hamiltonians,
+// Metropolis decision, state update and sample-row write.  The chain state lives in
+// registers for the whole block of proposals; HBM sees q once in, once out, and one
+// (d+1)-row per stored sample.
+//
+// Replaces Samplers.py:1463-1492 (propose + evaluate_acceptance), :1524-1726 (integrators),
+// MassMatrices.py:100-142,185-227, base.py:239-270 (corrector) for these targets.
+#pragma once
+#include "common.cuh"
+
+namespace hmcb {
+
+struct FusedArgs {
+  DevTarget T;
+  Schedule S;
+  int chains;
+  int proposals;          // B
+  long long thinning;
+  long long proposal_offset;
+  long long chain_offset;
+  unsigned long long seed;
+  double stepsize;
+  int randomize;
+  double* q;              // [C x d]
+  double* x;              // [C]
+  const double* z_in;     // [B x C x d] or null
+  const double* u_step_in;
+  const double* u_accept_in;
+  double* out_samples;
+  unsigned char* out_accept;
+  double* out_h0;
+  double* out_h1;
+  int* accepted_total;
+  double* out_q_prop;
+  double* out_p_prop;
+  double* trace_q;
+  double* trace_g;
+};
+
+// ------------------------------------------------------------------- priors only ---
+// Thread t of a chain owns coordinate pairs m = t + i*TPC (i < PPT): coordinates 2m, 2m+1.
+template <int TPC, int PPT>
+__global__ void __launch_bounds__((TPC < 256 ? 256 : TPC))
+hmc_fused_priors_kernel(const FusedArgs A) {
+  constexpr int BLOCK = TPC < 256 ? 256 : TPC;
+  constexpr int CPB = BLOCK / TPC;  // chains per block
+  constexpr int E = 2 * PPT;        // coordinates per thread
+  __shared__ double scratch[3 * ((TPC + 31) / 32) + 1];
+  const ChainReduce<TPC> red{scratch};
+  const DevTarget& T = A.T;
+  const int d = T.dims;
+
+  const int t = threadIdx.x % TPC;
+  int c = blockIdx.x * CPB + threadIdx.x / TPC;
+  const bool live = c < A.chains;
+  if (!live) c = A.chains - 1;  // keep the lanes converged; all writes are predicated
+  const size_t row = (size_t)c * d;
+  const size_t C = (size_t)A.chains;
+
+  int jj[E];
+  bool ok[E];
+  double qc[E], q[E], p[E];
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const int m = t + i * TPC;
+    jj[2 * i] = 2 * m; jj[2 * i + 1] = 2 * m + 1;
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    ok[e] = jj[e] < d;
+    qc[e] = ok[e] ? A.q[row + jj[e]] : 0.0;
+  }
+  double x = A.x[c];
+  int accepted = 0;
+  const bool grad_checks = T.grad_check_mask != 0u;
+
+  for (int kb = 0; kb < A.proposals; ++kb) {
+    const long long kglob = A.proposal_offset + kb;
+    const size_t kc = (size_t)kb * C + c;
+
+    // ---- draws -------------------------------------------------------------------
+    double u_step, u_acc;
+    uniform_pair(A.seed, (uint32_t)(A.chain_offset + c), (uint32_t)kglob, u_step, u_acc);
+    if (A.u_step_in) u_step = A.u_step_in[kc];
+    if (A.u_accept_in) u_acc = A.u_accept_in[kc];
+    const double eps = A.randomize ? __dmul_rn(u_step, A.stepsize) : A.stepsize;
+
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      double z0, z1;
+      if (A.z_in) {
+        const double* zr = A.z_in + kc * d;
+        z0 = ok[2 * i] ? zr[jj[2 * i]] : 0.0;
+        z1 = ok[2 * i + 1] ? zr[jj[2 * i + 1]] : 0.0;
+      } else {
+        normal_pair(A.seed, (uint32_t)(A.chain_offset + c), (uint32_t)kglob,
+                    (uint32_t)(t + i * TPC), z0, z1);
+      }
+      p[2 * i] = z0; p[2 * i + 1] = z1;
+    }
+    double k0 = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      q[e] = qc[e];
+      if (ok[e]) {
+        if (T.sqrtm) p[e] = __dmul_rn(__ldg(T.sqrtm + jj[e]), p[e]);
+        k0 = __dadd_rn(k0, kinetic_term(T, jj[e], p[e]));
+      } else {
+        p[e] = 0.0;
+      }
+    }
+
+    // ---- trajectory --------------------------------------------------------------
+    int gi = 0;
+    auto run_op = [&](const StageOp& op) {
+      if (op.has_b) {
+        unsigned oob = 0;
+        if (grad_checks) {
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            if (ok[e]) oob |= bound_violations(T, jj[e], q[e]);
+          oob = red.any_bits(oob);
+        }
+        const double cb = __dmul_rn(op.b, eps);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if (ok[e]) {
+            const double g = prior_gradient(T, jj[e], q[e], oob);
+            if (A.trace_q && live) {
+              const size_t o = (((size_t)kb * A.S.grads_per_proposal + gi) * C + c) * d + jj[e];
+              A.trace_q[o] = q[e];
+              A.trace_g[o] = g;
+            }
+            momentum_update(cb, g, p[e]);
+          }
+        }
+        ++gi;
+      }
+      const double ca = __dmul_rn(op.a, eps);
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (ok[e]) position_update(T, jj[e], ca, q[e], p[e]);
+    };
+    for (int s = 0; s < A.S.n_pre; ++s) run_op(A.S.pre[s]);
+    for (int r = 0; r < A.S.reps; ++r)
+      for (int s = 0; s < A.S.n_body; ++s) run_op(A.S.body[s]);
+    for (int s = 0; s < A.S.n_post; ++s) run_op(A.S.post[s]);
+
+    // ---- energies and decision ----------------------------------------------------
+    double k1 = 0.0, u1 = 0.0;
+    unsigned oob = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (ok[e]) {
+        k1 = __dadd_rn(k1, kinetic_term(T, jj[e], p[e]));
+        u1 = __dadd_rn(u1, prior_misfit(T, jj[e], q[e]));
+        oob |= bound_violations(T, jj[e], q[e]);
+      }
+    }
+    red.sum3(k0, k1, u1);
+    if (T.n_checks) oob = red.any_bits(oob);
+    double x1 = __dadd_rn(u1, T.const_sum);
+    if (oob) x1 = __dadd_rn(x1, CUDART_INF);
+    const double h0 = __dadd_rn(x, __dmul_rn(0.5, k0));
+    const double h1 = __dadd_rn(x1, __dmul_rn(0.5, k1));
+    const bool acc = metropolis_accept(h0, h1, u_acc);
+
+    if (live) {
+      if (A.out_q_prop) {
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if (ok[e]) {
+            A.out_q_prop[kc * d + jj[e]] = q[e];
+            A.out_p_prop[kc * d + jj[e]] = p[e];
+          }
+      }
+      if (t == 0) {
+        if (A.out_accept) A.out_accept[kc] = acc ? 1 : 0;
+        if (A.out_h0) A.out_h0[kc] = h0;
+        if (A.out_h1) A.out_h1[kc] = h1;
+      }
+    }
+    if (acc) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) qc[e] = q[e];
+      x = x1;
+      ++accepted;
+    }
+    if (A.out_samples && live && (kglob % A.thinning) == 0) {
+      const size_t srow = ((size_t)((kglob / A.thinning) - ((A.proposal_offset + A.thinning - 1) / A.thinning)) * C + c) *
+                          (size_t)(d + 1);
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (ok[e]) A.out_samples[srow + jj[e]] = qc[e];
+      if (t == 0) A.out_samples[srow + d] = x;
+    }
+  }
+
+  if (live) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (ok[e]) A.q[row + jj[e]] = qc[e];
+    if (t == 0) {
+      A.x[c] = x;
+      if (A.accepted_total) A.accepted_total[c] += accepted;
+    }
+  }
+}
+
+// Standalone batched misfit / gradient / reflection / mass-matrix kernels for the
+// single-vector protocol entry points (one thread per coordinate, block per chain-slab).
+template <int TPC>
+__global__ void __launch_bounds__((TPC < 256 ? 256 : TPC))
+prior_misfit_kernel(const DevTarget T, int chains, const double* __restrict__ q,
+                    double* __restrict__ x, const double* __restrict__ lik_misfit) {
+  constexpr int BLOCK = TPC < 256 ? 256 : TPC;
+  constexpr int CPB = BLOCK / TPC;
+  __shared__ double scratch[3 * ((TPC + 31) / 32) + 1];
+  const ChainReduce<TPC> red{scratch};
+  const int t = threadIdx.x % TPC;
+  int c = blockIdx.x * CPB + threadIdx.x / TPC;
+  const bool live = c < chains;
+  if (!live) c = chains - 1;
+  double u = 0.0, z0 = 0.0, z1 = 0.0;
+  unsigned oob = 0;
+  for (int j = t; j < T.dims; j += TPC) {
+    const double v = q[(size_t)c * T.dims + j];
+    u = __dadd_rn(u, prior_misfit(T, j, v));
+    oob |= bound_violations(T, j, v);
+  }
+  red.sum3(u, z0, z1);
+  oob = red.any_bits(oob);
+  if (live && t == 0) {
+    double r = __dadd_rn(u, T.const_sum);
+    if (lik_misfit) r = __dadd_rn(r, lik_misfit[c]);
+    if (oob) r = __dadd_rn(r, CUDART_INF);
+    x[c] = r;
+  }
+}
+
+template <int TPC>
+__global__ void __launch_bounds__((TPC < 256 ? 256 : TPC))
+prior_gradient_kernel(const DevTarget T, int chains, const double* __restrict__ q,
+                      double* __restrict__ g, int accumulate) {
+  constexpr int BLOCK = TPC < 256 ? 256 : TPC;
+  constexpr int CPB = BLOCK / TPC;
+  __shared__ double scratch[3 * ((TPC + 31) / 32) + 1];
+  const ChainReduce<TPC> red{scratch};
+  const int t = threadIdx.x % TPC;
+  int c = blockIdx.x * CPB + threadIdx.x / TPC;
+  const bool live = c < chains;
+  if (!live) c = chains - 1;
+  unsigned oob = 0;
+  if (T.grad_check_mask) {
+    for (int j = t; j < T.dims; j += TPC)
+      oob |= bound_violations(T, j, q[(size_t)c * T.dims + j]);
+    oob = red.any_bits(oob);
+  }
+  if (!live) return;
+  for (int j = t; j < T.dims; j += TPC) {
+    const size_t o = (size_t)c * T.dims + j;
+    const double pg = prior_gradient(T, j, q[o], oob);
+    g[o] = accumulate ? __dadd_rn(pg, g[o]) : pg;
+  }
+}
+
+#ifdef HMCB_FUSED_AUX_KERNELS
+__global__ void reflect_kernel(const DevTarget T, size_t total, double* __restrict__ q,
+                               double* __restrict__ p) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int j = (int)(i % T.dims);
+  double qq = q[i], pp = p[i];
+  reflect(T, j, qq, pp);
+  q[i] = qq; p[i] = pp;
+}
+
+// mode 0: p = sqrt(M) z ; mode 1: dK/dp
+__global__ void mass_elementwise_kernel(const DevTarget T, size_t total, int mode,
+                                        const double* __restrict__ in, double* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int j = (int)(i % T.dims);
+  const double v = in[i];
+  if (mode == 0) out[i] = T.sqrtm ? __dmul_rn(__ldg(T.sqrtm + j), v) : v;
+  else out[i] = kinetic_gradient(T, j, v);
+}
+#endif  // HMCB_FUSED_AUX_KERNELS
+
+template <int TPC>
+__global__ void __launch_bounds__((TPC < 256 ? 256 : TPC))
+kinetic_energy_kernel(const DevTarget T, int chains, const double* __restrict__ p,
+                      double* __restrict__ k) {
+  constexpr int BLOCK = TPC < 256 ? 256 : TPC;
+  constexpr int CPB = BLOCK / TPC;
+  __shared__ double scratch[3 * ((TPC + 31) / 32) + 1];
+  const ChainReduce<TPC> red{scratch};
+  const int t = threadIdx.x % TPC;
+  int c = blockIdx.x * CPB + threadIdx.x / TPC;
+  const bool live = c < chains;
+  if (!live) c = chains - 1;
+  double s = 0.0, z0 = 0.0, z1 = 0.0;
+  for (int j = t; j < T.dims; j += TPC)
+    s = __dadd_rn(s, kinetic_term(T, j, p[(size_t)c * T.dims + j]));
+  red.sum3(s, z0, z1);
+  if (live && t == 0) k[c] = __dmul_rn(0.5, s);
+}
+
+}  // namespace hmcb

@@ -1,0 +1,931 @@
+// hmcb.cu -- the C ABI of include/hmcb.h: engine object, target lowering to device
+// constants, path selection and the host-side orchestration of a block of proposals.
+//
+// No arithmetic of the hot path happens on the host: this file validates, uploads model
+// constants once, and enqueues kernels on the caller's stream.
+#include "../../include/hmcb.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "launch.cuh"
+
+using namespace hmcb;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(const std::string& msg) {
+  g_error = msg;
+  return -1;
+}
+
+#define HMCB_CUDA(expr)                                                                  \
+  do {                                                                                   \
+    cudaError_t err__ = (expr);                                                          \
+    if (err__ != cudaSuccess)                                                            \
+      return fail(std::string(#expr) + " failed: " + cudaGetErrorString(err__));         \
+  } while (0)
+
+#define HMCB_CHECK(cond, msg) \
+  do {                        \
+    if (!(cond)) return fail(msg); \
+  } while (0)
+
+enum LikKind { LK_NONE = 0, LK_DENSE_PREMULT, LK_DENSE_DIRECT, LK_CSR_DIRECT, LK_CSR_PREMULT, LK_SRCLOC };
+
+int round_up(int64_t v, int m) { return (int)((v + m - 1) / m * m); }
+
+struct HostPrior {
+  int kind;
+  int64_t offset, len;
+  std::vector<double> a, b;
+  double constant;
+};
+struct HostCheck {
+  int64_t offset, len;
+  bool has_lb, has_ub;
+  std::vector<double> lb, ub;
+  int in_gradient;
+};
+struct HostCsr {
+  int64_t rows = 0, cols = 0, nnz = 0;
+  std::vector<int32_t> indptr, indices;
+  std::vector<double> data;
+};
+
+}  // namespace
+
+struct hmcb_engine {
+  int device = 0;
+  int64_t C = 0, d = 0;
+  int integrator = HMCB_INTEGRATOR_LF;
+  int steps = 10;
+  bool mass_diag = false;
+  std::vector<double> h_diag, h_invdiag;
+  std::vector<HostPrior> priors;
+  std::vector<HostCheck> checks;
+  bool has_rlb = false, has_rub = false;
+  std::vector<double> rlb, rub;
+
+  int lik = LK_NONE;
+  int64_t N = 0;                       // data dimension (direct forms)
+  std::vector<double> h_A, h_At;       // dense: GtG or G ; Gt
+  bool has_At = false;
+  std::vector<double> h_vec, h_var, h_sigma;  // Gtd0 or d ; var ; sigma
+  double dtd = 0.0;
+  HostCsr csr, csr_t;
+  // srcloc
+  int64_t events = 0, stations = 0;
+  int infer_velocity = 0;
+  double velocity = 0.0;
+  std::vector<double> h_rx, h_ry, h_rz, h_tobs, h_std;
+
+  bool finalized = false;
+  int path = -1;
+  int64_t launches = 0;
+
+  // device state ---------------------------------------------------------------------
+  std::vector<void*> allocs;
+  DevTarget T{};
+  Schedule S{};
+  std::vector<StageOp> ops;  // flattened trajectory
+  SrcLocDev L{};
+  // staged path
+  int ld = 0, dpad = 0, npad = 0, jtiles = 0, ltiles = 0;
+  double *dA = nullptr, *dAt = nullptr, *dvec = nullptr, *dvar = nullptr, *dsigma = nullptr;
+  CsrDev csr_dev{}, csr_t_dev{};
+  double *q_cur = nullptr, *q_w[2] = {nullptr, nullptr}, *p_w = nullptr, *R = nullptr;
+  double *eps = nullptr, *uacc = nullptr, *k0part = nullptr, *k1part = nullptr, *upart = nullptr,
+         *lpart = nullptr;
+  unsigned* flags[3] = {nullptr, nullptr, nullptr};
+  unsigned char* accbuf = nullptr;
+  // hmcb_sample_host
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+};
+
+namespace {
+
+template <class Tv>
+int dev_alloc(hmcb_engine* e, size_t count, Tv** out, bool zero = true) {
+  void* p = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(Tv);
+  HMCB_CUDA(cudaMalloc(&p, bytes));
+  e->allocs.push_back(p);
+  if (zero) HMCB_CUDA(cudaMemset(p, 0, bytes));
+  *out = static_cast<Tv*>(p);
+  return 0;
+}
+
+template <class Tv>
+int dev_upload(hmcb_engine* e, const std::vector<Tv>& v, const Tv** out) {
+  Tv* p = nullptr;
+  if (dev_alloc(e, v.size(), &p, false)) return -1;
+  if (!v.empty()) HMCB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(Tv), cudaMemcpyHostToDevice));
+  *out = p;
+  return 0;
+}
+
+// rows x cols host matrix -> zero padded rows_pad x cols_pad device matrix
+int dev_upload_padded(hmcb_engine* e, const double* src, int64_t rows, int64_t cols, int64_t rows_pad,
+                      int64_t cols_pad, double** out) {
+  double* p = nullptr;
+  if (dev_alloc(e, (size_t)rows_pad * cols_pad, &p, true)) return -1;
+  HMCB_CUDA(cudaMemcpy2D(p, (size_t)cols_pad * sizeof(double), src, (size_t)cols * sizeof(double),
+                         (size_t)cols * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice));
+  *out = p;
+  return 0;
+}
+
+void free_device(hmcb_engine* e) {
+  for (void* p : e->allocs) cudaFree(p);
+  e->allocs.clear();
+  e->finalized = false;
+}
+
+int check_csr(const HostCsr& m, const char* what) {
+  HMCB_CHECK((int64_t)m.indptr.size() == m.rows + 1, std::string(what) + ": indptr size");
+  HMCB_CHECK(m.indptr[0] == 0 && m.indptr[m.rows] == m.nnz, std::string(what) + ": indptr range");
+  for (int64_t i = 0; i < m.rows; ++i)
+    HMCB_CHECK(m.indptr[i] <= m.indptr[i + 1], std::string(what) + ": indptr not monotone");
+  for (int64_t k = 0; k < m.nnz; ++k)
+    HMCB_CHECK(m.indices[k] >= 0 && m.indices[k] < m.cols, std::string(what) + ": column index out of range");
+  return 0;
+}
+
+void copy_vec(std::vector<double>& dst, const double* src, int64_t n) { dst.assign(src, src + n); }
+
+// Samplers.py:1524-1584 (lf), :1663-1726 (3s), :1586-1661 (4s); multipliers of eps.
+void build_schedule(hmcb_engine* e) {
+  Schedule& S = e->S;
+  std::memset(&S, 0, sizeof(S));
+  const int Lsteps = e->steps;
+  auto lone = [](double a) { return StageOp{0.0, a, 0, 0}; };
+  auto pair = [](double b, double a) { return StageOp{b, a, 1, 0}; };
+  if (e->integrator == HMCB_INTEGRATOR_LF) {
+    S.n_pre = 1; S.pre[0] = lone(0.5);
+    S.n_body = 1; S.body[0] = pair(1.0, 1.0); S.reps = Lsteps - 1;
+    S.n_post = 1; S.post[0] = pair(1.0, 0.5);
+    S.grads_per_proposal = Lsteps;
+  } else if (e->integrator == HMCB_INTEGRATOR_3S) {
+    const double a1 = 0.11888010966548, a2 = 1.0 / 2.0 - a1;
+    const double b1 = 0.29619504261126, b2 = 1.0 - 2.0 * b1;
+    S.n_body = 4; S.reps = Lsteps;
+    S.body[0] = lone(a1); S.body[1] = pair(b1, a2); S.body[2] = pair(b2, a2); S.body[3] = pair(b1, a1);
+    S.grads_per_proposal = 3 * Lsteps;
+  } else {
+    const double a1 = 0.071353913450279725904, a2 = 0.268548791161230105820;
+    const double a3 = 1.0 - 2.0 * a1 - 2.0 * a2;
+    const double b1 = 0.1916678, b2 = 1.0 / 2.0 - b1;
+    S.n_body = 5; S.reps = Lsteps;
+    S.body[0] = lone(a1); S.body[1] = pair(b1, a2); S.body[2] = pair(b2, a3);
+    S.body[3] = pair(b2, a2); S.body[4] = pair(b1, a1);
+    S.grads_per_proposal = 4 * Lsteps;
+  }
+  e->ops.clear();
+  for (int s = 0; s < S.n_pre; ++s) e->ops.push_back(S.pre[s]);
+  for (int r = 0; r < S.reps; ++r)
+    for (int s = 0; s < S.n_body; ++s) e->ops.push_back(S.body[s]);
+  for (int s = 0; s < S.n_post; ++s) e->ops.push_back(S.post[s]);
+}
+
+int upload_csr(hmcb_engine* e, const HostCsr& m, CsrDev* out) {
+  const int32_t *ip = nullptr, *ix = nullptr;
+  const double* dv = nullptr;
+  if (dev_upload(e, m.indptr, &ip) || dev_upload(e, m.indices, &ix) || dev_upload(e, m.data, &dv)) return -1;
+  out->indptr = ip; out->indices = ix; out->data = dv;
+  out->rows = (int)m.rows;
+  out->rows_per_chunk = 64;
+  out->chunks = (int)((m.rows + 63) / 64);
+  return 0;
+}
+
+StagedCommon staged_common(const hmcb_engine* e, const hmcb_block* b) {
+  StagedCommon S{};
+  S.T = e->T; S.C = (int)e->C; S.ld = e->ld; S.jtiles = e->jtiles;
+  if (b) {
+    S.chain_offset = b->chain_offset; S.seed = b->seed; S.stepsize = b->stepsize;
+    S.randomize = b->randomize_stepsize;
+  }
+  return S;
+}
+
+inline int staged_lik_mode(const hmcb_engine* e) {
+  switch (e->lik) {
+    case LK_DENSE_PREMULT: case LK_CSR_PREMULT: return LIK_PREMULT;
+    case LK_DENSE_DIRECT: case LK_CSR_DIRECT: return LIK_DIRECT;
+    default: return LIK_NONE;
+  }
+}
+
+// total gradient at q_in fused with the update described by `epi` (q_in -> epi.q_out)
+int staged_gradient_pass(hmcb_engine* e, const double* q_in, UpdateEpi epi, cudaStream_t s) {
+  epi.q_in = q_in;
+  switch (e->lik) {
+    case LK_NONE: {
+      HMCB_CUDA(launch_st_update(staged_common(e, nullptr), epi, s));
+      e->launches += 1;
+      break;
+    }
+    case LK_DENSE_PREMULT: {
+      epi.sub = e->dvec;
+      HMCB_CUDA(launch_gemm_update(e->dA, e->dpad, e->dpad, q_in, e->ld, e->dpad, epi, s));
+      e->launches += 1;
+      break;
+    }
+    case LK_DENSE_DIRECT: {
+      ResidualEpi r{(int)e->N, (int)e->C, e->ld, e->dvec, e->dvar, e->R};
+      HMCB_CUDA(launch_gemm_residual(e->dA, e->dpad, e->npad, q_in, e->ld, e->dpad, r, s));
+      epi.sub = nullptr;
+      HMCB_CUDA(launch_gemm_update(e->dAt, e->npad, e->dpad, e->R, e->ld, e->npad, epi, s));
+      e->launches += 2;
+      break;
+    }
+    case LK_CSR_DIRECT: {
+      ResidualEpi r{(int)e->N, (int)e->C, e->ld, e->dvec, e->dvar, e->R};
+      HMCB_CUDA(launch_spmm_residual(e->csr_dev, q_in, e->ld, r, s));
+      epi.sub = nullptr;
+      HMCB_CUDA(launch_spmm_update(e->csr_t_dev, e->R, e->ld, epi, s));
+      e->launches += 2;
+      break;
+    }
+    case LK_CSR_PREMULT: {
+      epi.sub = e->dvec;
+      HMCB_CUDA(launch_spmm_update(e->csr_dev, q_in, e->ld, epi, s));
+      e->launches += 1;
+      break;
+    }
+    default: return fail("internal: bad likelihood kind on the staged path");
+  }
+  return 0;
+}
+
+// per-chain partial sums of the likelihood misfit at q -> lpart
+int staged_misfit_pass(hmcb_engine* e, const double* q, cudaStream_t s) {
+  MisfitEpi m{};
+  m.mode = staged_lik_mode(e); m.C = (int)e->C; m.ld = e->ld; m.q = q; m.part = e->lpart;
+  switch (e->lik) {
+    case LK_NONE: return 0;
+    case LK_DENSE_PREMULT:
+      m.rows = (int)e->d; m.vec = e->dvec;
+      HMCB_CUDA(launch_gemm_misfit(e->dA, e->dpad, e->dpad, q, e->ld, e->dpad, m, s));
+      break;
+    case LK_DENSE_DIRECT:
+      m.rows = (int)e->N; m.vec = e->dvec; m.sigma = e->dsigma;
+      HMCB_CUDA(launch_gemm_misfit(e->dA, e->dpad, e->npad, q, e->ld, e->dpad, m, s));
+      break;
+    case LK_CSR_DIRECT:
+      m.rows = (int)e->N; m.vec = e->dvec; m.sigma = e->dsigma;
+      HMCB_CUDA(launch_spmm_misfit(e->csr_dev, q, e->ld, m, s));
+      break;
+    case LK_CSR_PREMULT:
+      m.rows = (int)e->d; m.vec = e->dvec;
+      HMCB_CUDA(launch_spmm_misfit(e->csr_dev, q, e->ld, m, s));
+      break;
+    default: return fail("internal: bad likelihood kind on the staged path");
+  }
+  e->launches += 1;
+  return 0;
+}
+
+DecideArgs decide_args(const hmcb_engine* e) {
+  DecideArgs D{};
+  D.C = (int)e->C; D.ld = e->ld; D.jtiles = e->jtiles; D.ltiles = e->ltiles;
+  D.lik_mode = staged_lik_mode(e);
+  D.dtd = e->dtd; D.const_sum = e->T.const_sum;
+  D.k0part = e->k0part; D.k1part = e->k1part; D.upart = e->upart; D.lpart = e->lpart;
+  D.uacc = e->uacc; D.acc = e->accbuf;
+  return D;
+}
+
+int staged_run_block(hmcb_engine* e, const hmcb_block* b, cudaStream_t s) {
+  const int C = (int)e->C, d = (int)e->d, ld = e->ld;
+  const bool grad_checks = e->T.grad_check_mask != 0u;
+  const bool any_checks = e->T.n_checks > 0;
+  const size_t flag_bytes = (size_t)ld * sizeof(unsigned);
+  const int G = e->S.grads_per_proposal;
+  StagedCommon SC = staged_common(e, b);
+
+  // chain-major API tensor -> transposed working layout
+  HMCB_CUDA(launch_st_transpose(b->q, C, d, d, e->q_cur, ld, s));
+  e->launches += 1;
+
+  const int64_t first_row = (b->proposal_offset + b->thinning - 1) / b->thinning;
+  for (int64_t kb = 0; kb < b->proposals; ++kb) {
+    const int64_t kglob = b->proposal_offset + kb;
+    const size_t kc = (size_t)kb * C;
+    int cur = 0, fcur = 0;
+    if (grad_checks) HMCB_CUDA(cudaMemsetAsync(e->flags[fcur], 0, flag_bytes, s));
+    HMCB_CUDA(launch_st_begin(SC, kglob, e->ops[0].a, e->q_cur, e->q_w[cur], e->p_w,
+                              b->z_in ? b->z_in + kc * d : nullptr,
+                              b->u_step_in ? b->u_step_in + kc : nullptr,
+                              b->u_accept_in ? b->u_accept_in + kc : nullptr, e->eps, e->uacc,
+                              e->k0part, grad_checks ? e->flags[fcur] : nullptr, s));
+    e->launches += 1;
+    int gi = 0;
+    for (size_t o = 1; o < e->ops.size(); ++o) {
+      const StageOp& op = e->ops[o];
+      if (op.has_b) {
+        UpdateEpi epi{};
+        epi.T = e->T; epi.C = C; epi.ld = ld;
+        epi.q_out = e->q_w[cur ^ 1]; epi.p = e->p_w; epi.eps = e->eps;
+        epi.b_mult = op.b; epi.a_mult = op.a;
+        if (grad_checks) {
+          HMCB_CUDA(cudaMemsetAsync(e->flags[fcur ^ 1], 0, flag_bytes, s));
+          epi.flags_in = e->flags[fcur];
+          epi.flags_out = e->flags[fcur ^ 1];
+        }
+        if (b->trace_q) {
+          const size_t off = (((size_t)kb * G + gi) * C) * d;
+          epi.trace_q = b->trace_q + off;
+          epi.trace_g = b->trace_g + off;
+        }
+        if (staged_gradient_pass(e, e->q_w[cur], epi, s)) return -1;
+        cur ^= 1; fcur ^= 1; ++gi;
+      } else {
+        if (grad_checks) HMCB_CUDA(cudaMemsetAsync(e->flags[fcur], 0, flag_bytes, s));
+        HMCB_CUDA(launch_st_position(SC, op.a, e->q_w[cur], e->p_w, e->eps,
+                                     grad_checks ? e->flags[fcur] : nullptr, s));
+        e->launches += 1;
+      }
+    }
+    // energies, decision, state update
+    if (any_checks) HMCB_CUDA(cudaMemsetAsync(e->flags[2], 0, flag_bytes, s));
+    HMCB_CUDA(launch_st_energy(SC, e->q_w[cur], e->p_w, e->k1part, e->upart,
+                               any_checks ? e->flags[2] : nullptr, s));
+    e->launches += 1;
+    if (staged_misfit_pass(e, e->q_w[cur], s)) return -1;
+    DecideArgs D = decide_args(e);
+    D.flags = any_checks ? e->flags[2] : nullptr;
+    D.x = b->x;
+    D.out_accept = b->out_accept ? b->out_accept + kc : nullptr;
+    D.out_h0 = b->out_h0 ? b->out_h0 + kc : nullptr;
+    D.out_h1 = b->out_h1 ? b->out_h1 + kc : nullptr;
+    D.accepted_total = b->accepted_total;
+    double* sample_rows = nullptr;
+    if (b->out_samples && (kglob % b->thinning) == 0) {
+      sample_rows = b->out_samples + (size_t)(kglob / b->thinning - first_row) * C * (size_t)(d + 1);
+      D.sample_misfit = sample_rows + d;
+      D.sample_stride = d + 1;
+    }
+    HMCB_CUDA(launch_st_decide(D, s));
+    HMCB_CUDA(launch_st_commit(C, d, ld, e->accbuf, e->q_w[cur], e->p_w, e->q_cur, sample_rows,
+                               b->out_q_prop ? b->out_q_prop + kc * d : nullptr,
+                               b->out_p_prop ? b->out_p_prop + kc * d : nullptr, s));
+    e->launches += 2;
+  }
+  HMCB_CUDA(launch_st_transpose(e->q_cur, d, C, ld, b->q, d, s));
+  e->launches += 1;
+  return 0;
+}
+
+FusedArgs fused_args(const hmcb_engine* e, const hmcb_block* b) {
+  FusedArgs A{};
+  A.T = e->T; A.S = e->S; A.chains = (int)e->C; A.proposals = (int)b->proposals;
+  A.thinning = b->thinning; A.proposal_offset = b->proposal_offset; A.chain_offset = b->chain_offset;
+  A.seed = b->seed; A.stepsize = b->stepsize; A.randomize = b->randomize_stepsize;
+  A.q = b->q; A.x = b->x; A.z_in = b->z_in; A.u_step_in = b->u_step_in; A.u_accept_in = b->u_accept_in;
+  A.out_samples = b->out_samples; A.out_accept = b->out_accept; A.out_h0 = b->out_h0; A.out_h1 = b->out_h1;
+  A.accepted_total = b->accepted_total; A.out_q_prop = b->out_q_prop; A.out_p_prop = b->out_p_prop;
+  A.trace_q = b->trace_q; A.trace_g = b->trace_g;
+  return A;
+}
+
+}  // namespace
+
+// ========================================================================== C ABI =====
+
+extern "C" {
+
+int hmcb_abi_version(void) { return HMCB_ABI_VERSION; }
+const char* hmcb_last_error(void) { return g_error.c_str(); }
+
+int hmcb_create(int device, int64_t chains, int64_t dims, hmcb_engine** out) {
+  HMCB_CHECK(out != nullptr, "hmcb_create: out is NULL");
+  *out = nullptr;
+  HMCB_CHECK(chains > 0 && chains < (1ll << 30), "hmcb_create: chains must be in [1, 2^30)");
+  HMCB_CHECK(dims > 0 && dims < (1ll << 24), "hmcb_create: dims must be in [1, 2^24)");
+  int count = 0;
+  HMCB_CUDA(cudaGetDeviceCount(&count));
+  HMCB_CHECK(device >= 0 && device < count, "hmcb_create: no such CUDA device");
+  cudaDeviceProp prop;
+  HMCB_CUDA(cudaGetDeviceProperties(&prop, device));
+  HMCB_CHECK(prop.major == 10,
+             std::string("hmcb_create: kernels are built for sm_100a (B200) only; device is ") + prop.name);
+  HMCB_CUDA(cudaSetDevice(device));
+  hmcb_engine* e = new hmcb_engine();
+  e->device = device; e->C = chains; e->d = dims;
+  *out = e;
+  return 0;
+}
+
+int hmcb_destroy(hmcb_engine* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  free_device(e);
+  if (e->s_compute) cudaStreamDestroy(e->s_compute);
+  if (e->s_copy) cudaStreamDestroy(e->s_copy);
+  delete e;
+  return 0;
+}
+
+int hmcb_set_integrator(hmcb_engine* e, int integrator, int amount_of_steps) {
+  HMCB_CHECK(e, "engine is NULL");
+  HMCB_CHECK(integrator >= HMCB_INTEGRATOR_LF && integrator <= HMCB_INTEGRATOR_4S,
+             "Unknown integrator used. Choices are: lf, 3s, 4s");
+  HMCB_CHECK(amount_of_steps > 0, "amount_of_steps must be a positive integer");
+  e->integrator = integrator; e->steps = amount_of_steps;
+  build_schedule(e);  // cheap; lets the integrator change after finalize
+  return 0;
+}
+
+int hmcb_set_mass_unit(hmcb_engine* e) {
+  HMCB_CHECK(e, "engine is NULL");
+  HMCB_CHECK(!e->finalized, "mass matrix must be set before hmcb_finalize");
+  e->mass_diag = false;
+  return 0;
+}
+
+int hmcb_set_mass_diagonal(hmcb_engine* e, const double* diagonal, const double* inverse_diagonal) {
+  HMCB_CHECK(e && diagonal && inverse_diagonal, "hmcb_set_mass_diagonal: NULL argument");
+  HMCB_CHECK(!e->finalized, "mass matrix must be set before hmcb_finalize");
+  for (int64_t j = 0; j < e->d; ++j)
+    HMCB_CHECK(diagonal[j] > 0.0, "hmcb_set_mass_diagonal: diagonal entries must be positive");
+  copy_vec(e->h_diag, diagonal, e->d);
+  copy_vec(e->h_invdiag, inverse_diagonal, e->d);
+  e->mass_diag = true;
+  return 0;
+}
+
+int hmcb_clear_target(hmcb_engine* e) {
+  HMCB_CHECK(e, "engine is NULL");
+  cudaSetDevice(e->device);
+  free_device(e);
+  e->priors.clear(); e->checks.clear();
+  e->has_rlb = e->has_rub = false;
+  e->lik = LK_NONE;
+  e->h_A.clear(); e->h_At.clear(); e->h_vec.clear(); e->h_var.clear(); e->h_sigma.clear();
+  e->csr = HostCsr(); e->csr_t = HostCsr();
+  return 0;
+}
+
+int hmcb_add_prior(hmcb_engine* e, int kind, int64_t offset, int64_t len, const double* a,
+                   const double* b, double constant) {
+  HMCB_CHECK(e && a && b, "hmcb_add_prior: NULL argument");
+  HMCB_CHECK(!e->finalized, "target must be described before hmcb_finalize");
+  HMCB_CHECK(kind == HMCB_PRIOR_NORMAL || kind == HMCB_PRIOR_LAPLACE, "hmcb_add_prior: unknown kind");
+  HMCB_CHECK(offset >= 0 && len > 0 && offset + len <= e->d, "hmcb_add_prior: range outside [0, dims)");
+  HMCB_CHECK((int)e->priors.size() < HMCB_MAX_PRIORS, "hmcb_add_prior: too many prior terms (max 8)");
+  HostPrior p;
+  p.kind = kind; p.offset = offset; p.len = len; p.constant = constant;
+  copy_vec(p.a, a, len); copy_vec(p.b, b, len);
+  e->priors.push_back(std::move(p));
+  return 0;
+}
+
+int hmcb_add_bound_check(hmcb_engine* e, int64_t offset, int64_t len, const double* lb,
+                         const double* ub, int in_gradient) {
+  HMCB_CHECK(e, "engine is NULL");
+  HMCB_CHECK(!e->finalized, "target must be described before hmcb_finalize");
+  HMCB_CHECK(offset >= 0 && len > 0 && offset + len <= e->d, "hmcb_add_bound_check: range outside [0, dims)");
+  if (!lb && !ub) return 0;
+  HMCB_CHECK((int)e->checks.size() < HMCB_MAX_CHECKS, "hmcb_add_bound_check: too many bound checks (max 8)");
+  HostCheck c;
+  c.offset = offset; c.len = len; c.has_lb = lb != nullptr; c.has_ub = ub != nullptr;
+  c.in_gradient = in_gradient ? 1 : 0;
+  if (lb) copy_vec(c.lb, lb, len);
+  if (ub) copy_vec(c.ub, ub, len);
+  e->checks.push_back(std::move(c));
+  return 0;
+}
+
+int hmcb_set_reflection(hmcb_engine* e, const double* lb, const double* ub) {
+  HMCB_CHECK(e, "engine is NULL");
+  HMCB_CHECK(!e->finalized, "target must be described before hmcb_finalize");
+  e->has_rlb = lb != nullptr; e->has_rub = ub != nullptr;
+  if (lb) copy_vec(e->rlb, lb, e->d);
+  if (ub) copy_vec(e->rub, ub, e->d);
+  return 0;
+}
+
+int hmcb_set_likelihood_dense_premult(hmcb_engine* e, const double* GtG, const double* Gtd0, double dtd) {
+  HMCB_CHECK(e && GtG && Gtd0, "hmcb_set_likelihood_dense_premult: NULL argument");
+  HMCB_CHECK(!e->finalized && e->lik == LK_NONE, "one likelihood per engine, set before hmcb_finalize");
+  copy_vec(e->h_A, GtG, e->d * e->d);
+  copy_vec(e->h_vec, Gtd0, e->d);
+  e->dtd = dtd;
+  e->lik = LK_DENSE_PREMULT;
+  return 0;
+}
+
+int hmcb_set_likelihood_dense_direct(hmcb_engine* e, int64_t N, const double* G, const double* Gt,
+                                     const double* d, const double* var, const double* sigma) {
+  HMCB_CHECK(e && G && d && var && sigma, "hmcb_set_likelihood_dense_direct: NULL argument");
+  HMCB_CHECK(!e->finalized && e->lik == LK_NONE, "one likelihood per engine, set before hmcb_finalize");
+  HMCB_CHECK(N > 0 && N < (1ll << 24), "hmcb_set_likelihood_dense_direct: bad N");
+  e->N = N;
+  copy_vec(e->h_A, G, N * e->d);
+  e->h_At.resize((size_t)N * e->d);
+  if (Gt) {
+    std::memcpy(e->h_At.data(), Gt, sizeof(double) * (size_t)N * e->d);
+  } else {
+    for (int64_t i = 0; i < N; ++i)
+      for (int64_t j = 0; j < e->d; ++j) e->h_At[(size_t)j * N + i] = G[(size_t)i * e->d + j];
+  }
+  copy_vec(e->h_vec, d, N); copy_vec(e->h_var, var, N); copy_vec(e->h_sigma, sigma, N);
+  e->lik = LK_DENSE_DIRECT;
+  return 0;
+}
+
+static int fill_csr(HostCsr& m, int64_t rows, int64_t cols, int64_t nnz, const int32_t* indptr,
+                    const int32_t* indices, const double* data, const char* what) {
+  m.rows = rows; m.cols = cols; m.nnz = nnz;
+  m.indptr.assign(indptr, indptr + rows + 1);
+  m.indices.assign(indices, indices + nnz);
+  m.data.assign(data, data + nnz);
+  return check_csr(m, what);
+}
+
+int hmcb_set_likelihood_csr_direct(hmcb_engine* e, int64_t N, int64_t nnz, const int32_t* indptr,
+                                   const int32_t* indices, const double* data, const int32_t* t_indptr,
+                                   const int32_t* t_indices, const double* t_data, const double* d,
+                                   const double* var, const double* sigma) {
+  HMCB_CHECK(e && indptr && t_indptr && d && var && sigma, "hmcb_set_likelihood_csr_direct: NULL argument");
+  HMCB_CHECK(nnz == 0 || (indices && data && t_indices && t_data), "hmcb_set_likelihood_csr_direct: NULL argument");
+  HMCB_CHECK(!e->finalized && e->lik == LK_NONE, "one likelihood per engine, set before hmcb_finalize");
+  HMCB_CHECK(N > 0 && N < (1ll << 30) && nnz >= 0 && nnz < (1ll << 31), "hmcb_set_likelihood_csr_direct: bad sizes");
+  if (fill_csr(e->csr, N, e->d, nnz, indptr, indices, data, "G")) return -1;
+  if (fill_csr(e->csr_t, e->d, N, nnz, t_indptr, t_indices, t_data, "G^T")) return -1;
+  e->N = N;
+  copy_vec(e->h_vec, d, N); copy_vec(e->h_var, var, N); copy_vec(e->h_sigma, sigma, N);
+  e->lik = LK_CSR_DIRECT;
+  return 0;
+}
+
+int hmcb_set_likelihood_csr_premult(hmcb_engine* e, int64_t nnz, const int32_t* indptr,
+                                    const int32_t* indices, const double* data, const double* Gtd0,
+                                    double dtd) {
+  HMCB_CHECK(e && indptr && Gtd0, "hmcb_set_likelihood_csr_premult: NULL argument");
+  HMCB_CHECK(nnz == 0 || (indices && data), "hmcb_set_likelihood_csr_premult: NULL argument");
+  HMCB_CHECK(!e->finalized && e->lik == LK_NONE, "one likelihood per engine, set before hmcb_finalize");
+  HMCB_CHECK(nnz >= 0 && nnz < (1ll << 31), "hmcb_set_likelihood_csr_premult: bad nnz");
+  if (fill_csr(e->csr, e->d, e->d, nnz, indptr, indices, data, "GtG")) return -1;
+  copy_vec(e->h_vec, Gtd0, e->d);
+  e->dtd = dtd;
+  e->lik = LK_CSR_PREMULT;
+  return 0;
+}
+
+int hmcb_set_likelihood_srcloc3d(hmcb_engine* e, int64_t events, int64_t stations, const double* rx,
+                                 const double* ry, const double* rz, const double* tobs,
+                                 const double* std, int infer_velocity, double velocity) {
+  HMCB_CHECK(e && rx && ry && rz && tobs && std, "hmcb_set_likelihood_srcloc3d: NULL argument");
+  HMCB_CHECK(!e->finalized && e->lik == LK_NONE, "one likelihood per engine, set before hmcb_finalize");
+  HMCB_CHECK(events > 0 && stations > 0, "hmcb_set_likelihood_srcloc3d: bad sizes");
+  HMCB_CHECK(e->d == 4 * events + (infer_velocity ? 1 : 0),
+             "hmcb_set_likelihood_srcloc3d: dims must be 4*events (+1 when the velocity is inferred)");
+  HMCB_CHECK(srcloc_supported((int)events, (int)stations),
+             "hmcb_set_likelihood_srcloc3d: events x stations exceeds the kernel's shared-memory staging");
+  e->events = events; e->stations = stations; e->infer_velocity = infer_velocity ? 1 : 0;
+  e->velocity = velocity;
+  copy_vec(e->h_rx, rx, stations); copy_vec(e->h_ry, ry, stations); copy_vec(e->h_rz, rz, stations);
+  copy_vec(e->h_tobs, tobs, events * stations); copy_vec(e->h_std, std, events * stations);
+  e->lik = LK_SRCLOC;
+  return 0;
+}
+
+int hmcb_finalize(hmcb_engine* e) {
+  HMCB_CHECK(e, "engine is NULL");
+  HMCB_CHECK(!e->finalized, "hmcb_finalize called twice (use hmcb_clear_target to start over)");
+  HMCB_CUDA(cudaSetDevice(e->device));
+  const int d = (int)e->d;
+  build_schedule(e);
+
+  DevTarget& T = e->T;
+  std::memset(&T, 0, sizeof(T));
+  T.dims = d;
+  T.n_priors = (int)e->priors.size();
+  T.n_checks = (int)e->checks.size();
+  double const_sum = 0.0;
+  for (int t = 0; t < T.n_priors; ++t) {
+    const HostPrior& P = e->priors[t];
+    T.prior[t].kind = P.kind; T.prior[t].offset = (int)P.offset; T.prior[t].len = (int)P.len;
+    if (dev_upload(e, P.a, &T.prior[t].a) || dev_upload(e, P.b, &T.prior[t].b)) return -1;
+    const_sum += P.constant;
+  }
+  T.const_sum = const_sum;
+  for (int k = 0; k < T.n_checks; ++k) {
+    const HostCheck& Ck = e->checks[k];
+    T.check[k].offset = (int)Ck.offset; T.check[k].len = (int)Ck.len; T.check[k].in_gradient = Ck.in_gradient;
+    if (Ck.has_lb && dev_upload(e, Ck.lb, &T.check[k].lb)) return -1;
+    if (Ck.has_ub && dev_upload(e, Ck.ub, &T.check[k].ub)) return -1;
+    if (Ck.in_gradient) T.grad_check_mask |= (1u << k);
+  }
+  if (e->has_rlb && dev_upload(e, e->rlb, &T.refl_lb)) return -1;
+  if (e->has_rub && dev_upload(e, e->rub, &T.refl_ub)) return -1;
+  if (e->mass_diag) {
+    std::vector<double> sq(e->h_diag.size());
+    for (size_t j = 0; j < sq.size(); ++j) sq[j] = std::sqrt(e->h_diag[j]);  // MassMatrices.py:226
+    if (dev_upload(e, e->h_invdiag, &T.invm) || dev_upload(e, sq, &T.sqrtm)) return -1;
+  }
+
+  // ---- path ------------------------------------------------------------------------
+  if (e->lik == LK_SRCLOC) {
+    e->path = HMCB_PATH_FUSED_SRCLOC;
+    SrcLocDev& L = e->L;
+    L.events = (int)e->events; L.stations = (int)e->stations; L.infer_velocity = e->infer_velocity;
+    L.velocity = e->velocity;
+    if (dev_upload(e, e->h_rx, &L.rx) || dev_upload(e, e->h_ry, &L.ry) || dev_upload(e, e->h_rz, &L.rz) ||
+        dev_upload(e, e->h_tobs, &L.tobs) || dev_upload(e, e->h_std, &L.std))
+      return -1;
+  } else if (e->lik == LK_NONE && fused_priors_supported(d) && !std::getenv("HMCB_FORCE_STAGED")) {
+    e->path = HMCB_PATH_FUSED_PRIORS;
+  } else {
+    e->path = HMCB_PATH_STAGED;
+    HMCB_CUDA(staged_init());
+    const int C = (int)e->C;
+    e->ld = round_up(C, 128);
+    e->dpad = round_up(d, 128);
+    e->npad = e->N ? round_up(e->N, 128) : 0;
+    e->jtiles = (d + ST_DT - 1) / ST_DT;
+    const size_t plane = (size_t)e->dpad * e->ld;
+    if (dev_alloc(e, plane, &e->q_cur) || dev_alloc(e, plane, &e->q_w[0]) || dev_alloc(e, plane, &e->q_w[1]) ||
+        dev_alloc(e, plane, &e->p_w))
+      return -1;
+    if (dev_alloc(e, (size_t)e->ld, &e->eps) || dev_alloc(e, (size_t)e->ld, &e->uacc) ||
+        dev_alloc(e, (size_t)e->ld, &e->accbuf))
+      return -1;
+    for (int f = 0; f < 3; ++f)
+      if (dev_alloc(e, (size_t)e->ld, &e->flags[f])) return -1;
+    const size_t parts = (size_t)e->jtiles * e->ld;
+    if (dev_alloc(e, parts, &e->k0part) || dev_alloc(e, parts, &e->k1part) || dev_alloc(e, parts, &e->upart))
+      return -1;
+    const double* tmp = nullptr;
+    switch (e->lik) {
+      case LK_NONE: e->ltiles = 0; break;
+      case LK_DENSE_PREMULT:
+        if (dev_upload_padded(e, e->h_A.data(), d, d, e->dpad, e->dpad, &e->dA)) return -1;
+        if (dev_upload(e, e->h_vec, &tmp)) return -1;
+        e->dvec = const_cast<double*>(tmp);
+        e->ltiles = e->dpad / GEMM_BM;
+        break;
+      case LK_DENSE_DIRECT:
+        if (dev_upload_padded(e, e->h_A.data(), e->N, d, e->npad, e->dpad, &e->dA)) return -1;
+        if (dev_upload_padded(e, e->h_At.data(), d, e->N, e->dpad, e->npad, &e->dAt)) return -1;
+        e->ltiles = e->npad / GEMM_BM;
+        break;
+      case LK_CSR_DIRECT:
+        if (upload_csr(e, e->csr, &e->csr_dev) || upload_csr(e, e->csr_t, &e->csr_t_dev)) return -1;
+        e->ltiles = e->csr_dev.chunks;
+        break;
+      case LK_CSR_PREMULT:
+        if (upload_csr(e, e->csr, &e->csr_dev)) return -1;
+        if (dev_upload(e, e->h_vec, &tmp)) return -1;
+        e->dvec = const_cast<double*>(tmp);
+        e->ltiles = e->csr_dev.chunks;
+        break;
+      default: return fail("internal: bad likelihood kind");
+    }
+    if (e->lik == LK_DENSE_DIRECT || e->lik == LK_CSR_DIRECT) {
+      const double *dv = nullptr, *vv = nullptr, *sv = nullptr;
+      if (dev_upload(e, e->h_vec, &dv) || dev_upload(e, e->h_var, &vv) || dev_upload(e, e->h_sigma, &sv)) return -1;
+      e->dvec = const_cast<double*>(dv); e->dvar = const_cast<double*>(vv); e->dsigma = const_cast<double*>(sv);
+      if (dev_alloc(e, (size_t)e->npad * e->ld, &e->R)) return -1;
+    }
+    if (e->ltiles && dev_alloc(e, (size_t)e->ltiles * e->ld, &e->lpart)) return -1;
+    // the host copies of the big operands are no longer needed
+    std::vector<double>().swap(e->h_A);
+    std::vector<double>().swap(e->h_At);
+  }
+  HMCB_CUDA(cudaDeviceSynchronize());
+  e->finalized = true;
+  return 0;
+}
+
+int hmcb_path(const hmcb_engine* e) { return e ? e->path : -1; }
+int64_t hmcb_grads_per_proposal(const hmcb_engine* e) { return e ? e->S.grads_per_proposal : -1; }
+int64_t hmcb_launch_count(const hmcb_engine* e) { return e ? e->launches : -1; }
+
+#define HMCB_READY(e)                                                      \
+  HMCB_CHECK((e) != nullptr, "engine is NULL");                            \
+  HMCB_CHECK((e)->finalized, "engine is not finalized (call hmcb_finalize)"); \
+  HMCB_CUDA(cudaSetDevice((e)->device))
+
+int hmcb_misfit(hmcb_engine* e, const double* q, double* x, void* stream) {
+  HMCB_READY(e);
+  HMCB_CHECK(q && x, "hmcb_misfit: NULL argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int C = (int)e->C, d = (int)e->d;
+  if (e->path == HMCB_PATH_FUSED_PRIORS) {
+    HMCB_CUDA(launch_prior_misfit(e->T, C, q, x, nullptr, s));
+    e->launches += 1;
+  } else if (e->path == HMCB_PATH_FUSED_SRCLOC) {
+    HMCB_CUDA(launch_srcloc_eval(e->T, e->L, C, 0, q, x, s));
+    e->launches += 1;
+  } else {
+    const bool any_checks = e->T.n_checks > 0;
+    HMCB_CUDA(launch_st_transpose(q, C, d, d, e->q_w[0], e->ld, s));
+    if (any_checks) HMCB_CUDA(cudaMemsetAsync(e->flags[2], 0, (size_t)e->ld * sizeof(unsigned), s));
+    HMCB_CUDA(launch_st_energy(staged_common(e, nullptr), e->q_w[0], nullptr, nullptr, e->upart,
+                               any_checks ? e->flags[2] : nullptr, s));
+    e->launches += 2;
+    if (staged_misfit_pass(e, e->q_w[0], s)) return -1;
+    DecideArgs D = decide_args(e);
+    D.flags = any_checks ? e->flags[2] : nullptr;
+    D.x = x; D.misfit_only = 1;
+    HMCB_CUDA(launch_st_decide(D, s));
+    e->launches += 1;
+  }
+  return 0;
+}
+
+int hmcb_gradient(hmcb_engine* e, const double* q, double* g, void* stream) {
+  HMCB_READY(e);
+  HMCB_CHECK(q && g, "hmcb_gradient: NULL argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int C = (int)e->C, d = (int)e->d;
+  if (e->path == HMCB_PATH_FUSED_PRIORS) {
+    HMCB_CUDA(launch_prior_gradient(e->T, C, q, g, 0, s));
+    e->launches += 1;
+  } else if (e->path == HMCB_PATH_FUSED_SRCLOC) {
+    HMCB_CUDA(launch_srcloc_eval(e->T, e->L, C, 1, q, g, s));
+    e->launches += 1;
+  } else {
+    const bool grad_checks = e->T.grad_check_mask != 0u;
+    HMCB_CUDA(launch_st_transpose(q, C, d, d, e->q_w[0], e->ld, s));
+    e->launches += 1;
+    if (grad_checks) {
+      HMCB_CUDA(cudaMemsetAsync(e->flags[2], 0, (size_t)e->ld * sizeof(unsigned), s));
+      HMCB_CUDA(launch_st_energy(staged_common(e, nullptr), e->q_w[0], nullptr, nullptr, e->upart,
+                                 e->flags[2], s));
+      e->launches += 1;
+    }
+    UpdateEpi epi{};
+    epi.T = e->T; epi.C = C; epi.ld = e->ld; epi.p = e->p_w; epi.q_out = e->q_w[1];
+    epi.flags_in = grad_checks ? e->flags[2] : nullptr;
+    epi.grad_only = 1;
+    if (staged_gradient_pass(e, e->q_w[0], epi, s)) return -1;
+    HMCB_CUDA(launch_st_transpose(e->p_w, d, C, e->ld, g, d, s));
+    e->launches += 1;
+  }
+  return 0;
+}
+
+int hmcb_reflect(hmcb_engine* e, double* q, double* p, void* stream) {
+  HMCB_READY(e);
+  HMCB_CHECK(q && p, "hmcb_reflect: NULL argument");
+  HMCB_CUDA(launch_reflect(e->T, (int)e->C, q, p, static_cast<cudaStream_t>(stream)));
+  e->launches += 1;
+  return 0;
+}
+
+int hmcb_scale_momentum(hmcb_engine* e, const double* z, double* p, void* stream) {
+  HMCB_READY(e);
+  HMCB_CHECK(z && p, "hmcb_scale_momentum: NULL argument");
+  HMCB_CUDA(launch_mass_elementwise(e->T, (int)e->C, 0, z, p, static_cast<cudaStream_t>(stream)));
+  e->launches += 1;
+  return 0;
+}
+
+int hmcb_kinetic_energy(hmcb_engine* e, const double* p, double* k, void* stream) {
+  HMCB_READY(e);
+  HMCB_CHECK(p && k, "hmcb_kinetic_energy: NULL argument");
+  HMCB_CUDA(launch_kinetic_energy(e->T, (int)e->C, p, k, static_cast<cudaStream_t>(stream)));
+  e->launches += 1;
+  return 0;
+}
+
+int hmcb_kinetic_gradient(hmcb_engine* e, const double* p, double* dk, void* stream) {
+  HMCB_READY(e);
+  HMCB_CHECK(p && dk, "hmcb_kinetic_gradient: NULL argument");
+  HMCB_CUDA(launch_mass_elementwise(e->T, (int)e->C, 1, p, dk, static_cast<cudaStream_t>(stream)));
+  e->launches += 1;
+  return 0;
+}
+
+int hmcb_run_block(hmcb_engine* e, const hmcb_block* b, void* stream) {
+  HMCB_READY(e);
+  HMCB_CHECK(b, "hmcb_run_block: block is NULL");
+  HMCB_CHECK(b->proposals > 0 && b->proposals < (1ll << 31), "hmcb_run_block: proposals must be positive");
+  HMCB_CHECK(b->thinning > 0, "hmcb_run_block: thinning must be positive");
+  HMCB_CHECK(b->proposal_offset >= 0 && b->chain_offset >= 0, "hmcb_run_block: negative offset");
+  HMCB_CHECK(b->stepsize > 0.0, "hmcb_run_block: stepsize must be positive");
+  HMCB_CHECK(b->q && b->x, "hmcb_run_block: q and x are required");
+  HMCB_CHECK((b->trace_q == nullptr) == (b->trace_g == nullptr), "hmcb_run_block: trace_q and trace_g go together");
+  HMCB_CHECK((b->out_q_prop == nullptr) == (b->out_p_prop == nullptr),
+             "hmcb_run_block: out_q_prop and out_p_prop go together");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (e->path == HMCB_PATH_FUSED_PRIORS) {
+    HMCB_CUDA(launch_fused_priors(fused_args(e, b), s));
+    e->launches += 1;
+    return 0;
+  }
+  if (e->path == HMCB_PATH_FUSED_SRCLOC) {
+    HMCB_CUDA(launch_fused_srcloc(fused_args(e, b), e->L, s));
+    e->launches += 1;
+    return 0;
+  }
+  return staged_run_block(e, b, s);
+}
+
+int hmcb_sample_host(hmcb_engine* e, const double* q0_host, int64_t proposals, int64_t thinning,
+                     int64_t block_proposals, double stepsize, int randomize_stepsize, uint64_t seed,
+                     int64_t chain_offset, double* samples_host, int32_t* accept_host,
+                     double* final_q_host, double* final_x_host) {
+  HMCB_READY(e);
+  HMCB_CHECK(q0_host, "hmcb_sample_host: q0_host is NULL");
+  HMCB_CHECK(proposals > 0 && thinning > 0 && proposals % thinning == 0,
+             "hmcb_sample_host: proposals must be a positive multiple of thinning");
+  HMCB_CHECK(stepsize > 0.0, "hmcb_sample_host: stepsize must be positive");
+  if (block_proposals <= 0) block_proposals = thinning;
+  block_proposals = (block_proposals + thinning - 1) / thinning * thinning;  // whole stored rows per block
+  const size_t C = (size_t)e->C, d = (size_t)e->d;
+  const size_t row_doubles = C * (d + 1);
+  const size_t rows_per_block = (size_t)(block_proposals / thinning);
+  if (!e->s_compute) HMCB_CUDA(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
+  if (!e->s_copy) HMCB_CUDA(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+
+  double *dq = nullptr, *dx = nullptr, *dbuf[2] = {nullptr, nullptr};
+  int32_t* dacc = nullptr;
+  cudaEvent_t produced[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
+  int rc = 0;
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(e->s_compute);
+    cudaStreamSynchronize(e->s_copy);
+    cudaFree(dq); cudaFree(dx); cudaFree(dacc); cudaFree(dbuf[0]); cudaFree(dbuf[1]);
+    for (int i = 0; i < 2; ++i) {
+      if (produced[i]) cudaEventDestroy(produced[i]);
+      if (drained[i]) cudaEventDestroy(drained[i]);
+    }
+  };
+#define HMCB_CUDA_C(expr)                                                             \
+  do {                                                                                \
+    cudaError_t err__ = (expr);                                                       \
+    if (err__ != cudaSuccess) {                                                       \
+      fail(std::string(#expr) + " failed: " + cudaGetErrorString(err__));             \
+      cleanup();                                                                      \
+      return -1;                                                                      \
+    }                                                                                 \
+  } while (0)
+  HMCB_CUDA_C(cudaMalloc(&dq, C * d * sizeof(double)));
+  HMCB_CUDA_C(cudaMalloc(&dx, C * sizeof(double)));
+  HMCB_CUDA_C(cudaMalloc(&dacc, C * sizeof(int32_t)));
+  if (samples_host) {
+    HMCB_CUDA_C(cudaMalloc(&dbuf[0], rows_per_block * row_doubles * sizeof(double)));
+    HMCB_CUDA_C(cudaMalloc(&dbuf[1], rows_per_block * row_doubles * sizeof(double)));
+  }
+  for (int i = 0; i < 2; ++i) {
+    HMCB_CUDA_C(cudaEventCreateWithFlags(&produced[i], cudaEventDisableTiming));
+    HMCB_CUDA_C(cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming));
+  }
+  HMCB_CUDA_C(cudaMemcpyAsync(dq, q0_host, C * d * sizeof(double), cudaMemcpyHostToDevice, e->s_compute));
+  HMCB_CUDA_C(cudaMemsetAsync(dacc, 0, C * sizeof(int32_t), e->s_compute));
+  rc = hmcb_misfit(e, dq, dx, e->s_compute);
+  if (rc) { cleanup(); return rc; }
+
+  int64_t done = 0, nblock = 0;
+  size_t rows_done = 0;
+  while (done < proposals) {
+    const int64_t B = std::min<int64_t>(block_proposals, proposals - done);
+    const int slot = (int)(nblock & 1);
+    hmcb_block blk;
+    std::memset(&blk, 0, sizeof(blk));
+    blk.proposals = B; blk.thinning = thinning; blk.proposal_offset = done; blk.chain_offset = chain_offset;
+    blk.seed = seed; blk.stepsize = stepsize; blk.randomize_stepsize = randomize_stepsize;
+    blk.q = dq; blk.x = dx; blk.accepted_total = dacc;
+    blk.out_samples = samples_host ? dbuf[slot] : nullptr;
+    if (samples_host && nblock >= 2) HMCB_CUDA_C(cudaStreamWaitEvent(e->s_compute, drained[slot], 0));
+    rc = hmcb_run_block(e, &blk, e->s_compute);
+    if (rc) { cleanup(); return rc; }
+    if (samples_host) {
+      const size_t rows = (size_t)(B / thinning);
+      HMCB_CUDA_C(cudaEventRecord(produced[slot], e->s_compute));
+      HMCB_CUDA_C(cudaStreamWaitEvent(e->s_copy, produced[slot], 0));
+      HMCB_CUDA_C(cudaMemcpyAsync(samples_host + rows_done * row_doubles, dbuf[slot],
+                                  rows * row_doubles * sizeof(double), cudaMemcpyDeviceToHost, e->s_copy));
+      HMCB_CUDA_C(cudaEventRecord(drained[slot], e->s_copy));
+      rows_done += rows;
+    }
+    done += B;
+    ++nblock;
+  }
+  if (accept_host)
+    HMCB_CUDA_C(cudaMemcpyAsync(accept_host, dacc, C * sizeof(int32_t), cudaMemcpyDeviceToHost, e->s_compute));
+  if (final_q_host)
+    HMCB_CUDA_C(cudaMemcpyAsync(final_q_host, dq, C * d * sizeof(double), cudaMemcpyDeviceToHost, e->s_compute));
+  if (final_x_host)
+    HMCB_CUDA_C(cudaMemcpyAsync(final_x_host, dx, C * sizeof(double), cudaMemcpyDeviceToHost, e->s_compute));
+  HMCB_CUDA_C(cudaStreamSynchronize(e->s_compute));
+  HMCB_CUDA_C(cudaStreamSynchronize(e->s_copy));
+  cleanup();
+#undef HMCB_CUDA_C
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// launch.cuh -- host-callable launchers, one translation unit per kernel family so the
+// template instantiations compile in parallel (see hmclab_b200/_build.py).
+#pragma once
+#include "common.cuh"
+#include "fused.cuh"
+#include "srcloc.cuh"
+#include "staged.cuh"
+
+namespace hmcb {
+
+// ---- launch_fused.cu -------------------------------------------------------------------
+// Thread mapping of the priors-only fused kernel for `dims` coordinates.
+void fused_priors_shape(int dims, int* tpc, int* ppt);
+bool fused_priors_supported(int dims);
+cudaError_t launch_fused_priors(const FusedArgs& A, cudaStream_t s);
+cudaError_t launch_prior_misfit(const DevTarget& T, int chains, const double* q, double* x,
+                                const double* lik_misfit, cudaStream_t s);
+cudaError_t launch_prior_gradient(const DevTarget& T, int chains, const double* q, double* g,
+                                  int accumulate, cudaStream_t s);
+cudaError_t launch_reflect(const DevTarget& T, int chains, double* q, double* p, cudaStream_t s);
+cudaError_t launch_mass_elementwise(const DevTarget& T, int chains, int mode, const double* in,
+                                    double* out, cudaStream_t s);
+cudaError_t launch_kinetic_energy(const DevTarget& T, int chains, const double* p, double* k,
+                                  cudaStream_t s);
+
+// ---- launch_srcloc.cu ------------------------------------------------------------------
+bool srcloc_supported(int events, int stations);
+size_t srcloc_smem_bytes(const SrcLocDev& L);
+cudaError_t launch_fused_srcloc(const FusedArgs& A, const SrcLocDev& L, cudaStream_t s);
+cudaError_t launch_srcloc_eval(const DevTarget& T, const SrcLocDev& L, int chains, int mode,
+                               const double* q, double* out, cudaStream_t s);
+
+// ---- launch_staged.cu ------------------------------------------------------------------
+cudaError_t staged_init();  // opt-in shared memory sizes
+cudaError_t launch_gemm_update(const double* A, int lda, int M, const double* B, int ldb, int K,
+                               const UpdateEpi& epi, cudaStream_t s);
+cudaError_t launch_gemm_residual(const double* A, int lda, int M, const double* B, int ldb, int K,
+                                 const ResidualEpi& epi, cudaStream_t s);
+cudaError_t launch_gemm_misfit(const double* A, int lda, int M, const double* B, int ldb, int K,
+                               const MisfitEpi& epi, cudaStream_t s);
+struct CsrDev {
+  const int* indptr;
+  const int* indices;
+  const double* data;
+  int rows;
+  int rows_per_chunk;
+  int chunks;
+};
+cudaError_t launch_spmm_update(const CsrDev& M, const double* B, int ldb, const UpdateEpi& epi,
+                               cudaStream_t s);
+cudaError_t launch_spmm_residual(const CsrDev& M, const double* B, int ldb, const ResidualEpi& epi,
+                                 cudaStream_t s);
+cudaError_t launch_spmm_misfit(const CsrDev& M, const double* B, int ldb, const MisfitEpi& epi,
+                               cudaStream_t s);
+cudaError_t launch_st_begin(const StagedCommon& S, long long kglob, double a_mult, const double* q_cur,
+                            double* q_w, double* p, const double* z_in, const double* u_step_in,
+                            const double* u_acc_in, double* eps_out, double* uacc_out, double* k0part,
+                            unsigned* flags_out, cudaStream_t s);
+cudaError_t launch_st_position(const StagedCommon& S, double a_mult, double* q_w, double* p,
+                               const double* eps, unsigned* flags_out, cudaStream_t s);
+cudaError_t launch_st_update(const StagedCommon& S, const UpdateEpi& epi, cudaStream_t s);
+cudaError_t launch_st_energy(const StagedCommon& S, const double* q, const double* p, double* k1part,
+                             double* upart, unsigned* flags_out, cudaStream_t s);
+cudaError_t launch_st_decide(const DecideArgs& D, cudaStream_t s);
+cudaError_t launch_st_commit(int C, int d, int ld, const unsigned char* acc, const double* q_w,
+                             const double* p, double* q_cur, double* sample_rows, double* q_prop,
+                             double* p_prop, cudaStream_t s);
+cudaError_t launch_st_transpose(const double* in, int R, int Cc, int ldin, double* out, int ldout,
+                                cudaStream_t s);
+
+}  // namespace hmcb

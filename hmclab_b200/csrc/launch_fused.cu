@@ -1,0 +1,101 @@
+// launch_fused.cu -- instantiations and dispatch of the priors-only fused HMC kernel and of
+// the standalone prior / mass-matrix kernels.
+#define HMCB_FUSED_AUX_KERNELS
+#include "launch.cuh"
+
+#include <cstdlib>
+
+namespace hmcb {
+
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// pairs = ceil(dims / 2) coordinate pairs are spread over TPC threads x PPT pairs each.
+// Small targets use one pair per thread; larger ones 2..8 pairs per thread so that a
+// chain stays inside one block of at most 1024 threads.
+void fused_priors_shape(int dims, int* tpc, int* ppt) {
+  const int pairs = (dims + 1) / 2;
+  int P = 1;
+  if (pairs > 64) {
+    P = pow2_ceil((pairs + 127) / 128);
+    if (P > 8) P = 8;
+  }
+  if (const char* env = std::getenv("HMCB_FUSED_PPT")) {
+    const int v = std::atoi(env);
+    if (v == 1 || v == 2 || v == 4 || v == 8) P = v;
+  }
+  int T = pow2_ceil((pairs + P - 1) / P);
+  if (P > 1 && T < 64) T = 64;
+  *tpc = T;
+  *ppt = P;
+}
+
+bool fused_priors_supported(int dims) {
+  int t, p;
+  fused_priors_shape(dims, &t, &p);
+  return p == 8 ? t <= 512 : t <= 1024;  // register budget of the widest shapes
+}
+
+// One translation unit per PPT (launch_fused_ppt.cu compiled with -DHMCB_PPT=n).
+cudaError_t launch_fused_priors_ppt1(const FusedArgs& A, int tpc, cudaStream_t s);
+cudaError_t launch_fused_priors_ppt2(const FusedArgs& A, int tpc, cudaStream_t s);
+cudaError_t launch_fused_priors_ppt4(const FusedArgs& A, int tpc, cudaStream_t s);
+cudaError_t launch_fused_priors_ppt8(const FusedArgs& A, int tpc, cudaStream_t s);
+
+cudaError_t launch_fused_priors(const FusedArgs& A, cudaStream_t s) {
+  int tpc, ppt;
+  fused_priors_shape(A.T.dims, &tpc, &ppt);
+  switch (ppt) {
+    case 1: return launch_fused_priors_ppt1(A, tpc, s);
+    case 2: return launch_fused_priors_ppt2(A, tpc, s);
+    case 4: return launch_fused_priors_ppt4(A, tpc, s);
+    case 8: return launch_fused_priors_ppt8(A, tpc, s);
+  }
+  return cudaErrorInvalidConfiguration;
+}
+
+// The standalone kernels loop over coordinates, so two thread shapes are enough.
+#define HMCB_TPC_DISPATCH(dims, CALL32, CALL256) \
+  if ((dims) <= 256) { CALL32; } else { CALL256; }
+
+cudaError_t launch_prior_misfit(const DevTarget& T, int chains, const double* q, double* x,
+                                const double* lik_misfit, cudaStream_t s) {
+  HMCB_TPC_DISPATCH(T.dims,
+                    (prior_misfit_kernel<32><<<(chains + 7) / 8, 256, 0, s>>>(T, chains, q, x, lik_misfit)),
+                    (prior_misfit_kernel<256><<<chains, 256, 0, s>>>(T, chains, q, x, lik_misfit)))
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prior_gradient(const DevTarget& T, int chains, const double* q, double* g,
+                                  int accumulate, cudaStream_t s) {
+  HMCB_TPC_DISPATCH(T.dims,
+                    (prior_gradient_kernel<32><<<(chains + 7) / 8, 256, 0, s>>>(T, chains, q, g, accumulate)),
+                    (prior_gradient_kernel<256><<<chains, 256, 0, s>>>(T, chains, q, g, accumulate)))
+  return cudaGetLastError();
+}
+
+cudaError_t launch_kinetic_energy(const DevTarget& T, int chains, const double* p, double* k,
+                                  cudaStream_t s) {
+  HMCB_TPC_DISPATCH(T.dims,
+                    (kinetic_energy_kernel<32><<<(chains + 7) / 8, 256, 0, s>>>(T, chains, p, k)),
+                    (kinetic_energy_kernel<256><<<chains, 256, 0, s>>>(T, chains, p, k)))
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reflect(const DevTarget& T, int chains, double* q, double* p, cudaStream_t s) {
+  const size_t total = (size_t)chains * T.dims;
+  reflect_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(T, total, q, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mass_elementwise(const DevTarget& T, int chains, int mode, const double* in,
+                                    double* out, cudaStream_t s) {
+  const size_t total = (size_t)chains * T.dims;
+  mass_elementwise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(T, total, mode, in, out);
+  return cudaGetLastError();
+}
+
+}  // namespace hmcb

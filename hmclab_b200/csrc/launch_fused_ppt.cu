@@ -1,0 +1,43 @@
+// launch_fused_ppt.cu -- instantiations of the priors-only fused HMC kernel for one value
+// of PPT (coordinate pairs per thread); compiled once per -DHMCB_PPT={1,2,4,8}.
+#include "launch.cuh"
+
+#ifndef HMCB_PPT
+#error "compile with -DHMCB_PPT=<pairs per thread>"
+#endif
+#define HMCB_CAT2(a, b) a##b
+#define HMCB_CAT(a, b) HMCB_CAT2(a, b)
+
+namespace hmcb {
+
+template <int TPC, int PPT>
+static cudaError_t launch_fp(const FusedArgs& A, cudaStream_t s) {
+  constexpr int BLOCK = TPC < 256 ? 256 : TPC;
+  constexpr int CPB = BLOCK / TPC;
+  const int grid = (A.chains + CPB - 1) / CPB;
+  hmc_fused_priors_kernel<TPC, PPT><<<grid, BLOCK, 0, s>>>(A);
+  return cudaGetLastError();
+}
+
+cudaError_t HMCB_CAT(launch_fused_priors_ppt, HMCB_PPT)(const FusedArgs& A, int tpc, cudaStream_t s) {
+  switch (tpc) {
+#if HMCB_PPT == 1
+    case 1: return launch_fp<1, 1>(A, s);
+    case 2: return launch_fp<2, 1>(A, s);
+    case 4: return launch_fp<4, 1>(A, s);
+    case 8: return launch_fp<8, 1>(A, s);
+    case 16: return launch_fp<16, 1>(A, s);
+    case 32: return launch_fp<32, 1>(A, s);
+#endif
+    case 64: return launch_fp<64, HMCB_PPT>(A, s);
+    case 128: return launch_fp<128, HMCB_PPT>(A, s);
+    case 256: return launch_fp<256, HMCB_PPT>(A, s);
+    case 512: return launch_fp<512, HMCB_PPT>(A, s);
+#if HMCB_PPT <= 4
+    case 1024: return launch_fp<1024, HMCB_PPT>(A, s);
+#endif
+  }
+  return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace hmcb

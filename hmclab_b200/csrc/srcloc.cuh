@@ -1,0 +1,352 @@
+// srcloc.cuh -- SourceLocation3D travel-time misfit / gradient and the fused HMC kernel
+// built on it (compute-bound elementwise-reduction; SourceLocation.py:482-540, 697-713).
+//
+// Thread mapping: a chain is owned by TPC threads; event e = t / LPE, the LPE lanes of an
+// event split the stations (s = sub, sub+LPE, ...).  All LPE lanes of an event hold the
+// event's 4 parameters (x, y, z, T) and integrate them redundantly (identical bits), so
+// the only communication per gradient is an LPE-lane butterfly.  Station geometry and
+// picks are staged in shared memory once per block.
+#pragma once
+#include "common.cuh"
+#include "fused.cuh"
+
+namespace hmcb {
+
+struct SrcLocDev {
+  int events, stations, infer_velocity, pad;
+  double velocity;
+  const double* rx; const double* ry; const double* rz;  // [S]
+  const double* tobs; const double* std;                 // [E x S]
+};
+
+struct SrcLocShared {
+  const double *rx, *ry, *rz, *tobs, *std;
+};
+
+__device__ __forceinline__ SrcLocShared srcloc_stage(const SrcLocDev& L, double* smem) {
+  const int S = L.stations, ES = L.events * L.stations;
+  double* rx = smem; double* ry = rx + S; double* rz = ry + S;
+  double* tobs = rz + S; double* sd = tobs + ES;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    rx[i] = L.rx[i]; ry[i] = L.ry[i]; rz[i] = L.rz[i];
+  }
+  for (int i = threadIdx.x; i < ES; i += blockDim.x) { tobs[i] = L.tobs[i]; sd[i] = L.std[i]; }
+  __syncthreads();
+  return SrcLocShared{rx, ry, rz, tobs, sd};
+}
+
+__device__ __forceinline__ double nan_to_zero(double v) { return (v != v) ? 0.0 : v; }
+
+// Partial (this lane's stations) gradient sums of event e (SourceLocation.py:495-524).
+template <int LPE>
+__device__ __forceinline__ void srcloc_gradient_partial(const SrcLocShared& M, int S, int e, int sub,
+                                                        double x, double y, double z, double T,
+                                                        double v, double& gx, double& gy,
+                                                        double& gz, double& gT, double& gv) {
+  gx = gy = gz = gT = gv = 0.0;
+  const double vv = __dmul_rn(v, v);
+  for (int s = sub; s < S; s += LPE) {
+    const double dx = __dsub_rn(x, M.rx[s]), dy = __dsub_rn(y, M.ry[s]), dz = __dsub_rn(z, M.rz[s]);
+    const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    const double tcalc = __dadd_rn(T, __ddiv_rn(dist, v));
+    const double sd = M.std[e * S + s];
+    const double w = __ddiv_rn(__dsub_rn(tcalc, M.tobs[e * S + s]), __dmul_rn(sd, sd));
+    const double vd = __dmul_rn(v, dist);
+    gx = __dadd_rn(gx, nan_to_zero(__dmul_rn(w, __ddiv_rn(dx, vd))));
+    gy = __dadd_rn(gy, nan_to_zero(__dmul_rn(w, __ddiv_rn(dy, vd))));
+    gz = __dadd_rn(gz, nan_to_zero(__dmul_rn(w, __ddiv_rn(dz, vd))));
+    gT = __dadd_rn(gT, nan_to_zero(w));
+    gv = __dadd_rn(gv, nan_to_zero(__dmul_rn(w, __ddiv_rn(-dist, vv))));
+  }
+}
+
+// Partial sum of squared standardised residuals of event e (SourceLocation.py:482-493).
+template <int LPE>
+__device__ __forceinline__ double srcloc_misfit_partial(const SrcLocShared& M, int S, int e, int sub,
+                                                        double x, double y, double z, double T,
+                                                        double v) {
+  double acc = 0.0;
+  for (int s = sub; s < S; s += LPE) {
+    const double dx = __dsub_rn(x, M.rx[s]), dy = __dsub_rn(y, M.ry[s]), dz = __dsub_rn(z, M.rz[s]);
+    const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    const double r = __ddiv_rn(__dsub_rn(M.tobs[e * S + s], __dadd_rn(T, __ddiv_rn(dist, v))), M.std[e * S + s]);
+    acc = __dadd_rn(acc, nan_to_zero(__dmul_rn(r, r)));
+  }
+  return acc;
+}
+
+template <int LPE>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int off = LPE / 2; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+
+// Per-thread view of one chain: 4 event parameters (+ the shared velocity).
+template <int TPC, int LPE>
+struct SrcLocLane {
+  int e, sub, c;
+  bool has_event, lead, vlead, live;
+
+  __device__ __forceinline__ void init(int chains, int E) {
+    constexpr int BLOCK = TPC <= 32 ? 256 : TPC;
+    constexpr int CPB = BLOCK / TPC;
+    const int t = threadIdx.x % TPC;
+    c = blockIdx.x * CPB + threadIdx.x / TPC;
+    live = c < chains;
+    if (!live) c = chains - 1;
+    e = t / LPE; sub = t % LPE;
+    has_event = e < E;
+    lead = has_event && sub == 0;  // the lane that accounts for / writes the event's coordinates
+    vlead = t == 0;                // the lane that accounts for / writes the velocity
+    if (!has_event) e = E - 1;
+  }
+};
+
+// Gradient of the full target at the lane's coordinates: prior terms + travel-time term.
+// g[0..3] for (x,y,z,T) of the lane's event, gvel for the velocity coordinate.
+template <int TPC, int LPE>
+__device__ __forceinline__ void srcloc_total_gradient(const DevTarget& T, const SrcLocDev& L,
+                                                      const SrcLocShared& M,
+                                                      const SrcLocLane<TPC, LPE>& ln,
+                                                      const ChainReduce<TPC>& red, const double* q,
+                                                      double qv, unsigned oob, double* g, double& gvel) {
+  const double v = L.infer_velocity ? qv : L.velocity;
+  double gx, gy, gz, gT, gv;
+  srcloc_gradient_partial<LPE>(M, L.stations, ln.e, ln.sub, q[0], q[1], q[2], q[3], v, gx, gy, gz, gT, gv);
+  gx = group_sum<LPE>(gx); gy = group_sum<LPE>(gy); gz = group_sum<LPE>(gz); gT = group_sum<LPE>(gT);
+  const int j0 = 4 * ln.e;
+  g[0] = __dadd_rn(prior_gradient(T, j0 + 0, q[0], oob), gx);
+  g[1] = __dadd_rn(prior_gradient(T, j0 + 1, q[1], oob), gy);
+  g[2] = __dadd_rn(prior_gradient(T, j0 + 2, q[2], oob), gz);
+  g[3] = __dadd_rn(prior_gradient(T, j0 + 3, q[3], oob), gT);
+  gvel = 0.0;
+  if (L.infer_velocity) {
+    double a = ln.has_event ? gv : 0.0, b = 0.0, c2 = 0.0;
+    red.sum3(a, b, c2);
+    gvel = __dadd_rn(prior_gradient(T, 4 * L.events, qv, oob), a);
+  }
+}
+
+template <int TPC, int LPE>
+__device__ __forceinline__ unsigned srcloc_violations(const DevTarget& T, const SrcLocDev& L,
+                                                      const SrcLocLane<TPC, LPE>& ln,
+                                                      const ChainReduce<TPC>& red, const double* q,
+                                                      double qv) {
+  unsigned m = 0;
+  if (T.n_checks) {
+    if (ln.lead) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m |= bound_violations(T, 4 * ln.e + i, q[i]);
+    }
+    if (L.infer_velocity && ln.vlead) m |= bound_violations(T, 4 * L.events, qv);
+    m = red.any_bits(m);
+  }
+  return m;
+}
+
+template <int TPC, int LPE>
+__global__ void __launch_bounds__((TPC <= 32 ? 256 : TPC))
+hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
+  extern __shared__ double dyn_smem[];
+  __shared__ double scratch[3 * ((TPC + 31) / 32) + 1];
+  const ChainReduce<TPC> red{scratch};
+  const SrcLocShared M = srcloc_stage(L, dyn_smem);
+  const DevTarget& T = A.T;
+  const int d = T.dims, E = L.events;
+  SrcLocLane<TPC, LPE> ln;
+  ln.init(A.chains, E);
+  const int c = ln.c;
+  const size_t row = (size_t)c * d, C = (size_t)A.chains;
+  const int j0 = 4 * ln.e, jv = 4 * E;
+  const bool inferv = L.infer_velocity != 0;
+  const bool grad_checks = T.grad_check_mask != 0u;
+
+  double qc[4], q[4], p[4], qcv = 0.0, qv = 0.0, pv = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) qc[i] = A.q[row + j0 + i];
+  if (inferv) qcv = A.q[row + jv];
+  double x = A.x[c];
+  int accepted = 0;
+
+  for (int kb = 0; kb < A.proposals; ++kb) {
+    const long long kglob = A.proposal_offset + kb;
+    const size_t kc = (size_t)kb * C + c;
+    const uint32_t cg = (uint32_t)(A.chain_offset + c), kg = (uint32_t)kglob;
+    double u_step, u_acc;
+    uniform_pair(A.seed, cg, kg, u_step, u_acc);
+    if (A.u_step_in) u_step = A.u_step_in[kc];
+    if (A.u_accept_in) u_acc = A.u_accept_in[kc];
+    const double eps = A.randomize ? __dmul_rn(u_step, A.stepsize) : A.stepsize;
+
+    if (A.z_in) {
+      const double* zr = A.z_in + kc * d;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p[i] = zr[j0 + i];
+      if (inferv) pv = zr[jv];
+    } else {
+      normal_pair(A.seed, cg, kg, (uint32_t)(2 * ln.e), p[0], p[1]);
+      normal_pair(A.seed, cg, kg, (uint32_t)(2 * ln.e + 1), p[2], p[3]);
+      if (inferv) { double unused; normal_pair(A.seed, cg, kg, (uint32_t)(2 * E), pv, unused); }
+    }
+    double k0 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      q[i] = qc[i];
+      if (T.sqrtm) p[i] = __dmul_rn(__ldg(T.sqrtm + j0 + i), p[i]);
+      if (ln.lead) k0 = __dadd_rn(k0, kinetic_term(T, j0 + i, p[i]));
+    }
+    if (inferv) {
+      qv = qcv;
+      if (T.sqrtm) pv = __dmul_rn(__ldg(T.sqrtm + jv), pv);
+      if (ln.vlead) k0 = __dadd_rn(k0, kinetic_term(T, jv, pv));
+    }
+
+    int gi = 0;
+    auto run_op = [&](const StageOp& op) {
+      if (op.has_b) {
+        unsigned oob = 0;
+        if (grad_checks) oob = srcloc_violations<TPC, LPE>(T, L, ln, red, q, qv);
+        double g[4], gvel;
+        srcloc_total_gradient<TPC, LPE>(T, L, M, ln, red, q, qv, oob, g, gvel);
+        if (A.trace_q && ln.live) {
+          const size_t o = (((size_t)kb * A.S.grads_per_proposal + gi) * C + c) * d;
+          if (ln.lead) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { A.trace_q[o + j0 + i] = q[i]; A.trace_g[o + j0 + i] = g[i]; }
+          }
+          if (inferv && ln.vlead) { A.trace_q[o + jv] = qv; A.trace_g[o + jv] = gvel; }
+        }
+        const double cb = __dmul_rn(op.b, eps);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) momentum_update(cb, g[i], p[i]);
+        if (inferv) momentum_update(cb, gvel, pv);
+        ++gi;
+      }
+      const double ca = __dmul_rn(op.a, eps);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) position_update(T, j0 + i, ca, q[i], p[i]);
+      if (inferv) position_update(T, jv, ca, qv, pv);
+    };
+    for (int s = 0; s < A.S.n_pre; ++s) run_op(A.S.pre[s]);
+    for (int r = 0; r < A.S.reps; ++r)
+      for (int s = 0; s < A.S.n_body; ++s) run_op(A.S.body[s]);
+    for (int s = 0; s < A.S.n_post; ++s) run_op(A.S.post[s]);
+
+    // energies: kinetic, prior misfit, travel-time misfit
+    double k1 = 0.0, u1 = 0.0;
+    if (ln.lead) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        k1 = __dadd_rn(k1, kinetic_term(T, j0 + i, p[i]));
+        u1 = __dadd_rn(u1, prior_misfit(T, j0 + i, q[i]));
+      }
+    }
+    if (inferv && ln.vlead) {
+      k1 = __dadd_rn(k1, kinetic_term(T, jv, pv));
+      u1 = __dadd_rn(u1, prior_misfit(T, jv, qv));
+    }
+    const double vel = inferv ? qv : L.velocity;
+    double lik = srcloc_misfit_partial<LPE>(M, L.stations, ln.e, ln.sub, q[0], q[1], q[2], q[3], vel);
+    if (!ln.has_event) lik = 0.0;
+    red.sum3(k0, k1, u1);
+    double z0 = 0.0, z1 = 0.0;
+    red.sum3(lik, z0, z1);
+    const unsigned oob = srcloc_violations<TPC, LPE>(T, L, ln, red, q, qv);
+    // BayesRule order: prior misfit first, then the likelihood, then the bounds
+    double x1 = __dadd_rn(__dadd_rn(u1, T.const_sum), __dmul_rn(0.5, lik));
+    if (oob) x1 = __dadd_rn(x1, CUDART_INF);
+    const double h0 = __dadd_rn(x, __dmul_rn(0.5, k0));
+    const double h1 = __dadd_rn(x1, __dmul_rn(0.5, k1));
+    const bool acc = metropolis_accept(h0, h1, u_acc);
+
+    if (ln.live) {
+      if (A.out_q_prop) {
+        if (ln.lead) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { A.out_q_prop[kc * d + j0 + i] = q[i]; A.out_p_prop[kc * d + j0 + i] = p[i]; }
+        }
+        if (inferv && ln.vlead) { A.out_q_prop[kc * d + jv] = qv; A.out_p_prop[kc * d + jv] = pv; }
+      }
+      if (ln.vlead) {
+        if (A.out_accept) A.out_accept[kc] = acc ? 1 : 0;
+        if (A.out_h0) A.out_h0[kc] = h0;
+        if (A.out_h1) A.out_h1[kc] = h1;
+      }
+    }
+    if (acc) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qc[i] = q[i];
+      qcv = qv; x = x1; ++accepted;
+    }
+    if (A.out_samples && ln.live && (kglob % A.thinning) == 0) {
+      const size_t srow = ((size_t)((kglob / A.thinning) - ((A.proposal_offset + A.thinning - 1) / A.thinning)) * C + c) *
+                          (size_t)(d + 1);
+      if (ln.lead) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) A.out_samples[srow + j0 + i] = qc[i];
+      }
+      if (ln.vlead) {
+        if (inferv) A.out_samples[srow + jv] = qcv;
+        A.out_samples[srow + d] = x;
+      }
+    }
+  }
+
+  if (ln.live) {
+    if (ln.lead) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) A.q[row + j0 + i] = qc[i];
+    }
+    if (ln.vlead) {
+      if (inferv) A.q[row + jv] = qcv;
+      A.x[c] = x;
+      if (A.accepted_total) A.accepted_total[c] += accepted;
+    }
+  }
+}
+
+// mode 0: x[c] = misfit ; mode 1: g[c,:] = gradient
+template <int TPC, int LPE>
+__global__ void __launch_bounds__((TPC <= 32 ? 256 : TPC))
+srcloc_eval_kernel(const DevTarget T, const SrcLocDev L, int chains, int mode,
+                   const double* __restrict__ qin, double* __restrict__ out) {
+  extern __shared__ double dyn_smem[];
+  __shared__ double scratch[3 * ((TPC + 31) / 32) + 1];
+  const ChainReduce<TPC> red{scratch};
+  const SrcLocShared M = srcloc_stage(L, dyn_smem);
+  const int d = T.dims, E = L.events;
+  SrcLocLane<TPC, LPE> ln;
+  ln.init(chains, E);
+  const size_t row = (size_t)ln.c * d;
+  const int j0 = 4 * ln.e, jv = 4 * E;
+  double q[4], qv = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = qin[row + j0 + i];
+  if (L.infer_velocity) qv = qin[row + jv];
+  const unsigned oob = srcloc_violations<TPC, LPE>(T, L, ln, red, q, qv);
+  if (mode == 0) {
+    double u1 = 0.0, z0 = 0.0, z1 = 0.0;
+    if (ln.lead)
+      for (int i = 0; i < 4; ++i) u1 = __dadd_rn(u1, prior_misfit(T, j0 + i, q[i]));
+    if (L.infer_velocity && ln.vlead) u1 = __dadd_rn(u1, prior_misfit(T, jv, qv));
+    const double vel = L.infer_velocity ? qv : L.velocity;
+    double lik = srcloc_misfit_partial<LPE>(M, L.stations, ln.e, ln.sub, q[0], q[1], q[2], q[3], vel);
+    if (!ln.has_event) lik = 0.0;
+    red.sum3(u1, lik, z0);
+    (void)z1;
+    double x1 = __dadd_rn(__dadd_rn(u1, T.const_sum), __dmul_rn(0.5, lik));
+    if (oob) x1 = __dadd_rn(x1, CUDART_INF);
+    if (ln.live && ln.vlead) out[ln.c] = x1;
+  } else {
+    double g[4], gvel;
+    srcloc_total_gradient<TPC, LPE>(T, L, M, ln, red, q, qv, oob, g, gvel);
+    if (ln.live) {
+      if (ln.lead)
+        for (int i = 0; i < 4; ++i) out[row + j0 + i] = g[i];
+      if (L.infer_velocity && ln.vlead) out[row + jv] = gvel;
+    }
+  }
+}
+
+}  // namespace hmcb

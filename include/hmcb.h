@@ -1,0 +1,178 @@
+/* hmcb.h -- C ABI of the B200-native batched HMC engine (libhmcb.so).
+ *
+ * This is the drop-in boundary for the hot path of hmclab's HMC sampler.  The
+ * reference has no FFI seam on this path: the seam is its Python object protocol
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it
+ * replaces (paths relative to the hmclab repository).  The only FFI precedent in the
+ * reference is hmclab/Helpers/InterfaceMKL.py:26-33,87-121 (ctypes, raw pointers,
+ * int32 CSR), whose style this header follows: plain pointers and sizes, no C++ or
+ * torch types, every function returns an int status (0 = ok, <0 = error, message via
+ * hmcb_last_error()), no exceptions cross the boundary, no ownership transfer.
+ *
+ * Memory:
+ *   - "HOST" pointers are read during the call and copied; the engine owns only its
+ *     private device copies of model constants (freed by hmcb_destroy).
+ *   - "DEVICE" pointers are CUDA device pointers owned by the caller (PyTorch tensors:
+ *     tensor.data_ptr()); calls enqueue work on `stream` (a cudaStream_t passed as
+ *     void*, NULL = legacy default stream) and return without synchronising.
+ *   - One engine per device and per host thread (one process per GPU); not thread-safe.
+ *
+ * Layout: every batch is [chains x dims] row-major (chain-major, dims contiguous),
+ * IEEE float64.  Engines with a coupled dense/CSR likelihood keep a private
+ * transposed [dims x chains] working copy; that is invisible here.
+ */
+#ifndef HMCB_H
+#define HMCB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMCB_ABI_VERSION 1
+
+typedef struct hmcb_engine hmcb_engine;
+
+/* Samplers.py:1728-1738 integrator registry {"lf","3s","4s"} */
+enum { HMCB_INTEGRATOR_LF = 0, HMCB_INTEGRATOR_3S = 1, HMCB_INTEGRATOR_4S = 2 };
+/* elementwise priors: base.py:539-574 (Normal, diagonal), base.py:689-710 (Laplace) */
+enum { HMCB_PRIOR_NORMAL = 0, HMCB_PRIOR_LAPLACE = 1 };
+/* execution path chosen by hmcb_finalize (reported by hmcb_path) */
+enum { HMCB_PATH_FUSED_PRIORS = 0, HMCB_PATH_FUSED_SRCLOC = 1, HMCB_PATH_STAGED = 2 };
+
+int hmcb_abi_version(void);
+const char *hmcb_last_error(void);
+
+/* lifetime ------------------------------------------------------------------------- */
+int hmcb_create(int device, int64_t chains, int64_t dims, hmcb_engine **out);
+int hmcb_destroy(hmcb_engine *e);
+
+/* tuning: HMC.sample(amount_of_steps=, integrator=) -- Samplers.py:1351-1358,1379-1384 */
+int hmcb_set_integrator(hmcb_engine *e, int integrator, int amount_of_steps);
+
+/* MassMatrices.Unit (MassMatrices.py:82-156) */
+int hmcb_set_mass_unit(hmcb_engine *e);
+/* MassMatrices.Diagonal (MassMatrices.py:159-238); HOST arrays of `dims` doubles.
+ * inverse_diagonal is passed (not recomputed) because the reference multiplies by its
+ * precomputed rounded reciprocal (:180,218). */
+int hmcb_set_mass_diagonal(hmcb_engine *e, const double *diagonal,
+                           const double *inverse_diagonal);
+
+/* target distribution ----------------------------------------------------------------
+ * Built from a distribution object tree (BayesRule / Composite / priors / likelihood) by
+ * hmclab_b200/_lowering.py.  All HOST arrays. */
+int hmcb_clear_target(hmcb_engine *e);
+/* Normal: a = means, b = inverse variances; Laplace: a = means, b = inverse dispersions;
+ * `constant` = normalization_constant.  Acts on coordinates [offset, offset+len)
+ * (CompositeDistribution, base.py:867-898). */
+int hmcb_add_prior(hmcb_engine *e, int kind, int64_t offset, int64_t len,
+                   const double *a, const double *b, double constant);
+/* misfit_bounds of one distribution object (base.py:361-374): misfit += inf when any
+ * coordinate of the range is outside [lb, ub]; if in_gradient, the gradient on the range
+ * gets +inf too (priors and containers do that, likelihoods do not).  lb / ub: `len`
+ * doubles each, either may be NULL. */
+int hmcb_add_bound_check(hmcb_engine *e, int64_t offset, int64_t len, const double *lb,
+                         const double *ub, int in_gradient);
+/* Bounds the trajectory reflects on (corrector: base.py:239-270,913-978,1111-1142);
+ * `dims` doubles each (+-inf where unbounded), either may be NULL. */
+int hmcb_set_reflection(hmcb_engine *e, const double *lb, const double *ub);
+
+/* LinearMatrix, dense G, premultiplied form (LinearMatrix.py:164-182,185-191,204-206):
+ * GtG [dims x dims] row-major, Gtd0 [dims], dtd scalar. */
+int hmcb_set_likelihood_dense_premult(hmcb_engine *e, const double *GtG,
+                                      const double *Gtd0, double dtd);
+/* LinearMatrix, dense G, direct form (LinearMatrix.py:192-202,207-208): G [N x dims]
+ * row-major (the dtype-rounded matrix), Gt [dims x N] row-major or NULL when it equals
+ * G^T (the reference keeps the caller's un-rounded G^T, :182), d/var/sigma [N]. */
+int hmcb_set_likelihood_dense_direct(hmcb_engine *e, int64_t N, const double *G,
+                                     const double *Gt, const double *d, const double *var,
+                                     const double *sigma);
+/* LinearMatrix, sparse G, direct form (LinearMatrix.py:406-426; replaces the MKL
+ * mkl_cspblas_dcsrgemv binding, InterfaceMKL.py:87-121): CSR of G [N x dims] and CSR of
+ * G^T [dims x N], int32 indices, float64 values. */
+int hmcb_set_likelihood_csr_direct(hmcb_engine *e, int64_t N, int64_t nnz,
+                                   const int32_t *indptr, const int32_t *indices,
+                                   const double *data, const int32_t *t_indptr,
+                                   const int32_t *t_indices, const double *t_data,
+                                   const double *d, const double *var, const double *sigma);
+/* LinearMatrix, sparse G, premultiplied form (LinearMatrix.py:341-357,390-396,417-419):
+ * CSR of the sparse GtG [dims x dims]. */
+int hmcb_set_likelihood_csr_premult(hmcb_engine *e, int64_t nnz, const int32_t *indptr,
+                                    const int32_t *indices, const double *data,
+                                    const double *Gtd0, double dtd);
+/* SourceLocation3D (SourceLocation.py:482-540,697-713): stations rx/ry/rz [S],
+ * observed travel times and standard deviations [E x S] row-major (NaN = missing pick);
+ * dims must be 4*E (+1 if infer_velocity). */
+int hmcb_set_likelihood_srcloc3d(hmcb_engine *e, int64_t events, int64_t stations,
+                                 const double *rx, const double *ry, const double *rz,
+                                 const double *tobs, const double *std, int infer_velocity,
+                                 double velocity);
+
+/* Validate the configuration, upload constants, choose the execution path and allocate
+ * workspaces.  Must be called after the setters and before any evaluation. */
+int hmcb_finalize(hmcb_engine *e);
+int hmcb_path(const hmcb_engine *e);
+/* gradient evaluations per proposal: amount_of_steps x {1,3,4} */
+int64_t hmcb_grads_per_proposal(const hmcb_engine *e);
+/* number of kernels launched by this engine since creation (bench bookkeeping) */
+int64_t hmcb_launch_count(const hmcb_engine *e);
+
+/* Distributions contract on a batch (DEVICE pointers) ---------------------------------
+ * misfit(m) -> float, gradient(m) -> (d,1)  (base.py:71,141), one row per chain. */
+int hmcb_misfit(hmcb_engine *e, const double *q, double *x, void *stream);
+int hmcb_gradient(hmcb_engine *e, const double *q, double *g, void *stream);
+/* corrector(q, p) in place (base.py:239-270) */
+int hmcb_reflect(hmcb_engine *e, double *q, double *p, void *stream);
+/* mass-matrix protocol (MassMatrices.py:42-69): p = sqrt(M) z ; K(p) ; dK/dp */
+int hmcb_scale_momentum(hmcb_engine *e, const double *z, double *p, void *stream);
+int hmcb_kinetic_energy(hmcb_engine *e, const double *p, double *k, void *stream);
+int hmcb_kinetic_gradient(hmcb_engine *e, const double *p, double *dk, void *stream);
+
+/* A block of HMC proposals for all chains (replaces the body of
+ * _AbstractSampler._sample_loop, Samplers.py:579-587,675-678, i.e. HMC._propose :1463 +
+ * HMC._evaluate_acceptance :1471 for `proposals` consecutive proposals).  DEVICE pointers. */
+typedef struct hmcb_block {
+  int64_t proposals;        /* B > 0 */
+  int64_t thinning;         /* online_thinning; global proposal k is stored iff k % thinning == 0 */
+  int64_t proposal_offset;  /* global index of the first proposal of this block */
+  int64_t chain_offset;     /* global id of local chain 0 (keys the on-device RNG) */
+  uint64_t seed;            /* Philox key for the on-device RNG */
+  double stepsize;          /* > 0 */
+  int32_t randomize_stepsize; /* eps = U(0.5,1.5) * stepsize per chain and proposal */
+  int32_t reserved;
+  double *q;                /* [C x d] in: current models; out: models after the block */
+  double *x;                /* [C]     in: current misfits; out: misfits after the block */
+  /* injected draws (parity mode); NULL = draw on the device (Philox4x32-10) */
+  const double *z_in;       /* [B x C x d] standard normals (momentum = sqrt(M) z) */
+  const double *u_step_in;  /* [B x C] uniforms in [0.5,1.5) */
+  const double *u_accept_in;/* [B x C] uniforms in [0,1) */
+  /* outputs; any may be NULL */
+  double *out_samples;      /* [ceil-stored x C x (d+1)] rows [model, misfit], post-decision */
+  uint8_t *out_accept;      /* [B x C] 1 = accepted */
+  double *out_h0;           /* [B x C] H(current) */
+  double *out_h1;           /* [B x C] H(proposed) */
+  int32_t *accepted_total;  /* [C] += accepted proposals */
+  /* debugging / parity outputs; any may be NULL */
+  double *out_q_prop;       /* [B x C x d] end-of-trajectory positions */
+  double *out_p_prop;       /* [B x C x d] end-of-trajectory momenta */
+  double *trace_q;          /* [B x G x C x d] position at every gradient evaluation */
+  double *trace_g;          /* [B x G x C x d] gradient at every gradient evaluation */
+} hmcb_block;
+
+int hmcb_run_block(hmcb_engine *e, const hmcb_block *block, void *stream);
+
+/* Whole sampling call with HOST buffers: q0_host [C x d] initial models (pinned or
+ * pageable), samples_host [(proposals/thinning) x C x (d+1)] output.  Copies run on
+ * private streams and overlap with the kernels of the next block; returns after the
+ * last sample has landed.  accept_host [C] (int32 accepted counts) may be NULL. */
+int hmcb_sample_host(hmcb_engine *e, const double *q0_host, int64_t proposals,
+                     int64_t thinning, int64_t block_proposals, double stepsize,
+                     int randomize_stepsize, uint64_t seed, int64_t chain_offset,
+                     double *samples_host, int32_t *accept_host, double *final_q_host,
+                     double *final_x_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMCB_H */
