@@ -1,7 +1,7 @@
 // common.cuh -- device-side building blocks shared by every HMC kernel.
 //
-//  * DevTarget: flattened target distribution (elementwise priors, bound checks,
-//    reflection bounds, mass matrix) passed by value to kernels.
+//  * DevTarget: flattened target distribution (per-coordinate tables of elementwise
+//    priors, bound checks, reflection bounds, mass matrix) passed by value to kernels.
 //  * Elementwise arithmetic follows the reference's operation order and is written with
 //    __dmul_rn/__dadd_rn/__dsub_rn so that nvcc never contracts it into FMAs: on separable
 //    targets a trajectory is bit-identical to numpy's.
@@ -17,35 +17,33 @@
 
 namespace hmcb {
 
-struct PriorTerm {
-  int kind;    // HMCB_PRIOR_NORMAL / HMCB_PRIOR_LAPLACE
-  int offset;  // first coordinate
-  int len;
-  const double* a;  // means            (indexed j - offset)
-  const double* b;  // inverse variance / inverse dispersion
-};
-
-struct BoundCheck {
-  int offset;
-  int len;
-  int in_gradient;
-  const double* lb;  // may be null (indexed j - offset)
-  const double* ub;  // may be null
-};
-
+// Flattened target distribution as per-coordinate tables (built once by hmcb_finalize):
+//   * prior terms: slot t of coordinate j holds the t-th elementwise prior covering j
+//     (kind 0 = none, 1 = Normal: a = mean, b = inverse variance; 2 = Laplace: a = mean,
+//     b = inverse dispersion), in the order the reference sums them;
+//   * bound checks: check k has lb/ub rows with -inf/+inf where it does not apply, and
+//     c_cover[j] has bit k set when coordinate j lies inside check k's range (that is
+//     where a fired check adds +inf to the gradient);
+//   * reflection bounds and the diagonal mass matrix.
 struct DevTarget {
   int dims;
-  int n_priors;
+  int n_terms;   // max number of prior terms covering one coordinate
   int n_checks;
   unsigned grad_check_mask;  // bit k set: check k adds +inf to the gradient on its range
   double const_sum;          // sum of the priors' normalisation constants
-  PriorTerm prior[HMCB_MAX_PRIORS];
-  BoundCheck check[HMCB_MAX_CHECKS];
+  const unsigned char* t_kind;  // [n_terms x dims]
+  const double* t_a;            // [n_terms x dims]
+  const double* t_b;            // [n_terms x dims]
+  const double* c_lb;           // [n_checks x dims]
+  const double* c_ub;           // [n_checks x dims]
+  const unsigned char* c_cover; // [dims]
   const double* refl_lb;  // [dims] or null
   const double* refl_ub;  // [dims] or null
   const double* invm;     // [dims] 1/diagonal, null = unit mass
   const double* sqrtm;    // [dims] sqrt(diagonal), null = unit mass
 };
+
+enum { TERM_NONE = 0, TERM_NORMAL = 1, TERM_LAPLACE = 2 };
 
 // ---------------------------------------------------------------- elementwise pieces ---
 
@@ -54,71 +52,63 @@ __device__ __forceinline__ double sign_np(double v) {
   return (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : ((v == 0.0) ? 0.0 : v));
 }
 
-// Sum over prior terms of d(chi)/dq_j at coordinate j (base.py:564-570, 703-710), plus
-// +inf when a gradient-visible bound check of this chain has fired (oob_mask).
+// d(chi)/dq of one prior term (base.py:564-570, 703-710)
+__device__ __forceinline__ double term_gradient(int kind, double a, double b, double q) {
+  return (kind == TERM_NORMAL) ? __dmul_rn(-b, __dsub_rn(a, q))           // -icov * (mu - q)
+                               : __dmul_rn(sign_np(__dsub_rn(q, a)), b);  // sign(q - mu) * idisp
+}
+// misfit contribution of one prior term, constants excluded (base.py:539-550, 689-700):
+// Normal 0.5*r*(icov*r), Laplace |q-mu|*idisp.
+__device__ __forceinline__ double term_misfit(int kind, double a, double b, double q) {
+  if (kind == TERM_NORMAL) {
+    const double d = __dsub_rn(a, q);
+    return __dmul_rn(0.5, __dmul_rn(d, __dmul_rn(b, d)));
+  }
+  return __dmul_rn(fabs(__dsub_rn(q, a)), b);
+}
+
+// Sum over prior terms of d(chi)/dq_j at coordinate j, plus +inf when a gradient-visible
+// bound check covering j has fired somewhere in this chain (oob_mask).
 __device__ __forceinline__ double prior_gradient(const DevTarget& T, int j, double q,
                                                  unsigned oob_mask) {
   double g = 0.0;
-#pragma unroll 1
-  for (int t = 0; t < T.n_priors; ++t) {
-    const PriorTerm& P = T.prior[t];
-    const unsigned r = (unsigned)(j - P.offset);
-    if (r < (unsigned)P.len) {
-      const double a = __ldg(P.a + r), b = __ldg(P.b + r);
-      double term;
-      if (P.kind == 0) term = __dmul_rn(-b, __dsub_rn(a, q));          // -icov * (mu - q)
-      else             term = __dmul_rn(sign_np(__dsub_rn(q, a)), b);  // sign(q - mu) * idisp
-      g = __dadd_rn(g, term);
-    }
+  for (int t = 0; t < T.n_terms; ++t) {
+    const size_t o = (size_t)t * T.dims + j;
+    const int kind = __ldg(T.t_kind + o);
+    if (kind) g = __dadd_rn(g, term_gradient(kind, __ldg(T.t_a + o), __ldg(T.t_b + o), q));
   }
   oob_mask &= T.grad_check_mask;
-  if (oob_mask) {
-#pragma unroll 1
-    for (int k = 0; k < T.n_checks; ++k)
-      if (((oob_mask >> k) & 1u) && (unsigned)(j - T.check[k].offset) < (unsigned)T.check[k].len)
-        g = __dadd_rn(g, CUDART_INF);
-  }
+  if (oob_mask && (oob_mask & __ldg(T.c_cover + j))) g = __dadd_rn(g, CUDART_INF);
   return g;
 }
 
-// Contribution of coordinate j to the prior misfit, constants excluded (base.py:539-550,
-// 689-700): Normal 0.5*r*(icov*r), Laplace |q-mu|*idisp.
+// Contribution of coordinate j to the prior misfit, constants excluded.
 __device__ __forceinline__ double prior_misfit(const DevTarget& T, int j, double q) {
   double s = 0.0;
-#pragma unroll 1
-  for (int t = 0; t < T.n_priors; ++t) {
-    const PriorTerm& P = T.prior[t];
-    const unsigned r = (unsigned)(j - P.offset);
-    if (r < (unsigned)P.len) {
-      const double a = __ldg(P.a + r), b = __ldg(P.b + r);
-      if (P.kind == 0) {
-        const double d = __dsub_rn(a, q);
-        s = __dadd_rn(s, __dmul_rn(0.5, __dmul_rn(d, __dmul_rn(b, d))));
-      } else {
-        s = __dadd_rn(s, __dmul_rn(fabs(__dsub_rn(q, a)), b));
-      }
-    }
+  for (int t = 0; t < T.n_terms; ++t) {
+    const size_t o = (size_t)t * T.dims + j;
+    const int kind = __ldg(T.t_kind + o);
+    if (kind) s = __dadd_rn(s, term_misfit(kind, __ldg(T.t_a + o), __ldg(T.t_b + o), q));
   }
   return s;
 }
 
 // Bit k set iff coordinate j violates bound check k (misfit_bounds, base.py:361-374).
+// NaN compares false on both sides, like numpy.
 __device__ __forceinline__ unsigned bound_violations(const DevTarget& T, int j, double q) {
   unsigned m = 0;
-#pragma unroll 1
   for (int k = 0; k < T.n_checks; ++k) {
-    const BoundCheck& B = T.check[k];
-    const unsigned r = (unsigned)(j - B.offset);
-    if (r < (unsigned)B.len) {
-      const bool low = B.lb && (q < __ldg(B.lb + r));
-      const bool high = B.ub && (q > __ldg(B.ub + r));
-      if (low || high) m |= (1u << k);
-    }
+    const size_t o = (size_t)k * T.dims + j;
+    if (q < __ldg(T.c_lb + o) || q > __ldg(T.c_ub + o)) m |= (1u << k);
   }
   return m;
 }
 
 // One-shot mirror reflection (base.py:258-270): the upper test sees the corrected q.
+__device__ __forceinline__ void reflect_on(double lb, double ub, double& q, double& p) {
+  if (q < lb) { q = __dadd_rn(q, __dmul_rn(2.0, __dsub_rn(lb, q))); p = -p; }
+  if (q > ub) { q = __dadd_rn(q, __dmul_rn(2.0, __dsub_rn(ub, q))); p = -p; }
+}
 __device__ __forceinline__ void reflect(const DevTarget& T, int j, double& q, double& p) {
   if (T.refl_lb) {
     const double lb = __ldg(T.refl_lb + j);
@@ -206,13 +196,19 @@ __device__ __forceinline__ void uniform_pair(uint64_t seed, uint32_t chain, uint
 // A chain is owned by TPC consecutive threads (TPC a power of two).  TPC <= 32: the group
 // lives inside one warp and reduces with xor-shuffles (every lane ends with the same
 // bits because each butterfly level adds the same two numbers on both partners).
-// TPC > 32: TPC == blockDim.x (one chain per block); warps reduce, then every thread
-// sums the per-warp partials in warp order.  Summation order is fixed => deterministic.
+// TPC > 32: the chain spans TPC/32 whole warps of the block (several chains may share a
+// block); warps reduce, then every thread sums its chain's per-warp partials in warp
+// order through a per-chain shared-memory segment.  Summation order is fixed =>
+// deterministic.
 
 template <int TPC>
 struct ChainReduce {
   static constexpr int kWarps = (TPC + 31) / 32;
-  double* scratch;  // >= 3 * kWarps doubles of shared memory (TPC > 32 only)
+  // shared-memory doubles a block of BLOCK threads needs (TPC > 32 only)
+  __host__ __device__ static constexpr int scratch_doubles(int block) { return TPC > 32 ? 3 * kWarps * (block / TPC) + 1 : 1; }
+  double* scratch;
+
+  __device__ __forceinline__ double* mine() const { return scratch + (threadIdx.x / TPC) * (3 * kWarps); }
 
   __device__ __forceinline__ void sum3(double& a, double& b, double& c) const {
     constexpr int W = TPC < 32 ? TPC : 32;
@@ -223,17 +219,18 @@ struct ChainReduce {
       c = __dadd_rn(c, __shfl_xor_sync(0xffffffffu, c, off));
     }
     if constexpr (TPC > 32) {
-      const int warp = threadIdx.x >> 5;
+      double* s = mine();
+      const int warp = (threadIdx.x % TPC) >> 5;  // warp index inside the chain
       if ((threadIdx.x & 31) == 0) {
-        scratch[warp] = a; scratch[kWarps + warp] = b; scratch[2 * kWarps + warp] = c;
+        s[warp] = a; s[kWarps + warp] = b; s[2 * kWarps + warp] = c;
       }
       __syncthreads();
       a = 0.0; b = 0.0; c = 0.0;
 #pragma unroll 4
       for (int w = 0; w < kWarps; ++w) {
-        a = __dadd_rn(a, scratch[w]);
-        b = __dadd_rn(b, scratch[kWarps + w]);
-        c = __dadd_rn(c, scratch[2 * kWarps + w]);
+        a = __dadd_rn(a, s[w]);
+        b = __dadd_rn(b, s[kWarps + w]);
+        c = __dadd_rn(c, s[2 * kWarps + w]);
       }
       __syncthreads();
     }
@@ -244,8 +241,8 @@ struct ChainReduce {
 #pragma unroll
     for (int off = W / 2; off > 0; off >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, off);
     if constexpr (TPC > 32) {
-      unsigned* s = reinterpret_cast<unsigned*>(scratch);
-      const int warp = threadIdx.x >> 5;
+      unsigned* s = reinterpret_cast<unsigned*>(mine());
+      const int warp = (threadIdx.x % TPC) >> 5;
       if ((threadIdx.x & 31) == 0) s[warp] = m;
       __syncthreads();
       m = 0;

@@ -43,13 +43,20 @@ struct FusedArgs {
 
 // ------------------------------------------------------------------- priors only ---
 // Thread t of a chain owns coordinate pairs m = t + i*TPC (i < PPT): coordinates 2m, 2m+1.
-template <int TPC, int PPT>
+// Everything that depends only on the coordinate (prior parameters, and with AUX the
+// reflection bounds and the mass matrix) is loaded into registers once; the trajectory
+// loop is pure fp64 arithmetic.  Padding coordinates (>= dims) carry q = p = 0 and a
+// "none" prior, so they add exact zeros to every reduction and need no predicates.
+// Supports at most one prior term per coordinate (T.n_terms <= 1); AUX = false requires
+// a unit mass matrix and no reflection bounds.
+template <int TPC, int PPT, bool AUX>
 __global__ void __launch_bounds__((TPC < 256 ? 256 : TPC))
 hmc_fused_priors_kernel(const FusedArgs A) {
   constexpr int BLOCK = TPC < 256 ? 256 : TPC;
   constexpr int CPB = BLOCK / TPC;  // chains per block
   constexpr int E = 2 * PPT;        // coordinates per thread
-  __shared__ double scratch[3 * ((TPC + 31) / 32) + 1];
+  constexpr int EA = AUX ? E : 1;
+  __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(BLOCK)];
   const ChainReduce<TPC> red{scratch};
   const DevTarget& T = A.T;
   const int d = T.dims;
@@ -62,8 +69,9 @@ hmc_fused_priors_kernel(const FusedArgs A) {
   const size_t C = (size_t)A.chains;
 
   int jj[E];
-  bool ok[E];
-  double qc[E], q[E], p[E];
+  unsigned okmask = 0, kinds = 0;
+  double qc[E], q[E], p[E], ta[E], tb[E];
+  double rlb[EA], rub[EA], im[EA], sm[EA];
 #pragma unroll
   for (int i = 0; i < PPT; ++i) {
     const int m = t + i * TPC;
@@ -71,9 +79,34 @@ hmc_fused_priors_kernel(const FusedArgs A) {
   }
 #pragma unroll
   for (int e = 0; e < E; ++e) {
-    ok[e] = jj[e] < d;
-    qc[e] = ok[e] ? A.q[row + jj[e]] : 0.0;
+    const bool ok = jj[e] < d;
+    if (ok) okmask |= 1u << e;
+    qc[e] = ok ? A.q[row + jj[e]] : 0.0;
+    ta[e] = 0.0; tb[e] = 0.0;
+    if (ok && T.n_terms > 0) {
+      kinds |= (unsigned)T.t_kind[jj[e]] << (2 * e);
+      ta[e] = T.t_a[jj[e]]; tb[e] = T.t_b[jj[e]];
+    }
+    if constexpr (AUX) {
+      rlb[e] = (ok && T.refl_lb) ? T.refl_lb[jj[e]] : -CUDART_INF;
+      rub[e] = (ok && T.refl_ub) ? T.refl_ub[jj[e]] : CUDART_INF;
+      im[e] = (ok && T.invm) ? T.invm[jj[e]] : 1.0;
+      sm[e] = (ok && T.sqrtm) ? T.sqrtm[jj[e]] : 1.0;
+    }
   }
+  const bool has_mass = AUX && T.invm != nullptr;
+  const bool has_refl = AUX && (T.refl_lb != nullptr || T.refl_ub != nullptr);
+  auto ok = [&](int e) { return (okmask >> e) & 1u; };
+  auto kind_of = [&](int e) { return (int)((kinds >> (2 * e)) & 3u); };
+  auto dkdp = [&](int e) { return has_mass ? __dmul_rn(im[AUX ? e : 0], p[e]) : p[e]; };
+  auto violations = [&]() {
+    unsigned m = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (ok(e)) m |= bound_violations(T, jj[e], q[e]);
+    return red.any_bits(m);
+  };
+
   double x = A.x[c];
   int accepted = 0;
   const bool grad_checks = T.grad_check_mask != 0u;
@@ -84,9 +117,13 @@ hmc_fused_priors_kernel(const FusedArgs A) {
 
     // ---- draws -------------------------------------------------------------------
     double u_step, u_acc;
-    uniform_pair(A.seed, (uint32_t)(A.chain_offset + c), (uint32_t)kglob, u_step, u_acc);
-    if (A.u_step_in) u_step = A.u_step_in[kc];
-    if (A.u_accept_in) u_acc = A.u_accept_in[kc];
+    if (A.u_step_in && A.u_accept_in) {
+      u_step = A.u_step_in[kc]; u_acc = A.u_accept_in[kc];
+    } else {
+      uniform_pair(A.seed, (uint32_t)(A.chain_offset + c), (uint32_t)kglob, u_step, u_acc);
+      if (A.u_step_in) u_step = A.u_step_in[kc];
+      if (A.u_accept_in) u_acc = A.u_accept_in[kc];
+    }
     const double eps = A.randomize ? __dmul_rn(u_step, A.stepsize) : A.stepsize;
 
 #pragma unroll
@@ -94,11 +131,13 @@ hmc_fused_priors_kernel(const FusedArgs A) {
       double z0, z1;
       if (A.z_in) {
         const double* zr = A.z_in + kc * d;
-        z0 = ok[2 * i] ? zr[jj[2 * i]] : 0.0;
-        z1 = ok[2 * i + 1] ? zr[jj[2 * i + 1]] : 0.0;
+        z0 = ok(2 * i) ? zr[jj[2 * i]] : 0.0;
+        z1 = ok(2 * i + 1) ? zr[jj[2 * i + 1]] : 0.0;
       } else {
         normal_pair(A.seed, (uint32_t)(A.chain_offset + c), (uint32_t)kglob,
                     (uint32_t)(t + i * TPC), z0, z1);
+        if (!ok(2 * i)) z0 = 0.0;
+        if (!ok(2 * i + 1)) z1 = 0.0;
       }
       p[2 * i] = z0; p[2 * i + 1] = z1;
     }
@@ -106,44 +145,36 @@ hmc_fused_priors_kernel(const FusedArgs A) {
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       q[e] = qc[e];
-      if (ok[e]) {
-        if (T.sqrtm) p[e] = __dmul_rn(__ldg(T.sqrtm + jj[e]), p[e]);
-        k0 = __dadd_rn(k0, kinetic_term(T, jj[e], p[e]));
-      } else {
-        p[e] = 0.0;
-      }
+      if (has_mass) p[e] = __dmul_rn(sm[AUX ? e : 0], p[e]);
+      k0 = __dadd_rn(k0, __dmul_rn(p[e], dkdp(e)));
     }
 
     // ---- trajectory --------------------------------------------------------------
     int gi = 0;
     auto run_op = [&](const StageOp& op) {
       if (op.has_b) {
-        unsigned oob = 0;
-        if (grad_checks) {
-#pragma unroll
-          for (int e = 0; e < E; ++e)
-            if (ok[e]) oob |= bound_violations(T, jj[e], q[e]);
-          oob = red.any_bits(oob);
-        }
+        const unsigned oob = grad_checks ? (violations() & T.grad_check_mask) : 0u;
         const double cb = __dmul_rn(op.b, eps);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-          if (ok[e]) {
-            const double g = prior_gradient(T, jj[e], q[e], oob);
-            if (A.trace_q && live) {
-              const size_t o = (((size_t)kb * A.S.grads_per_proposal + gi) * C + c) * d + jj[e];
-              A.trace_q[o] = q[e];
-              A.trace_g[o] = g;
-            }
-            momentum_update(cb, g, p[e]);
+          const int kind = kind_of(e);
+          double g = kind ? term_gradient(kind, ta[e], tb[e], q[e]) : 0.0;
+          if (oob && ok(e) && (oob & T.c_cover[jj[e]])) g = __dadd_rn(g, CUDART_INF);
+          if (A.trace_q && live && ok(e)) {
+            const size_t o = (((size_t)kb * A.S.grads_per_proposal + gi) * C + c) * d + jj[e];
+            A.trace_q[o] = q[e];
+            A.trace_g[o] = g;
           }
+          momentum_update(cb, g, p[e]);
         }
         ++gi;
       }
       const double ca = __dmul_rn(op.a, eps);
 #pragma unroll
-      for (int e = 0; e < E; ++e)
-        if (ok[e]) position_update(T, jj[e], ca, q[e], p[e]);
+      for (int e = 0; e < E; ++e) {
+        q[e] = __dadd_rn(q[e], __dmul_rn(ca, dkdp(e)));
+        if (has_refl) reflect_on(rlb[AUX ? e : 0], rub[AUX ? e : 0], q[e], p[e]);
+      }
     };
     for (int s = 0; s < A.S.n_pre; ++s) run_op(A.S.pre[s]);
     for (int r = 0; r < A.S.reps; ++r)
@@ -152,17 +183,14 @@ hmc_fused_priors_kernel(const FusedArgs A) {
 
     // ---- energies and decision ----------------------------------------------------
     double k1 = 0.0, u1 = 0.0;
-    unsigned oob = 0;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      if (ok[e]) {
-        k1 = __dadd_rn(k1, kinetic_term(T, jj[e], p[e]));
-        u1 = __dadd_rn(u1, prior_misfit(T, jj[e], q[e]));
-        oob |= bound_violations(T, jj[e], q[e]);
-      }
+      k1 = __dadd_rn(k1, __dmul_rn(p[e], dkdp(e)));
+      const int kind = kind_of(e);
+      if (kind) u1 = __dadd_rn(u1, term_misfit(kind, ta[e], tb[e], q[e]));
     }
     red.sum3(k0, k1, u1);
-    if (T.n_checks) oob = red.any_bits(oob);
+    const unsigned oob = T.n_checks ? violations() : 0u;
     double x1 = __dadd_rn(u1, T.const_sum);
     if (oob) x1 = __dadd_rn(x1, CUDART_INF);
     const double h0 = __dadd_rn(x, __dmul_rn(0.5, k0));
@@ -173,7 +201,7 @@ hmc_fused_priors_kernel(const FusedArgs A) {
       if (A.out_q_prop) {
 #pragma unroll
         for (int e = 0; e < E; ++e)
-          if (ok[e]) {
+          if (ok(e)) {
             A.out_q_prop[kc * d + jj[e]] = q[e];
             A.out_p_prop[kc * d + jj[e]] = p[e];
           }
@@ -195,7 +223,7 @@ hmc_fused_priors_kernel(const FusedArgs A) {
                           (size_t)(d + 1);
 #pragma unroll
       for (int e = 0; e < E; ++e)
-        if (ok[e]) A.out_samples[srow + jj[e]] = qc[e];
+        if (ok(e)) A.out_samples[srow + jj[e]] = qc[e];
       if (t == 0) A.out_samples[srow + d] = x;
     }
   }
@@ -203,7 +231,7 @@ hmc_fused_priors_kernel(const FusedArgs A) {
   if (live) {
 #pragma unroll
     for (int e = 0; e < E; ++e)
-      if (ok[e]) A.q[row + jj[e]] = qc[e];
+      if (ok(e)) A.q[row + jj[e]] = qc[e];
     if (t == 0) {
       A.x[c] = x;
       if (A.accepted_total) A.accepted_total[c] += accepted;
@@ -219,7 +247,7 @@ prior_misfit_kernel(const DevTarget T, int chains, const double* __restrict__ q,
                     double* __restrict__ x, const double* __restrict__ lik_misfit) {
   constexpr int BLOCK = TPC < 256 ? 256 : TPC;
   constexpr int CPB = BLOCK / TPC;
-  __shared__ double scratch[3 * ((TPC + 31) / 32) + 1];
+  __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(BLOCK)];
   const ChainReduce<TPC> red{scratch};
   const int t = threadIdx.x % TPC;
   int c = blockIdx.x * CPB + threadIdx.x / TPC;
@@ -248,7 +276,7 @@ prior_gradient_kernel(const DevTarget T, int chains, const double* __restrict__ 
                       double* __restrict__ g, int accumulate) {
   constexpr int BLOCK = TPC < 256 ? 256 : TPC;
   constexpr int CPB = BLOCK / TPC;
-  __shared__ double scratch[3 * ((TPC + 31) / 32) + 1];
+  __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(BLOCK)];
   const ChainReduce<TPC> red{scratch};
   const int t = threadIdx.x % TPC;
   int c = blockIdx.x * CPB + threadIdx.x / TPC;
@@ -297,7 +325,7 @@ kinetic_energy_kernel(const DevTarget T, int chains, const double* __restrict__ 
                       double* __restrict__ k) {
   constexpr int BLOCK = TPC < 256 ? 256 : TPC;
   constexpr int CPB = BLOCK / TPC;
-  __shared__ double scratch[3 * ((TPC + 31) / 32) + 1];
+  __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(BLOCK)];
   const ChainReduce<TPC> red{scratch};
   const int t = threadIdx.x % TPC;
   int c = blockIdx.x * CPB + threadIdx.x / TPC;

@@ -610,22 +610,46 @@ int hmcb_finalize(hmcb_engine* e) {
   DevTarget& T = e->T;
   std::memset(&T, 0, sizeof(T));
   T.dims = d;
-  T.n_priors = (int)e->priors.size();
   T.n_checks = (int)e->checks.size();
-  double const_sum = 0.0;
-  for (int t = 0; t < T.n_priors; ++t) {
-    const HostPrior& P = e->priors[t];
-    T.prior[t].kind = P.kind; T.prior[t].offset = (int)P.offset; T.prior[t].len = (int)P.len;
-    if (dev_upload(e, P.a, &T.prior[t].a) || dev_upload(e, P.b, &T.prior[t].b)) return -1;
-    const_sum += P.constant;
-  }
-  T.const_sum = const_sum;
-  for (int k = 0; k < T.n_checks; ++k) {
-    const HostCheck& Ck = e->checks[k];
-    T.check[k].offset = (int)Ck.offset; T.check[k].len = (int)Ck.len; T.check[k].in_gradient = Ck.in_gradient;
-    if (Ck.has_lb && dev_upload(e, Ck.lb, &T.check[k].lb)) return -1;
-    if (Ck.has_ub && dev_upload(e, Ck.ub, &T.check[k].ub)) return -1;
-    if (Ck.in_gradient) T.grad_check_mask |= (1u << k);
+  {
+    // per-coordinate prior-term table: slot t of coordinate j = t-th term covering j
+    std::vector<int> used((size_t)d, 0);
+    int n_terms = 0;
+    for (const HostPrior& P : e->priors)
+      for (int64_t r = 0; r < P.len; ++r) n_terms = std::max(n_terms, ++used[(size_t)(P.offset + r)]);
+    T.n_terms = n_terms;
+    std::vector<unsigned char> kind((size_t)std::max(n_terms, 1) * d, (unsigned char)TERM_NONE);
+    std::vector<double> ta(kind.size(), 0.0), tb(kind.size(), 0.0);
+    std::fill(used.begin(), used.end(), 0);
+    double const_sum = 0.0;
+    for (const HostPrior& P : e->priors) {
+      for (int64_t r = 0; r < P.len; ++r) {
+        const size_t j = (size_t)(P.offset + r);
+        const size_t o = (size_t)used[j]++ * d + j;
+        kind[o] = (unsigned char)(P.kind == HMCB_PRIOR_NORMAL ? TERM_NORMAL : TERM_LAPLACE);
+        ta[o] = P.a[(size_t)r];
+        tb[o] = P.b[(size_t)r];
+      }
+      const_sum += P.constant;
+    }
+    T.const_sum = const_sum;
+    if (dev_upload(e, kind, &T.t_kind) || dev_upload(e, ta, &T.t_a) || dev_upload(e, tb, &T.t_b)) return -1;
+    // bound checks: -inf / +inf where a check does not apply
+    const double inf = std::numeric_limits<double>::infinity();
+    const size_t nc = (size_t)std::max(T.n_checks, 1);
+    std::vector<double> clb(nc * d, -inf), cub(nc * d, inf);
+    std::vector<unsigned char> cover((size_t)d, 0);
+    for (int k = 0; k < T.n_checks; ++k) {
+      const HostCheck& Ck = e->checks[k];
+      for (int64_t r = 0; r < Ck.len; ++r) {
+        const size_t j = (size_t)(Ck.offset + r);
+        if (Ck.has_lb) clb[(size_t)k * d + j] = Ck.lb[(size_t)r];
+        if (Ck.has_ub) cub[(size_t)k * d + j] = Ck.ub[(size_t)r];
+        cover[j] |= (unsigned char)(1u << k);
+      }
+      if (Ck.in_gradient) T.grad_check_mask |= (1u << k);
+    }
+    if (dev_upload(e, clb, &T.c_lb) || dev_upload(e, cub, &T.c_ub) || dev_upload(e, cover, &T.c_cover)) return -1;
   }
   if (e->has_rlb && dev_upload(e, e->rlb, &T.refl_lb)) return -1;
   if (e->has_rub && dev_upload(e, e->rub, &T.refl_ub)) return -1;
@@ -644,7 +668,7 @@ int hmcb_finalize(hmcb_engine* e) {
     if (dev_upload(e, e->h_rx, &L.rx) || dev_upload(e, e->h_ry, &L.ry) || dev_upload(e, e->h_rz, &L.rz) ||
         dev_upload(e, e->h_tobs, &L.tobs) || dev_upload(e, e->h_std, &L.std))
       return -1;
-  } else if (e->lik == LK_NONE && fused_priors_supported(d) && !std::getenv("HMCB_FORCE_STAGED")) {
+  } else if (e->lik == LK_NONE && T.n_terms <= 1 && fused_priors_supported(d) && !std::getenv("HMCB_FORCE_STAGED")) {
     e->path = HMCB_PATH_FUSED_PRIORS;
   } else {
     e->path = HMCB_PATH_STAGED;

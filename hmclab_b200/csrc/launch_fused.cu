@@ -3,32 +3,39 @@
 #define HMCB_FUSED_AUX_KERNELS
 #include "launch.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace hmcb {
 
-static int pow2_ceil(int v) {
-  int p = 1;
-  while (p < v) p <<= 1;
-  return p;
+// Instantiated (TPC, PPT) shapes of the priors-only fused kernel: pairs = ceil(dims / 2)
+// coordinate pairs are spread over TPC threads x PPT pairs each.
+static const int kShapes[][2] = {{2, 1},   {8, 1},   {32, 1},  {64, 1},  {128, 1}, {512, 1}, {128, 2},
+                                 {256, 2}, {128, 4}, {64, 8},  {128, 8}, {256, 8}, {512, 8}};
+
+static bool shape_instantiated(int tpc, int ppt) {
+  for (const auto& sh : kShapes)
+    if (sh[0] == tpc && sh[1] == ppt) return true;
+  return false;
 }
 
-// pairs = ceil(dims / 2) coordinate pairs are spread over TPC threads x PPT pairs each.
-// Small targets use one pair per thread; larger ones 2..8 pairs per thread so that a
-// chain stays inside one block of at most 1024 threads.
 void fused_priors_shape(int dims, int* tpc, int* ppt) {
   const int pairs = (dims + 1) / 2;
-  int P = 1;
-  if (pairs > 64) {
-    P = pow2_ceil((pairs + 127) / 128);
-    if (P > 8) P = 8;
+  int T = 0, P = 0;
+  if (pairs <= 2) { T = 2; P = 1; }
+  else if (pairs <= 8) { T = 8; P = 1; }
+  else if (pairs <= 32) { T = 32; P = 1; }
+  else if (pairs <= 64) { T = 64; P = 1; }
+  else if (pairs <= 128) { T = 128; P = 1; }
+  else if (pairs <= 256) { T = 128; P = 2; }
+  else if (pairs <= 512) { T = 128; P = 4; }
+  else if (pairs <= 1024) { T = 128; P = 8; }
+  else if (pairs <= 2048) { T = 256; P = 8; }
+  else if (pairs <= 4096) { T = 512; P = 8; }
+  if (const char* env = std::getenv("HMCB_FUSED_SHAPE")) {  // tuning override "TPC,PPT"
+    int t = 0, p = 0;
+    if (std::sscanf(env, "%d,%d", &t, &p) == 2 && shape_instantiated(t, p) && t * p >= pairs) { T = t; P = p; }
   }
-  if (const char* env = std::getenv("HMCB_FUSED_PPT")) {
-    const int v = std::atoi(env);
-    if (v == 1 || v == 2 || v == 4 || v == 8) P = v;
-  }
-  int T = pow2_ceil((pairs + P - 1) / P);
-  if (P > 1 && T < 64) T = 64;
   *tpc = T;
   *ppt = P;
 }
@@ -36,7 +43,7 @@ void fused_priors_shape(int dims, int* tpc, int* ppt) {
 bool fused_priors_supported(int dims) {
   int t, p;
   fused_priors_shape(dims, &t, &p);
-  return p == 8 ? t <= 512 : t <= 1024;  // register budget of the widest shapes
+  return t > 0;
 }
 
 // One translation unit per PPT (launch_fused_ppt.cu compiled with -DHMCB_PPT=n).
@@ -48,6 +55,7 @@ cudaError_t launch_fused_priors_ppt8(const FusedArgs& A, int tpc, cudaStream_t s
 cudaError_t launch_fused_priors(const FusedArgs& A, cudaStream_t s) {
   int tpc, ppt;
   fused_priors_shape(A.T.dims, &tpc, &ppt);
+  if (A.T.n_terms > 1) return cudaErrorInvalidConfiguration;
   switch (ppt) {
     case 1: return launch_fused_priors_ppt1(A, tpc, s);
     case 2: return launch_fused_priors_ppt2(A, tpc, s);

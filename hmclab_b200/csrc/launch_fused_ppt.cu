@@ -15,26 +15,33 @@ static cudaError_t launch_fp(const FusedArgs& A, cudaStream_t s) {
   constexpr int BLOCK = TPC < 256 ? 256 : TPC;
   constexpr int CPB = BLOCK / TPC;
   const int grid = (A.chains + CPB - 1) / CPB;
-  hmc_fused_priors_kernel<TPC, PPT><<<grid, BLOCK, 0, s>>>(A);
+  // AUX: reflection bounds and/or a diagonal mass matrix live in registers too
+  if (A.T.invm || A.T.refl_lb || A.T.refl_ub)
+    hmc_fused_priors_kernel<TPC, PPT, true><<<grid, BLOCK, 0, s>>>(A);
+  else
+    hmc_fused_priors_kernel<TPC, PPT, false><<<grid, BLOCK, 0, s>>>(A);
   return cudaGetLastError();
 }
 
 cudaError_t HMCB_CAT(launch_fused_priors_ppt, HMCB_PPT)(const FusedArgs& A, int tpc, cudaStream_t s) {
   switch (tpc) {
 #if HMCB_PPT == 1
-    case 1: return launch_fp<1, 1>(A, s);
     case 2: return launch_fp<2, 1>(A, s);
-    case 4: return launch_fp<4, 1>(A, s);
     case 8: return launch_fp<8, 1>(A, s);
-    case 16: return launch_fp<16, 1>(A, s);
     case 32: return launch_fp<32, 1>(A, s);
-#endif
-    case 64: return launch_fp<64, HMCB_PPT>(A, s);
-    case 128: return launch_fp<128, HMCB_PPT>(A, s);
-    case 256: return launch_fp<256, HMCB_PPT>(A, s);
-    case 512: return launch_fp<512, HMCB_PPT>(A, s);
-#if HMCB_PPT <= 4
-    case 1024: return launch_fp<1024, HMCB_PPT>(A, s);
+    case 64: return launch_fp<64, 1>(A, s);
+    case 128: return launch_fp<128, 1>(A, s);
+    case 512: return launch_fp<512, 1>(A, s);
+#elif HMCB_PPT == 2
+    case 128: return launch_fp<128, 2>(A, s);
+    case 256: return launch_fp<256, 2>(A, s);
+#elif HMCB_PPT == 4
+    case 128: return launch_fp<128, 4>(A, s);
+#elif HMCB_PPT == 8
+    case 64: return launch_fp<64, 8>(A, s);
+    case 128: return launch_fp<128, 8>(A, s);
+    case 256: return launch_fp<256, 8>(A, s);
+    case 512: return launch_fp<512, 8>(A, s);
 #endif
   }
   return cudaErrorInvalidConfiguration;

@@ -149,7 +149,7 @@ template <int TPC, int LPE>
 __global__ void __launch_bounds__((TPC <= 32 ? 256 : TPC))
 hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
   extern __shared__ double dyn_smem[];
-  __shared__ double scratch[3 * ((TPC + 31) / 32) + 1];
+  __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(TPC <= 32 ? 256 : TPC)];
   const ChainReduce<TPC> red{scratch};
   const SrcLocShared M = srcloc_stage(L, dyn_smem);
   const DevTarget& T = A.T;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__((TPC <= 32 ? 256 : TPC))
 srcloc_eval_kernel(const DevTarget T, const SrcLocDev L, int chains, int mode,
                    const double* __restrict__ qin, double* __restrict__ out) {
   extern __shared__ double dyn_smem[];
-  __shared__ double scratch[3 * ((TPC + 31) / 32) + 1];
+  __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(TPC <= 32 ? 256 : TPC)];
   const ChainReduce<TPC> red{scratch};
   const SrcLocShared M = srcloc_stage(L, dyn_smem);
   const int d = T.dims, E = L.events;
