@@ -1,0 +1,427 @@
+"""Batched Hamiltonian Monte Carlo behind the reference's sampler API.
+
+``HMC().sample(...)`` keeps the signature, argument meaning, validation and error
+behaviour of ``hmclab.Samplers.HMC.sample`` (hmclab/Samplers.py:1180-1311, 321-479,
+1313-1417) and adds ``chains=`` (and a few batching knobs).  What the reference does in a
+per-proposal Python loop (``_sample_loop`` :579-587, ``_propose`` :1463, integrators
+:1524-1726, ``_evaluate_acceptance`` :1471) runs on the GPU in blocks of proposals for all
+chains at once through the C ABI (``include/hmcb.h``); between blocks the host streams the
+stored samples to the reference's ``Samples`` file format and checks ``max_time`` and
+Ctrl-C, so an interrupted run leaves a valid file exactly like the reference
+(:684-704).
+
+Not offered on this path (they raise): ``autotuning`` (Samplers.py:1494-1522, a "next"
+item) and ``diagnostic_mode`` (the per-function timers make no sense for fused kernels;
+use ``get_diagnostics()`` for block-level timings).
+"""
+from __future__ import annotations
+
+import time as _time
+from datetime import datetime as _datetime
+from typing import Optional
+
+import numpy as _numpy
+
+from hmclab_b200 import parallel as _parallel
+from hmclab_b200.Distributions.base import _AbstractDistribution
+from hmclab_b200.MassMatrices import Unit as _Unit
+from hmclab_b200.MassMatrices import _AbstractMassMatrix
+from hmclab_b200.Samples import Samples as _Samples
+
+_SUPPORTED_DISTRIBUTIONS = ("Normal", "Laplace", "Uniform", "CompositeDistribution",
+                            "AdditiveDistribution", "BayesRule", "LinearMatrix",
+                            "_LinearMatrix_dense_forward_simple_covariance",
+                            "_LinearMatrix_sparse_forward_simple_covariance", "SourceLocation3D")
+
+
+def _is_distribution(obj) -> bool:
+    """Objects of this package, or genuine hmclab distributions (read by attribute name)."""
+    if isinstance(obj, _AbstractDistribution):
+        return True
+    return any(k.__name__ == "_AbstractDistribution" for k in type(obj).__mro__)
+
+
+def _is_mass_matrix(obj) -> bool:
+    if isinstance(obj, _AbstractMassMatrix):
+        return True
+    return any(k.__name__ == "_AbstractMassMatrix" for k in type(obj).__mro__)
+
+
+class HMC:
+    """Hamiltonian Monte Carlo over a batch of independent chains (hmclab/Samplers.py:1105)."""
+
+    name = "Hamiltonian Monte Carlo"
+    available_integrators = ["lf", "3s", "4s"]
+    integrators_full_names = {"lf": "leapfrog integrator", "3s": "three stage integrator",
+                              "4s": "four stage integrator"}
+
+    def __init__(self, seed=None):
+        # Samplers.py:316-319: one Generator per sampler.  It seeds the on-device counter RNG
+        # (Philox keyed by seed, global chain id, proposal) and, with ``host_rng=True``,
+        # supplies the draws itself in the reference's order.
+        self.seed = seed
+        self.rng = _numpy.random.default_rng(seed)
+        self.samples = None
+        self.accepted_proposals = 0
+        self.current_proposal = 0
+        self.amount_of_writes = 0
+        self.engine = None
+        self._timings = {}
+
+    # ------------------------------------------------------------------------- API ----
+    def sample(
+        self,
+        samples_filename: str,
+        distribution,
+        stepsize: float = 0.1,
+        randomize_stepsize: bool = True,
+        amount_of_steps: int = 10,
+        mass_matrix=None,
+        integrator: str = "lf",
+        initial_model: _numpy.ndarray = None,
+        proposals: int = 100,
+        online_thinning: int = 1,
+        diagnostic_mode: bool = False,
+        overwrite_existing_file: bool = False,
+        max_time: float = None,
+        autotuning: bool = False,
+        target_acceptance_rate: float = 0.65,
+        learning_rate: float = 0.75,
+        queue=None,
+        disable_progressbar=False,
+        *,
+        chains: Optional[int] = None,
+        block_proposals: Optional[int] = None,
+        host_rng: bool = False,
+        device: Optional[int] = None,
+        distributed: bool = False,
+        **kwargs,
+    ):
+        """Sample ``chains`` independent Markov chains of ``proposals`` proposals each.
+
+        Reference arguments: see hmclab/Samplers.py:1201-1287.  Additional arguments:
+
+        chains: number of chains (default: the number of rows of ``initial_model`` if it is
+            2-D ``[chains, dimensions]``, else 1).  All chains share the tuning settings.
+        block_proposals: proposals per device launch sequence / host hand-over.
+        host_rng: draw momenta, step-size factors and acceptance uniforms from
+            ``self.rng`` on the host in the reference's order (normal(d,1), uniform(0.5,1.5),
+            uniform(0,1) per proposal; chain c uses ``default_rng(seed + c)`` for c > 0).
+            With ``chains=1`` this reproduces a reference run with the same seed to
+            rounding.  Default: counter-based RNG on the device.
+        distributed: under an initialised ``torch.distributed`` group, shard ``chains``
+            over the ranks (one process per GPU); every rank writes ``<name>.rank<r><ext>``.
+        """
+        self.samples = None
+        try:
+            self._init_sampler(
+                samples_filename=samples_filename, distribution=distribution,
+                initial_model=initial_model, proposals=proposals,
+                online_thinning=online_thinning,
+                overwrite_existing_file=overwrite_existing_file, max_time=max_time,
+                disable_progressbar=disable_progressbar, diagnostic_mode=diagnostic_mode,
+                chains=chains, block_proposals=block_proposals, host_rng=host_rng,
+                device=device, distributed=distributed,
+                stepsize=stepsize, randomize_stepsize=randomize_stepsize,
+                amount_of_steps=amount_of_steps, mass_matrix=mass_matrix, integrator=integrator,
+                autotuning=autotuning, target_acceptance_rate=target_acceptance_rate,
+                learning_rate=learning_rate, **kwargs)
+        except Exception:
+            if self.samples is not None:
+                self.samples.close()
+            raise
+        self._sample_loop()
+        if queue is not None:
+            queue.put({"0": self._summary()})
+        return self
+
+    # ---------------------------------------------------------------------- set-up ----
+    def _init_sampler(self, samples_filename, distribution, initial_model, proposals,
+                      online_thinning, overwrite_existing_file, max_time, disable_progressbar,
+                      diagnostic_mode, chains, block_proposals, host_rng, device, distributed,
+                      **kwargs):
+        assert type(samples_filename) == str, (
+            f"First argument should be a string containing the path of the file to which to "
+            f"write samples. It was an object of type {type(samples_filename)}.")
+        assert _is_distribution(distribution), (
+            "The passed target distribution should be a derived class of _AbstractDistribution.")
+        self.distribution = distribution
+        assert type(distribution.dimensions) == int and distribution.dimensions > 0, (
+            "The passed target distribution should have an integer dimension larger than zero.")
+        self.dimensions = d = distribution.dimensions
+        assert type(proposals) == int and proposals > 0, (
+            "The amount of proposal requested (`proposals`) should be an integer number larger "
+            "than zero.")
+        self.proposals = proposals
+        assert type(online_thinning) == int and online_thinning > 0, (
+            "The amount of online thinning (`online_thinning`) should be an integer number "
+            "larger than zero.")
+        self.online_thinning = online_thinning
+        assert proposals % online_thinning == 0, (
+            "The amount of proposals (`proposals`) needs to be a multiple of the online "
+            "thinning (`online_thinning`) number, to prevent sample wastage.")
+        self.proposals_after_thinning = proposals // online_thinning
+        if diagnostic_mode:
+            raise NotImplementedError(
+                "diagnostic_mode wraps per-call Python functions in timers (Samplers.py:1386-1417); "
+                "the batched engine fuses those calls into kernels. Use get_diagnostics().")
+
+        # initial models: (d,), (d,1) -> one chain (or broadcast to `chains`); [C, d] -> C chains
+        if initial_model is None:
+            n_chains = 1 if chains is None else int(chains)
+            q0 = _numpy.zeros((n_chains, d))
+        else:
+            arr = _numpy.array(initial_model, dtype=_numpy.float64)
+            if arr.ndim == 2 and arr.shape[1] == d and arr.shape != (d, 1):
+                q0 = arr
+            else:
+                assert arr.size == d, (
+                    f"The initial model (`initial_model`) dimension is incompatible with the "
+                    f"target distribution. Supplied model shape: {arr.shape}."
+                    f"Required shape: {(d, 1)}")
+                q0 = arr.reshape(1, d)
+            n_chains = q0.shape[0] if chains is None else int(chains)
+            if q0.shape[0] == 1 and n_chains > 1:
+                q0 = _numpy.repeat(q0, n_chains, axis=0)
+            assert q0.shape[0] == n_chains, (
+                f"`initial_model` holds {q0.shape[0]} chains but chains={n_chains}.")
+        assert n_chains > 0, "`chains` should be an integer number larger than zero."
+        self.total_chains = n_chains
+
+        # chain sharding (one process per GPU)
+        self.rank, self.world_size = _parallel.world() if distributed else (0, 1)
+        lo, hi = _parallel.shard_range(n_chains, self.world_size, self.rank)
+        self.chain_offset, self.chains = lo, hi - lo
+        assert self.chains > 0, "more ranks than chains"
+        q0 = _numpy.ascontiguousarray(q0[lo:hi])
+        if self.world_size > 1:
+            import os
+
+            stem, ext = os.path.splitext(samples_filename)
+            samples_filename = f"{stem}.rank{self.rank}{ext}"
+        self.samples_filename = samples_filename
+        self.samples = _Samples(samples_filename, mode="w", overwrite=overwrite_existing_file)
+
+        if max_time is not None:
+            max_time = float(max_time)
+            assert max_time > 0.0, (
+                "The maximal runtime (`max_time`) should be a float larger than zero.")
+        self.max_time = max_time
+        self.disable_progressbar = disable_progressbar
+        self.host_rng = bool(host_rng)
+
+        self._init_sampler_specific(**kwargs)
+
+        # engine ---------------------------------------------------------------------------
+        import torch
+
+        from hmclab_b200._engine import Engine
+        from hmclab_b200._lowering import describe, describe_mass, flatten
+
+        self.engine = Engine(flatten(describe(distribution)), describe_mass(self.mass_matrix),
+                             self.chains, integrator=self.integrator,
+                             amount_of_steps=self.amount_of_steps, device=device)
+        self._torch = torch
+        self._q = torch.as_tensor(q0, dtype=torch.float64).to(self.engine.device).contiguous()
+        self._x = self.engine.misfit(self._q)
+        x0 = self._x.cpu().numpy()
+        assert not _numpy.isnan(x0).any(), "Initial position in model space gives NaN probability"
+        assert not _numpy.isinf(x0).any(), (
+            "Initial position in model space gives inf/-inf probability")
+        self.current_model = q0.T.copy()
+        self.current_x = float(x0[0]) if self.chains == 1 else x0
+        self.accepted_proposals = 0
+        self.accepted_proposals_per_chain = _numpy.zeros(self.chains, dtype=_numpy.int64)
+        self.amount_of_writes = 0
+        self.current_proposal = 0
+
+        # block size: whole stored rows, at most ~256 MiB of samples per block
+        row_bytes = self.chains * (d + 1) * 8
+        rows = max(1, min(self.proposals_after_thinning, (256 << 20) // row_bytes))
+        if block_proposals is not None:
+            assert type(block_proposals) == int and block_proposals > 0
+            rows = max(1, min(self.proposals_after_thinning, block_proposals // online_thinning))
+        self.block_proposals = rows * online_thinning
+
+        self.samples.allocate(self.chains, self.proposals_after_thinning, d)
+        self._write_tuning_settings()
+        self.samples.write_attribute("proposals", self.proposals)
+        self.samples.write_attribute("acceptance_rate", 0)
+        self.samples.write_attribute("online_thinning", self.online_thinning)
+        self.samples.write_attribute("start_time", _datetime.now().strftime("%d-%b-%Y (%H:%M:%S.%f)"))
+        self.samples.write_attribute("sampler", self.name)
+        self.samples.write_attribute("chain_offset", self.chain_offset)
+
+    def _init_sampler_specific(self, **kwargs):
+        for key in ("stepsize", "randomize_stepsize", "amount_of_steps", "mass_matrix",
+                    "integrator", "autotuning", "target_acceptance_rate", "learning_rate"):
+            setattr(self, key, kwargs.pop(key))
+        if len(kwargs) != 0:
+            raise TypeError(f"Unidentified argument(s) not applicable to sampler: {kwargs}")
+        if self.autotuning:
+            raise NotImplementedError(
+                "Step-size autotuning (Samplers.py:1494-1522) is not part of the batched path yet.")
+        self.stepsize = float(self.stepsize)
+        assert self.stepsize > 0.0, "Stepsize should be a float larger than zero."
+        assert type(self.amount_of_steps) == int, (
+            "The amount of steps (amount_of_steps) the HMC integrator should make should be an "
+            "integer.")
+        assert self.amount_of_steps > 0, (
+            "The amount of steps (amount_of_steps) the HMC integrator should make should be "
+            "larger than zero.")
+        if self.mass_matrix is None:
+            self.mass_matrix = _Unit(self.dimensions)
+        assert _is_mass_matrix(self.mass_matrix), (
+            "The passed mass matrix (mass_matrix) should be a class derived from "
+            "_AbstractMassMatrix.")
+        self.mass_matrix.rng = self.rng
+        assert self.mass_matrix.dimensions == self.dimensions, (
+            f"The passed mass matrix (mass_matrix) should have dimensions equal to the target "
+            f"distribution. Passed: {self.mass_matrix.dimensions}, required: {self.dimensions}.")
+        self.integrator = str(self.integrator)
+        if self.integrator not in self.available_integrators:
+            raise ValueError(f"Unknown integrator used. Choices are: {self.available_integrators}")
+
+    def _write_tuning_settings(self):
+        self.samples.write_attribute("stepsize", self.stepsize)
+        self.samples.write_attribute("amount_of_steps", self.amount_of_steps)
+        self.samples.write_attribute("mass_matrix", self.mass_matrix.name)
+        self.samples.write_attribute("integrator", self.integrators_full_names[self.integrator])
+
+    # ------------------------------------------------------------------- main loop ----
+    def _host_draws(self, k0, B):
+        """Draws for proposals [k0, k0+B) of every local chain, consumed in the reference's
+        per-proposal order from one Generator per chain."""
+        C, d = self.chains, self.dimensions
+        if not hasattr(self, "_chain_rngs"):
+            rngs = []
+            for c in range(C):
+                g = self.chain_offset + c
+                if g == 0:
+                    rngs.append(self.rng)
+                else:
+                    base = self.seed if isinstance(self.seed, (int, _numpy.integer)) else None
+                    rngs.append(_numpy.random.default_rng(None if base is None else base + g))
+            self._chain_rngs = rngs
+        z = _numpy.empty((B, C, d))
+        us = _numpy.ones((B, C))
+        ua = _numpy.empty((B, C))
+        for c, rng in enumerate(self._chain_rngs):
+            for k in range(B):
+                z[k, c] = rng.normal(size=(d, 1))[:, 0]
+                if self.randomize_stepsize:
+                    us[k, c] = rng.uniform(0.5, 1.5)
+                ua[k, c] = rng.uniform(0, 1)
+        return z, us, ua
+
+    def _sample_loop(self):
+        torch, eng = self._torch, self.engine
+        C, d, thin = self.chains, self.dimensions, self.online_thinning
+        dev = eng.device
+        rows_max = self.block_proposals // thin
+        dbuf = [torch.empty(rows_max, C, d + 1, dtype=torch.float64, device=dev) for _ in range(2)]
+        hbuf = [torch.empty(rows_max, C, d + 1, dtype=torch.float64).pin_memory() for _ in range(2)]
+        accepted = torch.zeros(C, dtype=torch.int32, device=dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [None, None]      # event: D2H of slot finished
+        pending = None             # (slot, rows) waiting to be written to disk
+        # the device RNG key: one draw from the sampler's Generator (reproducible per seed)
+        device_seed = int(self.rng.integers(0, 2**63 - 1)) if not self.host_rng else 0
+
+        self.start_time = _datetime.now()
+        t_start = _time.time()
+        done, nblock = 0, 0
+        self._timings = {"device_blocks_s": 0.0, "host_write_s": 0.0, "blocks": 0}
+
+        def drain(item):
+            slot, rows = item
+            copied[slot].synchronize()
+            t0 = _time.time()
+            self.samples.write_block(hbuf[slot][:rows].numpy())
+            self.amount_of_writes += rows
+            self._timings["host_write_s"] += _time.time() - t0
+
+        try:
+            while done < self.proposals:
+                B = min(self.block_proposals, self.proposals - done)
+                rows = B // thin
+                slot = nblock & 1
+                draws = {}
+                if self.host_rng:
+                    z, us, ua = self._host_draws(done, B)
+                    draws = dict(z=torch.as_tensor(z).to(dev), u_step=torch.as_tensor(us).to(dev),
+                                 u_accept=torch.as_tensor(ua).to(dev))
+                if copied[slot] is not None:
+                    torch.cuda.current_stream(dev).wait_event(copied[slot])
+                t0 = _time.time()
+                eng.run_block(self._q, self._x, B, stepsize=self.stepsize,
+                              randomize_stepsize=self.randomize_stepsize, thinning=thin,
+                              proposal_offset=done, chain_offset=self.chain_offset, seed=device_seed,
+                              out_samples=dbuf[slot][:rows], accepted_total=accepted, **draws)
+                produced = torch.cuda.Event()
+                produced.record(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(produced)
+                    hbuf[slot][:rows].copy_(dbuf[slot][:rows], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                copied[slot] = ev
+                # while the GPU works on this block, put the previous one on disk
+                if pending is not None:
+                    drain(pending)
+                pending = (slot, rows)
+                produced.synchronize()
+                self._timings["device_blocks_s"] += _time.time() - t0
+                self._timings["blocks"] += 1
+                done += B
+                nblock += 1
+                self.current_proposal = done - 1
+                if self.max_time is not None and _time.time() - t_start > self.max_time:
+                    raise TimeoutError
+        except KeyboardInterrupt:
+            pass  # Samplers.py:688-699: keep what was sampled, close the file cleanly
+        except TimeoutError:
+            pass
+        finally:
+            if pending is not None:
+                drain(pending)
+            torch.cuda.synchronize(dev)
+            self.end_time = _datetime.now()
+            self._close_sampler(accepted)
+
+    def _close_sampler(self, accepted):
+        per_chain = accepted.cpu().numpy().astype(_numpy.int64)
+        x_local = self._x
+        if self.world_size > 1:
+            acc_all, x_all = _parallel.gather_diagnostics(accepted, self._x, self.total_chains)
+            self.accepted_proposals_all_chains = acc_all.cpu().numpy().astype(_numpy.int64)
+            self.current_x_all_chains = x_all.cpu().numpy()
+        self.accepted_proposals_per_chain = per_chain
+        self.accepted_proposals = int(per_chain.sum())
+        q = self._q.cpu().numpy()
+        x = x_local.cpu().numpy()
+        self.current_model = q.T.copy()
+        self.current_x = float(x[0]) if self.chains == 1 else x
+        n_done = self.current_proposal + 1
+        self.samples.write_attribute("acceptance_rate",
+                                     self.accepted_proposals / max(1, n_done * self.chains))
+        self.samples.write_attribute("end_time", self.end_time.strftime("%d-%b-%Y (%H:%M:%S.%f)"))
+        self.samples.write_attribute("runtime", str(self.end_time - self.start_time))
+        self.samples.write_attribute("runtime_seconds",
+                                     (self.end_time - self.start_time).total_seconds())
+        self.samples.close()
+
+    # ------------------------------------------------------------------ reporting ----
+    def load_results(self, burn_in: int = 0) -> _numpy.ndarray:
+        """Samples.py reader on the file just written (Samplers.py:766-774)."""
+        with _Samples(self.samples_filename, burn_in=burn_in) as s:
+            return _numpy.array(s.numpy)
+
+    def get_diagnostics(self):
+        return dict(self._timings, launches=self.engine.launch_count if self.engine else 0,
+                    path=self.engine.path if self.engine else None)
+
+    def _summary(self):
+        return {"proposals": self.proposals, "chains": self.chains,
+                "acceptance_rate": self.accepted_proposals / max(1, (self.current_proposal + 1) * self.chains),
+                "path": self.engine.path if self.engine else None}

@@ -29,6 +29,7 @@ struct DevTarget {
   int dims;
   int n_terms;   // max number of prior terms covering one coordinate
   int n_checks;
+  int uniform_kind;  // TERM_* when every coordinate has exactly one prior term of this kind, else 0
   unsigned grad_check_mask;  // bit k set: check k adds +inf to the gradient on its range
   double const_sum;          // sum of the priors' normalisation constants
   const unsigned char* t_kind;  // [n_terms x dims]
@@ -269,10 +270,40 @@ struct StageOp {
 struct Schedule {
   int n_pre, n_body, reps, n_post;
   int grads_per_proposal;
-  int pad;
+  int kind;  // 0 lf, 1 3s, 2 4s (HMCB_INTEGRATOR_*)
   StageOp pre[2];
   StageOp body[6];
   StageOp post[2];
 };
+
+// Runs one trajectory with the integrator's stage sequence laid out at compile time, so
+// the per-stage work is straight-line code: `pos(ca)` is a position sub-step
+// q += ca * dK/dp (+ reflection), `mom(cb)` a momentum sub-step p -= cb * grad(q).
+// Coefficients are the host's multipliers times the chain's step size, formed exactly as
+// the reference forms them (Samplers.py:1539, 1562-1569, 1588-1603, 1666-1679).
+template <class Mom, class Pos>
+__device__ __forceinline__ void run_schedule(const Schedule& S, double eps, Mom&& mom, Pos&& pos) {
+  if (S.kind == 0) {
+    const double half = __dmul_rn(S.pre[0].a, eps);
+    const double cb = __dmul_rn(S.body[0].b, eps), ca = __dmul_rn(S.body[0].a, eps);
+    pos(half);
+    for (int r = 0; r < S.reps; ++r) { mom(cb); pos(ca); }
+    mom(__dmul_rn(S.post[0].b, eps));
+    pos(__dmul_rn(S.post[0].a, eps));
+  } else if (S.kind == 1) {
+    const double a1 = __dmul_rn(S.body[0].a, eps), b1 = __dmul_rn(S.body[1].b, eps);
+    const double a2 = __dmul_rn(S.body[1].a, eps), b2 = __dmul_rn(S.body[2].b, eps);
+    for (int r = 0; r < S.reps; ++r) {
+      pos(a1); mom(b1); pos(a2); mom(b2); pos(a2); mom(b1); pos(a1);
+    }
+  } else {
+    const double a1 = __dmul_rn(S.body[0].a, eps), b1 = __dmul_rn(S.body[1].b, eps);
+    const double a2 = __dmul_rn(S.body[1].a, eps), b2 = __dmul_rn(S.body[2].b, eps);
+    const double a3 = __dmul_rn(S.body[2].a, eps);
+    for (int r = 0; r < S.reps; ++r) {
+      pos(a1); mom(b1); pos(a2); mom(b2); pos(a3); mom(b2); pos(a2); mom(b1); pos(a1);
+    }
+  }
+}
 
 }  // namespace hmcb

@@ -50,7 +50,7 @@ struct FusedArgs {
 // Supports at most one prior term per coordinate (T.n_terms <= 1); AUX = false requires
 // a unit mass matrix and no reflection bounds.
 template <int TPC, int PPT, bool AUX>
-__global__ void __launch_bounds__((TPC < 256 ? 256 : TPC))
+__global__ void __launch_bounds__((TPC < 256 ? 256 : TPC), ((TPC <= 256 && PPT < 4) ? 2 : 1))
 hmc_fused_priors_kernel(const FusedArgs A) {
   constexpr int BLOCK = TPC < 256 ? 256 : TPC;
   constexpr int CPB = BLOCK / TPC;  // chains per block
@@ -70,8 +70,8 @@ hmc_fused_priors_kernel(const FusedArgs A) {
 
   int jj[E];
   unsigned okmask = 0, kinds = 0;
-  double qc[E], q[E], p[E], ta[E], tb[E];
-  double rlb[EA], rub[EA], im[EA], sm[EA];
+  double qc[E], q[E], p[E] = {}, ta[E], tb[E];
+  double rlb[EA] = {}, rub[EA] = {}, im[EA] = {}, sm[EA] = {};
 #pragma unroll
   for (int i = 0; i < PPT; ++i) {
     const int m = t + i * TPC;
@@ -98,7 +98,10 @@ hmc_fused_priors_kernel(const FusedArgs A) {
   const bool has_refl = AUX && (T.refl_lb != nullptr || T.refl_ub != nullptr);
   auto ok = [&](int e) { return (okmask >> e) & 1u; };
   auto kind_of = [&](int e) { return (int)((kinds >> (2 * e)) & 3u); };
-  auto dkdp = [&](int e) { return has_mass ? __dmul_rn(im[AUX ? e : 0], p[e]) : p[e]; };
+  auto dkdp = [&](int e) {
+    if constexpr (AUX) return has_mass ? __dmul_rn(im[e], p[e]) : p[e];
+    else return p[e];
+  };
   auto violations = [&]() {
     unsigned m = 0;
 #pragma unroll
@@ -110,8 +113,47 @@ hmc_fused_priors_kernel(const FusedArgs A) {
   double x = A.x[c];
   int accepted = 0;
   const bool grad_checks = T.grad_check_mask != 0u;
+  // Fast path: every coordinate carries exactly one prior term of the same kind, no bound
+  // check is visible to the gradient and nothing is traced -> branch-free element loops.
+  const int fast_kind = (!grad_checks && !A.trace_q) ? T.uniform_kind : TERM_NONE;
 
-  for (int kb = 0; kb < A.proposals; ++kb) {
+  // Sub-steps of the trajectory (see run_schedule): momentum update with the gradient of
+  // the priors, position update with reflection.
+  int gi = 0, kb = 0;
+  auto mom_normal = [&](double cb) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) momentum_update(cb, term_gradient(TERM_NORMAL, ta[e], tb[e], q[e]), p[e]);
+  };
+  auto mom_laplace = [&](double cb) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) momentum_update(cb, term_gradient(TERM_LAPLACE, ta[e], tb[e], q[e]), p[e]);
+  };
+  auto mom_generic = [&](double cb) {
+    const unsigned oob = grad_checks ? (violations() & T.grad_check_mask) : 0u;
+    const size_t C_ = (size_t)A.chains;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int kind = kind_of(e);
+      double g = kind ? term_gradient(kind, ta[e], tb[e], q[e]) : 0.0;
+      if (oob && ok(e) && (oob & T.c_cover[jj[e]])) g = __dadd_rn(g, CUDART_INF);
+      if (A.trace_q && live && ok(e)) {
+        const size_t o = (((size_t)kb * A.S.grads_per_proposal + gi) * C_ + c) * d + jj[e];
+        A.trace_q[o] = q[e];
+        A.trace_g[o] = g;
+      }
+      momentum_update(cb, g, p[e]);
+    }
+    ++gi;
+  };
+  auto pos = [&](double ca) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      q[e] = __dadd_rn(q[e], __dmul_rn(ca, dkdp(e)));
+      if constexpr (AUX) { if (has_refl) reflect_on(rlb[e], rub[e], q[e], p[e]); }
+    }
+  };
+
+  for (kb = 0; kb < A.proposals; ++kb) {
     const long long kglob = A.proposal_offset + kb;
     const size_t kc = (size_t)kb * C + c;
 
@@ -145,41 +187,15 @@ hmc_fused_priors_kernel(const FusedArgs A) {
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       q[e] = qc[e];
-      if (has_mass) p[e] = __dmul_rn(sm[AUX ? e : 0], p[e]);
+      if constexpr (AUX) { if (has_mass) p[e] = __dmul_rn(sm[e], p[e]); }
       k0 = __dadd_rn(k0, __dmul_rn(p[e], dkdp(e)));
     }
 
     // ---- trajectory --------------------------------------------------------------
-    int gi = 0;
-    auto run_op = [&](const StageOp& op) {
-      if (op.has_b) {
-        const unsigned oob = grad_checks ? (violations() & T.grad_check_mask) : 0u;
-        const double cb = __dmul_rn(op.b, eps);
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const int kind = kind_of(e);
-          double g = kind ? term_gradient(kind, ta[e], tb[e], q[e]) : 0.0;
-          if (oob && ok(e) && (oob & T.c_cover[jj[e]])) g = __dadd_rn(g, CUDART_INF);
-          if (A.trace_q && live && ok(e)) {
-            const size_t o = (((size_t)kb * A.S.grads_per_proposal + gi) * C + c) * d + jj[e];
-            A.trace_q[o] = q[e];
-            A.trace_g[o] = g;
-          }
-          momentum_update(cb, g, p[e]);
-        }
-        ++gi;
-      }
-      const double ca = __dmul_rn(op.a, eps);
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        q[e] = __dadd_rn(q[e], __dmul_rn(ca, dkdp(e)));
-        if (has_refl) reflect_on(rlb[AUX ? e : 0], rub[AUX ? e : 0], q[e], p[e]);
-      }
-    };
-    for (int s = 0; s < A.S.n_pre; ++s) run_op(A.S.pre[s]);
-    for (int r = 0; r < A.S.reps; ++r)
-      for (int s = 0; s < A.S.n_body; ++s) run_op(A.S.body[s]);
-    for (int s = 0; s < A.S.n_post; ++s) run_op(A.S.post[s]);
+    gi = 0;
+    if (fast_kind == TERM_NORMAL) run_schedule(A.S, eps, mom_normal, pos);
+    else if (fast_kind == TERM_LAPLACE) run_schedule(A.S, eps, mom_laplace, pos);
+    else run_schedule(A.S, eps, mom_generic, pos);
 
     // ---- energies and decision ----------------------------------------------------
     double k1 = 0.0, u1 = 0.0;

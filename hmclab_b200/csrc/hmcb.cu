@@ -166,6 +166,7 @@ void build_schedule(hmcb_engine* e) {
   Schedule& S = e->S;
   std::memset(&S, 0, sizeof(S));
   const int Lsteps = e->steps;
+  S.kind = e->integrator;
   auto lone = [](double a) { return StageOp{0.0, a, 0, 0}; };
   auto pair = [](double b, double a) { return StageOp{b, a, 1, 0}; };
   if (e->integrator == HMCB_INTEGRATOR_LF) {
@@ -633,6 +634,12 @@ int hmcb_finalize(hmcb_engine* e) {
       const_sum += P.constant;
     }
     T.const_sum = const_sum;
+    if (n_terms == 1) {
+      int uk = kind[0];
+      for (int j = 0; j < d; ++j)
+        if (kind[(size_t)j] != uk) uk = TERM_NONE;
+      T.uniform_kind = uk;
+    }
     if (dev_upload(e, kind, &T.t_kind) || dev_upload(e, ta, &T.t_a) || dev_upload(e, tb, &T.t_b)) return -1;
     // bound checks: -inf / +inf where a check does not apply
     const double inf = std::numeric_limits<double>::infinity();

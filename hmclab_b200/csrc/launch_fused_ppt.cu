@@ -1,5 +1,5 @@
 // launch_fused_ppt.cu -- instantiations of the priors-only fused HMC kernel for one value
-// of PPT (coordinate pairs per thread); compiled once per -DHMCB_PPT={1,2,4,8}.
+// of PPT (coordinate pairs per thread); compiled once per -DHMCB_PPT={1,2,4}.
 #include "launch.cuh"
 
 #ifndef HMCB_PPT
@@ -35,13 +35,10 @@ cudaError_t HMCB_CAT(launch_fused_priors_ppt, HMCB_PPT)(const FusedArgs& A, int 
 #elif HMCB_PPT == 2
     case 128: return launch_fp<128, 2>(A, s);
     case 256: return launch_fp<256, 2>(A, s);
+    case 512: return launch_fp<512, 2>(A, s);
 #elif HMCB_PPT == 4
     case 128: return launch_fp<128, 4>(A, s);
-#elif HMCB_PPT == 8
-    case 64: return launch_fp<64, 8>(A, s);
-    case 128: return launch_fp<128, 8>(A, s);
-    case 256: return launch_fp<256, 8>(A, s);
-    case 512: return launch_fp<512, 8>(A, s);
+    case 512: return launch_fp<512, 4>(A, s);
 #endif
   }
   return cudaErrorInvalidConfiguration;

@@ -146,7 +146,7 @@ __device__ __forceinline__ unsigned srcloc_violations(const DevTarget& T, const 
 }
 
 template <int TPC, int LPE>
-__global__ void __launch_bounds__((TPC <= 32 ? 256 : TPC))
+__global__ void __launch_bounds__((TPC <= 32 ? 256 : TPC), (TPC <= 256 ? 2 : 1))
 hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
   extern __shared__ double dyn_smem[];
   __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(TPC <= 32 ? 256 : TPC)];
@@ -203,35 +203,30 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
     }
 
     int gi = 0;
-    auto run_op = [&](const StageOp& op) {
-      if (op.has_b) {
-        unsigned oob = 0;
-        if (grad_checks) oob = srcloc_violations<TPC, LPE>(T, L, ln, red, q, qv);
-        double g[4], gvel;
-        srcloc_total_gradient<TPC, LPE>(T, L, M, ln, red, q, qv, oob, g, gvel);
-        if (A.trace_q && ln.live) {
-          const size_t o = (((size_t)kb * A.S.grads_per_proposal + gi) * C + c) * d;
-          if (ln.lead) {
+    auto mom = [&](double cb) {
+      unsigned oob = 0;
+      if (grad_checks) oob = srcloc_violations<TPC, LPE>(T, L, ln, red, q, qv);
+      double g[4], gvel;
+      srcloc_total_gradient<TPC, LPE>(T, L, M, ln, red, q, qv, oob, g, gvel);
+      if (A.trace_q && ln.live) {
+        const size_t o = (((size_t)kb * A.S.grads_per_proposal + gi) * C + c) * d;
+        if (ln.lead) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { A.trace_q[o + j0 + i] = q[i]; A.trace_g[o + j0 + i] = g[i]; }
-          }
-          if (inferv && ln.vlead) { A.trace_q[o + jv] = qv; A.trace_g[o + jv] = gvel; }
+          for (int i = 0; i < 4; ++i) { A.trace_q[o + j0 + i] = q[i]; A.trace_g[o + j0 + i] = g[i]; }
         }
-        const double cb = __dmul_rn(op.b, eps);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) momentum_update(cb, g[i], p[i]);
-        if (inferv) momentum_update(cb, gvel, pv);
-        ++gi;
+        if (inferv && ln.vlead) { A.trace_q[o + jv] = qv; A.trace_g[o + jv] = gvel; }
       }
-      const double ca = __dmul_rn(op.a, eps);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) momentum_update(cb, g[i], p[i]);
+      if (inferv) momentum_update(cb, gvel, pv);
+      ++gi;
+    };
+    auto pos = [&](double ca) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) position_update(T, j0 + i, ca, q[i], p[i]);
       if (inferv) position_update(T, jv, ca, qv, pv);
     };
-    for (int s = 0; s < A.S.n_pre; ++s) run_op(A.S.pre[s]);
-    for (int r = 0; r < A.S.reps; ++r)
-      for (int s = 0; s < A.S.n_body; ++s) run_op(A.S.body[s]);
-    for (int s = 0; s < A.S.n_post; ++s) run_op(A.S.post[s]);
+    run_schedule(A.S, eps, mom, pos);
 
     // energies: kinetic, prior misfit, travel-time misfit
     double k1 = 0.0, u1 = 0.0;

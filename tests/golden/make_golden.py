@@ -138,12 +138,40 @@ def check_public_sample_call(hmclab, name, inp, golden, tmpdir):
     assert np.array_equal(stored, golden["samples"][:, 0, :]), name
 
 
+def seeded_public_runs(hmclab, tmpdir):
+    """Reference HMC(seed).sample(...) with its own numpy Generator (no replay): what a
+    user gets for a given seed.  hmclab_b200's ``host_rng=True`` mode must reproduce these
+    sample files from the same seed."""
+    out = {}
+    for name, seed, thin in (("dense_premult_cfg1", 42, 1), ("srcloc_fixed_v", 7, 2),
+                             ("normal_bounded", 3, 1)):
+        s = cases.SETTINGS[name]
+        inp = cases.make_inputs(name)
+        post, mass = cases.build(name, inp, hmclab)
+        fn = os.path.join(tmpdir, f"seeded_{name}.npy")
+        sampler = hmclab.Samplers.HMC(seed=seed)
+        with np.errstate(all="ignore"):
+            sampler.sample(fn, post, stepsize=s["stepsize"], randomize_stepsize=s["randomize"],
+                           amount_of_steps=s["steps"], mass_matrix=mass, integrator=s["integrator"],
+                           initial_model=inp["q0"][0].copy(), proposals=24, online_thinning=thin,
+                           overwrite_existing_file=True, disable_progressbar=True)
+        out[f"{name}__samples"] = np.load(fn)
+        out[f"{name}__seed"] = np.int64(seed)
+        out[f"{name}__thinning"] = np.int64(thin)
+        out[f"{name}__accepted"] = np.int64(sampler.accepted_proposals)
+    np.savez_compressed(os.path.join(HERE, "seeded_public_runs.npz"), **out)
+    print("seeded_public_runs", {k: v.shape for k, v in out.items() if k.endswith("samples")})
+
+
 def main():
     hmclab = import_reference()
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
     from hmclab_b200._lowering import describe, describe_mass
 
     with tempfile.TemporaryDirectory() as tmpdir:
+        seeded_public_runs(hmclab, tmpdir)
+        if "--seeded-only" in sys.argv:
+            return
         for name in cases.CASES:
             inp = cases.make_inputs(name)
             golden, post, mass = drive_reference(hmclab, name, inp, tmpdir)

@@ -1,0 +1,187 @@
+"""HMC().sample(...) end to end on the GPU: reference reproduction from the same seed,
+file format, determinism, chain-sharding invariance, early termination."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+import cases
+from helpers import GOLDEN_DIR, build_mirror, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+@pytest.mark.parametrize("name", ["dense_premult_cfg1", "srcloc_fixed_v", "normal_bounded"])
+def test_same_seed_reproduces_the_reference_samples_file(tmp_path, name):
+    """hmclab.Samplers.HMC(seed).sample(...) (run in the build container, stored in
+    tests/golden/seeded_public_runs.npz) vs hmclab_b200 with host_rng=True, same seed."""
+    from hmclab_b200.Samplers import HMC
+
+    gold = np.load(os.path.join(GOLDEN_DIR, "seeded_public_runs.npz"))
+    ref = gold[f"{name}__samples"]
+    seed, thin = int(gold[f"{name}__seed"]), int(gold[f"{name}__thinning"])
+    inp, _ = load_golden(name)
+    s = cases.SETTINGS[name]
+    post, mass = build_mirror(name, inp)
+    fn = str(tmp_path / "run.npy")
+    sampler = HMC(seed=seed).sample(
+        fn, post, stepsize=s["stepsize"], randomize_stepsize=s["randomize"],
+        amount_of_steps=s["steps"], mass_matrix=mass, integrator=s["integrator"],
+        initial_model=inp["q0"][0].copy(), proposals=24, online_thinning=thin,
+        disable_progressbar=True, host_rng=True, block_proposals=10)
+    got = np.load(fn)
+    assert got.shape == ref.shape
+    # identical accept/reject sequence <=> identical pattern of repeated rows
+    assert np.array_equal(np.all(np.diff(got, axis=0) == 0, axis=1),
+                          np.all(np.diff(ref, axis=0) == 0, axis=1))
+    assert rel_err(got, ref) < TOL
+    assert sampler.accepted_proposals == int(gold[f"{name}__accepted"])
+    assert sampler.current_model.shape == (post.dimensions, 1)
+    assert rel_err(sampler.current_model[:, 0], ref[-1, :-1]) < TOL
+    assert isinstance(sampler.current_x, float)
+
+
+def test_file_attributes_and_reader(tmp_path):
+    from hmclab_b200 import Distributions as D
+    from hmclab_b200.Samplers import HMC
+    from hmclab_b200.Samples import Samples
+
+    d, C = 6, 5
+    post = D.Normal(np.zeros((d, 1)), 1.0)
+    fn = str(tmp_path / "multi.npy")
+    sampler = HMC(seed=3).sample(fn, post, stepsize=0.3, proposals=40, online_thinning=4,
+                                 chains=C, disable_progressbar=True, block_proposals=12)
+    with Samples(fn) as s:
+        assert s.numpy.shape == (d + 1, C * 10)
+        for key in ("write_index", "last_written_sample", "proposals", "acceptance_rate",
+                    "online_thinning", "start_time", "sampler", "stepsize", "amount_of_steps",
+                    "mass_matrix", "integrator", "end_time", "runtime", "runtime_seconds",
+                    "chains", "samples_per_chain"):
+            s.read_attribute(key)
+        assert s.read_attribute("write_index") == C * 10
+        assert s.read_attribute("sampler") == "Hamiltonian Monte Carlo"
+        assert s.read_attribute("integrator") == "leapfrog integrator"
+        assert s.read_attribute("mass_matrix") == "unit mass matrix"
+        last = s.chain(C - 1)[:, -1]
+        # stored misfit is chi of the stored model: 0.5 * |m|^2
+        assert rel_err(s.misfits, 0.5 * np.sum(s.samples ** 2, axis=0)) < 1e-13
+    assert rel_err(last[:-1], sampler.current_model[:, C - 1]) == 0.0
+    assert sampler.current_x.shape == (C,)
+    assert sampler.amount_of_writes == 10 and sampler.current_proposal == 39
+    assert 0 < sampler.accepted_proposals <= 40 * C
+    with pytest.raises(FileExistsError):
+        HMC(seed=3).sample(fn, post, proposals=4, chains=C)
+    assert sampler.load_results(burn_in=2).shape == (d + 1, C * 10 - 2)
+
+
+def test_device_rng_is_reproducible_and_independent_of_sharding(tmp_path):
+    """Same seed -> same file; chains [0,8) in one engine == chains [0,4) + [4,8) in two
+    engines (random streams are keyed by the global chain id)."""
+    import torch
+
+    from hmclab_b200._engine import Engine
+    from hmclab_b200._lowering import describe, describe_mass, flatten
+    from hmclab_b200 import workloads
+    from hmclab_b200.Samplers import HMC
+
+    w = workloads.source_location(events=3, stations=6, chains=8)
+    a = HMC(seed=11).sample(str(tmp_path / "a.npy"), w.posterior, stepsize=w.stepsize, proposals=12,
+                            mass_matrix=w.mass_matrix, initial_model=w.initial_models)
+    b = HMC(seed=11).sample(str(tmp_path / "b.npy"), w.posterior, stepsize=w.stepsize, proposals=12,
+                            mass_matrix=w.mass_matrix, initial_model=w.initial_models,
+                            block_proposals=5)
+    assert np.array_equal(np.load(a.samples_filename), np.load(b.samples_filename))
+    c = HMC(seed=12).sample(str(tmp_path / "c.npy"), w.posterior, stepsize=w.stepsize, proposals=12,
+                            mass_matrix=w.mass_matrix, initial_model=w.initial_models)
+    assert not np.array_equal(np.load(a.samples_filename), np.load(c.samples_filename))
+
+    plan, mplan = flatten(describe(w.posterior)), describe_mass(w.mass_matrix)
+
+    def run(lo, hi):
+        eng = Engine(plan, mplan, hi - lo, integrator="3s", amount_of_steps=4)
+        q = torch.as_tensor(w.initial_models[lo:hi]).cuda().contiguous()
+        x = eng.misfit(q)
+        out = torch.zeros(6, hi - lo, w.dims + 1, dtype=torch.float64, device="cuda")
+        eng.run_block(q, x, 6, stepsize=w.stepsize, seed=99, chain_offset=lo, out_samples=out)
+        return out.cpu().numpy()
+
+    whole = run(0, 8)
+    assert np.array_equal(whole[:, :4], run(0, 4)) and np.array_equal(whole[:, 4:], run(4, 8))
+
+
+def test_device_momenta_are_standard_normal():
+    """One proposal with a huge mass-less free flight: q1 - q0 = eps * p0 exposes the draws."""
+    import torch
+
+    from hmclab_b200._engine import Engine
+
+    d, C = 512, 2048
+    big = 1e30   # prior variance so large that the gradient vanishes
+    plan = {"dims": d, "terms": [{"kind": "normal", "offset": 0, "len": d, "a": np.zeros(d),
+                                  "b": np.full(d, 1.0 / big), "const": 0.0}],
+            "checks": [], "likelihood": None, "reflect_lb": None, "reflect_ub": None}
+    eng = Engine(plan, {"kind": "unit", "dims": d}, C, integrator="lf", amount_of_steps=1)
+    q = torch.zeros(C, d, dtype=torch.float64, device="cuda")
+    x = eng.misfit(q)
+    qp = torch.zeros(1, C, d, dtype=torch.float64, device="cuda")
+    pp = torch.zeros(1, C, d, dtype=torch.float64, device="cuda")
+    eng.run_block(q, x, 1, stepsize=1.0, randomize_stepsize=False, seed=5, out_q_prop=qp, out_p_prop=pp)
+    z = pp[0].cpu().numpy()
+    n = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(n)
+    assert abs(z.var() - 1) < 5 * np.sqrt(2 / n)
+    assert abs((z ** 3).mean()) < 5 * np.sqrt(15 / n)
+    assert abs((z ** 4).mean() - 3) < 5 * np.sqrt(96 / n)
+    assert np.abs(z).max() < 7 and np.abs(z).max() > 4
+    # chains and coordinates are uncorrelated
+    assert abs(np.corrcoef(z[0], z[1])[0, 1]) < 0.25
+    assert abs(np.mean(z[:, 0] * z[:, 1])) < 5 / np.sqrt(C)
+    # Kolmogorov-Smirnov against the normal CDF
+    from scipy import stats
+
+    assert stats.kstest(z.ravel()[:200000], "norm").pvalue > 1e-4
+
+
+def test_sampling_statistics_of_a_known_target(tmp_path):
+    from hmclab_b200 import Distributions as D
+    from hmclab_b200.Samplers import HMC
+    from hmclab_b200.Samples import Samples
+
+    d, C = 8, 512
+    mu = np.linspace(-1, 1, d).reshape(d, 1)
+    var = np.linspace(0.5, 2.0, d).reshape(d, 1)
+    post = D.Normal(mu, var)
+    fn = str(tmp_path / "stat.npy")
+    HMC(seed=21).sample(fn, post, stepsize=0.5, amount_of_steps=8, proposals=300, online_thinning=3,
+                        chains=C, initial_model=np.tile(mu.T, (C, 1)), integrator="4s")
+    with Samples(fn, burn_in=0) as s:
+        per = int(s.read_attribute("samples_per_chain"))
+        x = np.stack([s.chain(c)[:-1, per // 4:] for c in range(C)])   # [C, d, n]
+        rate = s.read_attribute("acceptance_rate")
+    assert 0.6 < rate <= 1.0
+    n_eff = C * 20
+    assert np.all(np.abs(x.mean(axis=(0, 2)) - mu[:, 0]) < 5 * np.sqrt(var[:, 0] / n_eff))
+    assert np.all(np.abs(x.var(axis=(0, 2)) / var[:, 0] - 1) < 0.1)
+
+
+def test_max_time_stops_early_and_leaves_a_valid_file(tmp_path):
+    from hmclab_b200 import workloads
+    from hmclab_b200.Samplers import HMC
+    from hmclab_b200.Samples import Samples
+
+    w = workloads.normal_iid(dims=200, chains=256)
+    fn = str(tmp_path / "cut.npy")
+    t0 = time.time()
+    sampler = HMC(seed=1).sample(fn, w.posterior, stepsize=0.05, proposals=2_000_000,
+                                 online_thinning=1000, chains=256, initial_model=w.initial_models,
+                                 max_time=0.5, block_proposals=2000)
+    assert time.time() - t0 < 30
+    done = sampler.current_proposal + 1
+    assert 0 < done < 2_000_000 and done % 2000 == 0
+    with Samples(fn) as s:
+        per = s.read_attribute("samples_per_chain")
+        assert per == done // 1000 and s.numpy.shape == (201, 256 * per)
+        assert np.all(np.isfinite(s.numpy))
