@@ -48,7 +48,7 @@ class Samples:
         else:
             raise AttributeError(f"Unkown extension `{ext}` for samples file.")
         self.mode, self.filename = mode, filename
-        self._closed = False
+        self._closed = True  # nothing to flush until the constructor has succeeded
         self._attributes = {}
         self._memmap = None
         self._h5 = None
@@ -75,6 +75,7 @@ class Samples:
             self.burn_in = 0 if burn_in is None else burn_in
             self.last_sample = self.read_attribute("write_index")
             if self.last_sample <= self.burn_in:
+                self._closed = False
                 self.close()
                 raise ValueError(
                     f"The burn-in phase is longer than the chain itself. "
@@ -102,6 +103,7 @@ class Samples:
             self.write_attribute("last_written_sample", -1)
         else:
             raise AttributeError(f"Unkown file mode `{mode}` for samples file.")
+        self._closed = False
 
     @staticmethod
     def _require_h5py():
@@ -129,6 +131,7 @@ class Samples:
                 "samples", (self._width, total), maxshape=(None, None), dtype="f8", chunks=True)
             for key, value in self._attributes.items():
                 self._dataset.attrs[key] = value
+        self._allocated = True
         self.write_attribute("chains", self._chains)
         self.write_attribute("samples_per_chain", self._per_chain)
 
@@ -225,8 +228,8 @@ class Samples:
             if self._memmap is not None:
                 self._memmap.flush()
                 self._memmap = None
-            if self.filetype == "NPY" and not _os.path.exists(self.filename):
-                return  # nothing was ever allocated: leave no attribute file behind either
+            if not getattr(self, "_allocated", False):
+                return  # nothing was ever written: leave existing files and attributes alone
             self._flush_attributes()
         if self._h5 is not None:
             self._h5.close()

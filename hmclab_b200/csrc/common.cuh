@@ -193,6 +193,24 @@ __device__ __forceinline__ void uniform_pair(uint64_t seed, uint32_t chain, uint
   u_acc = u53(r.z, r.w);
 }
 
+// The (step-size factor, acceptance uniform) pair is one Philox call per chain and
+// proposal.  Instead of every thread of the chain repeating it, lane l of a group of
+// W = min(TPC, 32) lanes evaluates the pair of proposal base + l, and each proposal then
+// fetches its pair with two shuffles: one Philox call per W proposals per warp.
+template <int TPC>
+struct UniformPairCache {
+  static constexpr int W = TPC < 32 ? TPC : 32;
+  double us, ua;
+  __device__ __forceinline__ void fill(uint64_t seed, uint32_t chain, long long first_proposal) {
+    uniform_pair(seed, chain, (uint32_t)(first_proposal + (threadIdx.x % W)), us, ua);
+  }
+  __device__ __forceinline__ void get(int slot, double& u_step, double& u_acc) const {
+    const int src = ((threadIdx.x & 31) & ~(W - 1)) + slot;
+    u_step = __shfl_sync(0xffffffffu, us, src);
+    u_acc = __shfl_sync(0xffffffffu, ua, src);
+  }
+};
+
 // ---------------------------------------------------------------- chain reductions ---
 // A chain is owned by TPC consecutive threads (TPC a power of two).  TPC <= 32: the group
 // lives inside one warp and reduces with xor-shuffles (every lane ends with the same

@@ -157,6 +157,8 @@ hmc_fused_priors_kernel(const FusedArgs A) {
     }
   };
 
+  UniformPairCache<TPC> ucache;
+  ucache.us = ucache.ua = 0.0;
   for (kb = 0; kb < A.proposals; ++kb) {
     const long long kglob = A.proposal_offset + kb;
     const size_t kc = (size_t)kb * C + c;
@@ -166,7 +168,9 @@ hmc_fused_priors_kernel(const FusedArgs A) {
     if (A.u_step_in && A.u_accept_in) {
       u_step = A.u_step_in[kc]; u_acc = A.u_accept_in[kc];
     } else {
-      uniform_pair(A.seed, (uint32_t)(A.chain_offset + c), (uint32_t)kglob, u_step, u_acc);
+      constexpr int W = UniformPairCache<TPC>::W;
+      if ((kb % W) == 0) ucache.fill(A.seed, (uint32_t)(A.chain_offset + c), kglob);
+      ucache.get(kb % W, u_step, u_acc);
       if (A.u_step_in) u_step = A.u_step_in[kc];
       if (A.u_accept_in) u_acc = A.u_accept_in[kc];
     }

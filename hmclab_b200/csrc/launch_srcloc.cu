@@ -23,13 +23,13 @@ static int srcloc_lpe(int stations) {
 }
 
 size_t srcloc_smem_bytes(const SrcLocDev& L) {
-  return sizeof(double) * (3 * (size_t)L.stations + 2 * (size_t)L.events * L.stations);
+  return sizeof(double) * srcloc_smem_doubles(L.events, L.stations);
 }
 
 bool srcloc_supported(int events, int stations) {
   if (events < 1 || stations < 1) return false;
   if (pow2_ceil(events) * srcloc_lpe(stations) > 1024) return false;
-  return sizeof(double) * (3 * (size_t)stations + 2 * (size_t)events * stations) <= 200 * 1024;
+  return sizeof(double) * srcloc_smem_doubles(events, stations) <= 200 * 1024;
 }
 
 cudaError_t launch_fused_srcloc_lpe1(const FusedArgs&, const SrcLocDev&, int, cudaStream_t);

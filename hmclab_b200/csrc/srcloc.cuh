@@ -20,43 +20,62 @@ struct SrcLocDev {
 };
 
 struct SrcLocShared {
-  const double *rx, *ry, *rz, *tobs, *std;
+  const double *rx, *ry, *rz, *tobs, *inv_var, *inv_sigma;
 };
+
+// Shared-memory doubles: 3 station coordinate rows + observed times, 1/sigma^2, 1/sigma.
+__host__ __device__ inline size_t srcloc_smem_doubles(int events, int stations) {
+  return 3 * (size_t)stations + 3 * (size_t)events * stations;
+}
 
 __device__ __forceinline__ SrcLocShared srcloc_stage(const SrcLocDev& L, double* smem) {
   const int S = L.stations, ES = L.events * L.stations;
   double* rx = smem; double* ry = rx + S; double* rz = ry + S;
-  double* tobs = rz + S; double* sd = tobs + ES;
+  double* tobs = rz + S; double* iv = tobs + ES; double* is = iv + ES;
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
     rx[i] = L.rx[i]; ry[i] = L.ry[i]; rz[i] = L.rz[i];
   }
-  for (int i = threadIdx.x; i < ES; i += blockDim.x) { tobs[i] = L.tobs[i]; sd[i] = L.std[i]; }
+  for (int i = threadIdx.x; i < ES; i += blockDim.x) {
+    const double sd = L.std[i];
+    tobs[i] = L.tobs[i];
+    iv[i] = __ddiv_rn(1.0, __dmul_rn(sd, sd));
+    is[i] = __ddiv_rn(1.0, sd);
+  }
   __syncthreads();
-  return SrcLocShared{rx, ry, rz, tobs, sd};
+  return SrcLocShared{rx, ry, rz, tobs, iv, is};
 }
 
 __device__ __forceinline__ double nan_to_zero(double v) { return (v != v) ? 0.0 : v; }
 
-// Partial (this lane's stations) gradient sums of event e (SourceLocation.py:495-524).
+// The reference evaluates, per event-station pair, dist = sqrt(.), t = T + dist / v,
+// w = (t - t_obs) / sigma^2 and the direction terms dx / (v * dist) (SourceLocation.py:495-524):
+// six IEEE divisions and a square root.  Here one reciprocal square root per pair and
+// precomputed reciprocals (1/v, 1/sigma^2, 1/sigma) replace them; every product still rounds
+// once, so terms agree with the reference to a few ulp (the sums over stations already differ
+// from numpy's pairwise order at that level; parity tolerance is 1e-10).  NaN semantics of
+// nansum are kept term by term: a missing pick (NaN t_obs) drops the pair from every sum, a
+// zero distance (0/0 direction) drops only the direction terms.
 template <int LPE>
 __device__ __forceinline__ void srcloc_gradient_partial(const SrcLocShared& M, int S, int e, int sub,
                                                         double x, double y, double z, double T,
-                                                        double v, double& gx, double& gy,
-                                                        double& gz, double& gT, double& gv) {
+                                                        double inv_v, bool want_gv, double& gx,
+                                                        double& gy, double& gz, double& gT, double& gv) {
   gx = gy = gz = gT = gv = 0.0;
-  const double vv = __dmul_rn(v, v);
+  const double neg_inv_vv = -__dmul_rn(inv_v, inv_v);
+#pragma unroll 3
   for (int s = sub; s < S; s += LPE) {
     const double dx = __dsub_rn(x, M.rx[s]), dy = __dsub_rn(y, M.ry[s]), dz = __dsub_rn(z, M.rz[s]);
-    const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-    const double tcalc = __dadd_rn(T, __ddiv_rn(dist, v));
-    const double sd = M.std[e * S + s];
-    const double w = __ddiv_rn(__dsub_rn(tcalc, M.tobs[e * S + s]), __dmul_rn(sd, sd));
-    const double vd = __dmul_rn(v, dist);
-    gx = __dadd_rn(gx, nan_to_zero(__dmul_rn(w, __ddiv_rn(dx, vd))));
-    gy = __dadd_rn(gy, nan_to_zero(__dmul_rn(w, __ddiv_rn(dy, vd))));
-    gz = __dadd_rn(gz, nan_to_zero(__dmul_rn(w, __ddiv_rn(dz, vd))));
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    const double rinv = rsqrt(d2);
+    const double dist = __dmul_rn(d2, rinv);
+    const double tcalc = __dadd_rn(T, __dmul_rn(dist, inv_v));
+    const double w = __dmul_rn(__dsub_rn(tcalc, M.tobs[e * S + s]), M.inv_var[e * S + s]);
+    const double u = __dmul_rn(w, __dmul_rn(inv_v, rinv));  // w / (v * dist)
+    gx = __dadd_rn(gx, nan_to_zero(__dmul_rn(u, dx)));
+    gy = __dadd_rn(gy, nan_to_zero(__dmul_rn(u, dy)));
+    gz = __dadd_rn(gz, nan_to_zero(__dmul_rn(u, dz)));
     gT = __dadd_rn(gT, nan_to_zero(w));
-    gv = __dadd_rn(gv, nan_to_zero(__dmul_rn(w, __ddiv_rn(-dist, vv))));
+    if (want_gv) gv = __dadd_rn(gv, nan_to_zero(__dmul_rn(w, __dmul_rn(dist, neg_inv_vv))));
   }
 }
 
@@ -64,12 +83,15 @@ __device__ __forceinline__ void srcloc_gradient_partial(const SrcLocShared& M, i
 template <int LPE>
 __device__ __forceinline__ double srcloc_misfit_partial(const SrcLocShared& M, int S, int e, int sub,
                                                         double x, double y, double z, double T,
-                                                        double v) {
+                                                        double inv_v) {
   double acc = 0.0;
+#pragma unroll 3
   for (int s = sub; s < S; s += LPE) {
     const double dx = __dsub_rn(x, M.rx[s]), dy = __dsub_rn(y, M.ry[s]), dz = __dsub_rn(z, M.rz[s]);
-    const double dist = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-    const double r = __ddiv_rn(__dsub_rn(M.tobs[e * S + s], __dadd_rn(T, __ddiv_rn(dist, v))), M.std[e * S + s]);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    const double dist = sqrt(d2);
+    const double r = __dmul_rn(__dsub_rn(M.tobs[e * S + s], __dadd_rn(T, __dmul_rn(dist, inv_v))),
+                               M.inv_sigma[e * S + s]);
     acc = __dadd_rn(acc, nan_to_zero(__dmul_rn(r, r)));
   }
   return acc;
@@ -111,9 +133,10 @@ __device__ __forceinline__ void srcloc_total_gradient(const DevTarget& T, const 
                                                       const SrcLocLane<TPC, LPE>& ln,
                                                       const ChainReduce<TPC>& red, const double* q,
                                                       double qv, unsigned oob, double* g, double& gvel) {
-  const double v = L.infer_velocity ? qv : L.velocity;
+  const double inv_v = __ddiv_rn(1.0, L.infer_velocity ? qv : L.velocity);
   double gx, gy, gz, gT, gv;
-  srcloc_gradient_partial<LPE>(M, L.stations, ln.e, ln.sub, q[0], q[1], q[2], q[3], v, gx, gy, gz, gT, gv);
+  srcloc_gradient_partial<LPE>(M, L.stations, ln.e, ln.sub, q[0], q[1], q[2], q[3], inv_v,
+                               L.infer_velocity != 0, gx, gy, gz, gT, gv);
   gx = group_sum<LPE>(gx); gy = group_sum<LPE>(gy); gz = group_sum<LPE>(gz); gT = group_sum<LPE>(gT);
   const int j0 = 4 * ln.e;
   g[0] = __dadd_rn(prior_gradient(T, j0 + 0, q[0], oob), gx);
@@ -169,14 +192,22 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
   double x = A.x[c];
   int accepted = 0;
 
+  UniformPairCache<TPC> ucache;
+  ucache.us = ucache.ua = 0.0;
   for (int kb = 0; kb < A.proposals; ++kb) {
     const long long kglob = A.proposal_offset + kb;
     const size_t kc = (size_t)kb * C + c;
     const uint32_t cg = (uint32_t)(A.chain_offset + c), kg = (uint32_t)kglob;
     double u_step, u_acc;
-    uniform_pair(A.seed, cg, kg, u_step, u_acc);
-    if (A.u_step_in) u_step = A.u_step_in[kc];
-    if (A.u_accept_in) u_acc = A.u_accept_in[kc];
+    if (A.u_step_in && A.u_accept_in) {
+      u_step = A.u_step_in[kc]; u_acc = A.u_accept_in[kc];
+    } else {
+      constexpr int W = UniformPairCache<TPC>::W;
+      if ((kb % W) == 0) ucache.fill(A.seed, cg, kglob);
+      ucache.get(kb % W, u_step, u_acc);
+      if (A.u_step_in) u_step = A.u_step_in[kc];
+      if (A.u_accept_in) u_acc = A.u_accept_in[kc];
+    }
     const double eps = A.randomize ? __dmul_rn(u_step, A.stepsize) : A.stepsize;
 
     if (A.z_in) {
@@ -241,8 +272,8 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
       k1 = __dadd_rn(k1, kinetic_term(T, jv, pv));
       u1 = __dadd_rn(u1, prior_misfit(T, jv, qv));
     }
-    const double vel = inferv ? qv : L.velocity;
-    double lik = srcloc_misfit_partial<LPE>(M, L.stations, ln.e, ln.sub, q[0], q[1], q[2], q[3], vel);
+    const double inv_vel = __ddiv_rn(1.0, inferv ? qv : L.velocity);
+    double lik = srcloc_misfit_partial<LPE>(M, L.stations, ln.e, ln.sub, q[0], q[1], q[2], q[3], inv_vel);
     if (!ln.has_event) lik = 0.0;
     red.sum3(k0, k1, u1);
     double z0 = 0.0, z1 = 0.0;
@@ -325,8 +356,8 @@ srcloc_eval_kernel(const DevTarget T, const SrcLocDev L, int chains, int mode,
     if (ln.lead)
       for (int i = 0; i < 4; ++i) u1 = __dadd_rn(u1, prior_misfit(T, j0 + i, q[i]));
     if (L.infer_velocity && ln.vlead) u1 = __dadd_rn(u1, prior_misfit(T, jv, qv));
-    const double vel = L.infer_velocity ? qv : L.velocity;
-    double lik = srcloc_misfit_partial<LPE>(M, L.stations, ln.e, ln.sub, q[0], q[1], q[2], q[3], vel);
+    const double inv_vel = __ddiv_rn(1.0, L.infer_velocity ? qv : L.velocity);
+    double lik = srcloc_misfit_partial<LPE>(M, L.stations, ln.e, ln.sub, q[0], q[1], q[2], q[3], inv_vel);
     if (!ln.has_event) lik = 0.0;
     red.sum3(u1, lik, z0);
     (void)z1;

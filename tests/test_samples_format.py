@@ -62,6 +62,11 @@ def test_error_behaviour(tmp_path):
     _write(path)
     with pytest.raises(FileExistsError, match="already existing file"):
         Samples(path, mode="w")
+    import gc
+
+    gc.collect()  # the refused writer must not touch the existing files when it is collected
+    with Samples(path) as s:
+        assert s.read_attribute("write_index") == 15
     Samples(path, mode="w", overwrite=True).close()
     with pytest.raises(FileNotFoundError):
         Samples(str(tmp_path / "missing.npy"))
