@@ -212,7 +212,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="normal_iid")
-    ap.add_argument("--block", type=int, default=10, help="proposals per step")
+    ap.add_argument("--block", type=int, default=0, help="proposals per step (default: per workload)")
     ap.add_argument("--thinning", type=int, default=1)
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -249,6 +249,9 @@ def main():
     from hmclab_b200._lowering import describe, describe_mass, flatten
 
     w = workloads.BUILDERS[args.workload](**kwargs)
+    if not args.block:
+        # long enough steps that host launch overhead is invisible, short enough for minutes
+        args.block = {"normal_iid": 50, "source_location": 50, "dense_small": 50}.get(args.workload, 1)
     C, d, B, thin = w.chains, w.dims, args.block, args.thinning
     assert B % thin == 0
     eng = Engine(flatten(describe(w.posterior)), describe_mass(w.mass_matrix), C,
@@ -272,16 +275,16 @@ def main():
 
     for k in range(args.warmup):
         step(k)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()      # NVML init takes milliseconds: keep it in front of the barrier
     launches0 = eng.launch_count
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 0xFF)           # evict the previous step's lines from L2 (untimed)
@@ -294,9 +297,14 @@ def main():
         dist.barrier()
     launches = eng.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = sum(step_ms)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    per_rank_ms = [total_ms / args.steps]
     if world > 1:
+        every = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(every, t / args.steps)
+        per_rank_ms = [float(v) for v in every.cpu()]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     evals_per_step = world * C * B * w.grads_per_proposal
@@ -375,6 +383,8 @@ def main():
                    "l2": "256 MiB flush write between timed steps"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu, "acceptance_rate": acc_rate, "wall_s_timed_region": wall,
+        "ms_per_step_by_rank": per_rank_ms,
+        "step_ms_rank0": {"min": min(step_ms), "median": float(np.median(step_ms)), "max": max(step_ms)},
     }
     print(json.dumps(line), flush=True)
     if world > 1:
