@@ -318,15 +318,17 @@ def main():
         out_host = torch.empty(rows, C, d + 1, dtype=torch.float64).pin_memory()
         acc_host = torch.empty(C, dtype=torch.int32).pin_memory()
         n_e2e = max(3, min(args.steps, 10))
+        # sub-blocks so that the D2H of one sub-block overlaps the kernels of the next
+        e2e_block = max(thin, (B // 5) // thin * thin) if B >= 5 * thin else B
         for _ in range(2):
-            eng.sample_host(q0_host, B, stepsize=w.stepsize, thinning=thin, block_proposals=B,
+            eng.sample_host(q0_host, B, stepsize=w.stepsize, thinning=thin, block_proposals=e2e_block,
                             seed=7, chain_offset=chain_offset, samples=out_host, accepted=acc_host)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for i in range(n_e2e):
-            eng.sample_host(q0_host, B, stepsize=w.stepsize, thinning=thin, block_proposals=B,
+            eng.sample_host(q0_host, B, stepsize=w.stepsize, thinning=thin, block_proposals=e2e_block,
                             seed=8 + i, chain_offset=chain_offset, samples=out_host, accepted=acc_host)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0

@@ -159,6 +159,9 @@ hmc_fused_priors_kernel(const FusedArgs A) {
 
   UniformPairCache<TPC> ucache;
   ucache.us = ucache.ua = 0.0;
+  // stored proposals: global index k with k % thinning == 0 (no division inside the loop)
+  long long next_store = (A.proposal_offset + A.thinning - 1) / A.thinning * A.thinning;
+  size_t store_row = 0;
   for (kb = 0; kb < A.proposals; ++kb) {
     const long long kglob = A.proposal_offset + kb;
     const size_t kc = (size_t)kb * C + c;
@@ -242,14 +245,16 @@ hmc_fused_priors_kernel(const FusedArgs A) {
       x = x1;
       ++accepted;
     }
-    if (A.out_samples && live && (kglob % A.thinning) == 0) {
-      const size_t srow = ((size_t)((kglob / A.thinning) - ((A.proposal_offset + A.thinning - 1) / A.thinning)) * C + c) *
-                          (size_t)(d + 1);
+    const bool store_now = kglob == next_store;
+    if (store_now) next_store += A.thinning;
+    if (A.out_samples && live && store_now) {
+      const size_t srow = (store_row * C + c) * (size_t)(d + 1);
 #pragma unroll
       for (int e = 0; e < E; ++e)
         if (ok(e)) A.out_samples[srow + jj[e]] = qc[e];
       if (t == 0) A.out_samples[srow + d] = x;
     }
+    if (store_now) ++store_row;
   }
 
   if (live) {

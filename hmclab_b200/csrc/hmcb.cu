@@ -106,8 +106,12 @@ struct hmcb_engine {
          *lpart = nullptr;
   unsigned* flags[3] = {nullptr, nullptr, nullptr};
   unsigned char* accbuf = nullptr;
-  // hmcb_sample_host
+  // hmcb_sample_host: streams, events and device buffers are created once and reused
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_produced[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
+  double *sh_q = nullptr, *sh_x = nullptr, *sh_buf[2] = {nullptr, nullptr};
+  int32_t* sh_acc = nullptr;
+  size_t sh_buf_doubles = 0;
 };
 
 namespace {
@@ -432,6 +436,11 @@ int hmcb_destroy(hmcb_engine* e) {
   free_device(e);
   if (e->s_compute) cudaStreamDestroy(e->s_compute);
   if (e->s_copy) cudaStreamDestroy(e->s_copy);
+  cudaFree(e->sh_q); cudaFree(e->sh_x); cudaFree(e->sh_acc); cudaFree(e->sh_buf[0]); cudaFree(e->sh_buf[1]);
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_produced[i]) cudaEventDestroy(e->ev_produced[i]);
+    if (e->ev_drained[i]) cudaEventDestroy(e->ev_drained[i]);
+  }
   delete e;
   return 0;
 }
@@ -882,18 +891,10 @@ int hmcb_sample_host(hmcb_engine* e, const double* q0_host, int64_t proposals, i
   if (!e->s_compute) HMCB_CUDA(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
   if (!e->s_copy) HMCB_CUDA(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
 
-  double *dq = nullptr, *dx = nullptr, *dbuf[2] = {nullptr, nullptr};
-  int32_t* dacc = nullptr;
-  cudaEvent_t produced[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
   int rc = 0;
   auto cleanup = [&]() {
     cudaStreamSynchronize(e->s_compute);
     cudaStreamSynchronize(e->s_copy);
-    cudaFree(dq); cudaFree(dx); cudaFree(dacc); cudaFree(dbuf[0]); cudaFree(dbuf[1]);
-    for (int i = 0; i < 2; ++i) {
-      if (produced[i]) cudaEventDestroy(produced[i]);
-      if (drained[i]) cudaEventDestroy(drained[i]);
-    }
   };
 #define HMCB_CUDA_C(expr)                                                             \
   do {                                                                                \
@@ -904,17 +905,28 @@ int hmcb_sample_host(hmcb_engine* e, const double* q0_host, int64_t proposals, i
       return -1;                                                                      \
     }                                                                                 \
   } while (0)
-  HMCB_CUDA_C(cudaMalloc(&dq, C * d * sizeof(double)));
-  HMCB_CUDA_C(cudaMalloc(&dx, C * sizeof(double)));
-  HMCB_CUDA_C(cudaMalloc(&dacc, C * sizeof(int32_t)));
-  if (samples_host) {
-    HMCB_CUDA_C(cudaMalloc(&dbuf[0], rows_per_block * row_doubles * sizeof(double)));
-    HMCB_CUDA_C(cudaMalloc(&dbuf[1], rows_per_block * row_doubles * sizeof(double)));
+  if (!e->sh_q) {
+    HMCB_CUDA_C(cudaMalloc(&e->sh_q, C * d * sizeof(double)));
+    HMCB_CUDA_C(cudaMalloc(&e->sh_x, C * sizeof(double)));
+    HMCB_CUDA_C(cudaMalloc(&e->sh_acc, C * sizeof(int32_t)));
+    for (int i = 0; i < 2; ++i) {
+      HMCB_CUDA_C(cudaEventCreateWithFlags(&e->ev_produced[i], cudaEventDisableTiming));
+      HMCB_CUDA_C(cudaEventCreateWithFlags(&e->ev_drained[i], cudaEventDisableTiming));
+    }
   }
-  for (int i = 0; i < 2; ++i) {
-    HMCB_CUDA_C(cudaEventCreateWithFlags(&produced[i], cudaEventDisableTiming));
-    HMCB_CUDA_C(cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming));
+  if (samples_host && e->sh_buf_doubles < rows_per_block * row_doubles) {
+    for (int i = 0; i < 2; ++i) {
+      if (e->sh_buf[i]) cudaFree(e->sh_buf[i]);
+      e->sh_buf[i] = nullptr;
+    }
+    e->sh_buf_doubles = 0;
+    HMCB_CUDA_C(cudaMalloc(&e->sh_buf[0], rows_per_block * row_doubles * sizeof(double)));
+    HMCB_CUDA_C(cudaMalloc(&e->sh_buf[1], rows_per_block * row_doubles * sizeof(double)));
+    e->sh_buf_doubles = rows_per_block * row_doubles;
   }
+  double *dq = e->sh_q, *dx = e->sh_x, **dbuf = e->sh_buf;
+  int32_t* dacc = e->sh_acc;
+  cudaEvent_t *produced = e->ev_produced, *drained = e->ev_drained;
   HMCB_CUDA_C(cudaMemcpyAsync(dq, q0_host, C * d * sizeof(double), cudaMemcpyHostToDevice, e->s_compute));
   HMCB_CUDA_C(cudaMemsetAsync(dacc, 0, C * sizeof(int32_t), e->s_compute));
   rc = hmcb_misfit(e, dq, dx, e->s_compute);

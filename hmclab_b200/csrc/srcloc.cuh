@@ -194,6 +194,9 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
 
   UniformPairCache<TPC> ucache;
   ucache.us = ucache.ua = 0.0;
+  // stored proposals: global index k with k % thinning == 0 (no division inside the loop)
+  long long next_store = (A.proposal_offset + A.thinning - 1) / A.thinning * A.thinning;
+  size_t store_row = 0;
   for (int kb = 0; kb < A.proposals; ++kb) {
     const long long kglob = A.proposal_offset + kb;
     const size_t kc = (size_t)kb * C + c;
@@ -305,9 +308,10 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
       for (int i = 0; i < 4; ++i) qc[i] = q[i];
       qcv = qv; x = x1; ++accepted;
     }
-    if (A.out_samples && ln.live && (kglob % A.thinning) == 0) {
-      const size_t srow = ((size_t)((kglob / A.thinning) - ((A.proposal_offset + A.thinning - 1) / A.thinning)) * C + c) *
-                          (size_t)(d + 1);
+    const bool store_now = kglob == next_store;
+    if (store_now) next_store += A.thinning;
+    if (A.out_samples && ln.live && store_now) {
+      const size_t srow = (store_row * C + c) * (size_t)(d + 1);
       if (ln.lead) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) A.out_samples[srow + j0 + i] = qc[i];
@@ -317,6 +321,7 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
         A.out_samples[srow + d] = x;
       }
     }
+    if (store_now) ++store_row;
   }
 
   if (ln.live) {

@@ -127,3 +127,57 @@ def test_full_size_config2_fused_equals_staged_pipeline():
     assert 0.05 < f[2].mean() < 0.999                 # both decisions occur at this step size
     # energy error of a leapfrog trajectory is O(eps^2): a coarse sanity bound on H1 - H0
     assert np.median(np.abs(f[4] - f[3])) < 5.0
+
+
+@pytest.mark.parametrize("name", ["normal_iid", "dense_large", "dense_large_premult", "tomography",
+                                  "source_location"])
+def test_full_size_trajectories_are_time_reversible(name):
+    """At BASELINE.json's full sizes (no oracle can follow there): integrating forward, flipping
+    the momentum and integrating again must return every chain to its start -- a property of
+    the symmetric lf/3s/4s schemes that any error in the gradient, the mass matrix, the
+    stage coefficients or the chain indexing of a kernel would break."""
+    import torch
+
+    from hmclab_b200._engine import Engine
+
+    w = workloads.BUILDERS[name]()
+    C, d = w.chains, w.dims
+    mtree = describe_mass(w.mass_matrix)
+    eng = Engine(flatten(describe(w.posterior)), mtree, C, integrator=w.integrator,
+                 amount_of_steps=w.amount_of_steps)
+    sqrtm = (torch.as_tensor(np.sqrt(mtree["diagonal"])).cuda() if mtree["kind"] == "diagonal"
+             else torch.ones(d, dtype=torch.float64, device="cuda"))
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    q0 = torch.as_tensor(w.initial_models).cuda().contiguous()
+    z = torch.randn(1, C, d, dtype=torch.float64, device="cuda", generator=gen)
+    us = torch.ones(1, C, dtype=torch.float64, device="cuda")
+    ua = torch.zeros(1, C, dtype=torch.float64, device="cuda")
+
+    def trajectory(q_start, z_in):
+        q = q_start.clone()
+        x = eng.misfit(q)
+        q1 = torch.empty(1, C, d, dtype=torch.float64, device="cuda")
+        p1 = torch.empty(1, C, d, dtype=torch.float64, device="cuda")
+        h0 = torch.empty(1, C, dtype=torch.float64, device="cuda")
+        h1 = torch.empty(1, C, dtype=torch.float64, device="cuda")
+        eng.run_block(q, x, 1, stepsize=w.stepsize, randomize_stepsize=False, z=z_in, u_step=us,
+                      u_accept=ua, out_q_prop=q1, out_p_prop=p1, out_h0=h0, out_h1=h1)
+        return q1[0], p1[0], h0[0], h1[0]
+
+    q1, p1, h0, h1 = trajectory(q0, z)
+    assert torch.isfinite(h1).all()
+    moved = (q1 - q0).abs().max().item()
+    assert moved > 0
+    # energy is conserved up to the integrator's O(eps^2) error
+    assert (h1 - h0).abs().median().item() < 10.0
+    q2, p2, _, _ = trajectory(q1.contiguous(), (-(p1 / sqrtm)).unsqueeze(0).contiguous())
+    scale = max(q0.abs().max().item(), 1e-300)
+    assert (q2 - q0).abs().max().item() < 1e-9 * scale
+    p0 = z[0] * sqrtm
+    assert (p2 + p0).abs().max().item() < 1e-8 * p0.abs().max().item()
+
+
+def test_single_chain_single_dimension():
+    w = workloads.normal_iid(dims=1, chains=1)
+    eng, ref = _compare_with_oracle(w, K=5, chains_checked=1)
+    assert eng.path == "fused_priors"
