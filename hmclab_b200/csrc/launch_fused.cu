@@ -10,8 +10,8 @@ namespace hmcb {
 
 // Instantiated (TPC, PPT) shapes of the priors-only fused kernel: pairs = ceil(dims / 2)
 // coordinate pairs are spread over TPC threads x PPT pairs each.
-static const int kShapes[][2] = {{2, 1},   {8, 1},   {32, 1},  {64, 1},  {128, 1}, {512, 1},
-                                 {128, 2}, {256, 2}, {512, 2}, {128, 4}, {512, 4}};
+static const int kShapes[][2] = {{2, 1},   {8, 1},   {32, 1},  {64, 1}, {128, 1},
+                                 {128, 2}, {256, 2}, {128, 4}, {256, 4}};
 
 static bool shape_instantiated(int tpc, int ppt) {
   for (const auto& sh : kShapes)
@@ -28,9 +28,8 @@ void fused_priors_shape(int dims, int* tpc, int* ppt) {
   else if (pairs <= 64) { T = 64; P = 1; }
   else if (pairs <= 128) { T = 128; P = 1; }
   else if (pairs <= 256) { T = 128; P = 2; }
-  else if (pairs <= 512) { T = 256; P = 2; }
-  else if (pairs <= 1024) { T = 512; P = 2; }
-  else if (pairs <= 2048) { T = 512; P = 4; }  // beyond: the staged path takes over
+  else if (pairs <= 512) { T = 128; P = 4; }   // 1000 dims: measured best of the instantiated shapes
+  else if (pairs <= 1024) { T = 256; P = 4; }  // beyond 2048 dims the staged path takes over
   if (const char* env = std::getenv("HMCB_FUSED_SHAPE")) {  // tuning override "TPC,PPT"
     int t = 0, p = 0;
     if (std::sscanf(env, "%d,%d", &t, &p) == 2 && shape_instantiated(t, p) && t * p >= pairs) { T = t; P = p; }

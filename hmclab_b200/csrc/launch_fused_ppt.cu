@@ -31,14 +31,12 @@ cudaError_t HMCB_CAT(launch_fused_priors_ppt, HMCB_PPT)(const FusedArgs& A, int 
     case 32: return launch_fp<32, 1>(A, s);
     case 64: return launch_fp<64, 1>(A, s);
     case 128: return launch_fp<128, 1>(A, s);
-    case 512: return launch_fp<512, 1>(A, s);
 #elif HMCB_PPT == 2
     case 128: return launch_fp<128, 2>(A, s);
     case 256: return launch_fp<256, 2>(A, s);
-    case 512: return launch_fp<512, 2>(A, s);
 #elif HMCB_PPT == 4
     case 128: return launch_fp<128, 4>(A, s);
-    case 512: return launch_fp<512, 4>(A, s);
+    case 256: return launch_fp<256, 4>(A, s);
 #endif
   }
   return cudaErrorInvalidConfiguration;

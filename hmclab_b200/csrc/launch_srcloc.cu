@@ -14,7 +14,8 @@ static int pow2_ceil(int v) {
 
 // Lanes per event: each lane walks stations sub, sub+LPE, ...
 static int srcloc_lpe(int stations) {
-  int lpe = stations <= 12 ? 1 : (stations <= 40 ? 2 : 4);
+  // measured on config 5 (30 stations): 1 lane per event 5.5e8, 2 lanes 4.6e8, 4 lanes 2.6e8 evals/s
+  int lpe = stations <= 48 ? 1 : (stations <= 128 ? 2 : 4);
   if (const char* env = std::getenv("HMCB_SRCLOC_LPE")) {
     const int v = std::atoi(env);
     if (v == 1 || v == 2 || v == 4) lpe = v;

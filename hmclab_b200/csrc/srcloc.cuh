@@ -20,41 +20,55 @@ struct SrcLocDev {
 };
 
 struct SrcLocShared {
-  const double *rx, *ry, *rz, *tobs, *inv_var, *inv_sigma;
+  const double2* xy;    // [S] station (x, y)
+  const double* z;      // [S] station z
+  const double2* pick;  // [E x S] (t_obs, 1/sigma^2); a missing pick is stored as (0, 0)
 };
 
-// Shared-memory doubles: 3 station coordinate rows + observed times, 1/sigma^2, 1/sigma.
+// Shared-memory doubles: 3 per station + 2 per event-station pair.
 __host__ __device__ inline size_t srcloc_smem_doubles(int events, int stations) {
-  return 3 * (size_t)stations + 3 * (size_t)events * stations;
+  return 3 * (size_t)stations + 2 * (size_t)events * stations + 2;
 }
 
 __device__ __forceinline__ SrcLocShared srcloc_stage(const SrcLocDev& L, double* smem) {
   const int S = L.stations, ES = L.events * L.stations;
-  double* rx = smem; double* ry = rx + S; double* rz = ry + S;
-  double* tobs = rz + S; double* iv = tobs + ES; double* is = iv + ES;
+  double2* pick = reinterpret_cast<double2*>(smem);          // 16-byte aligned
+  double2* xy = pick + ES;
+  double* z = reinterpret_cast<double*>(xy + S);
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
-    rx[i] = L.rx[i]; ry[i] = L.ry[i]; rz[i] = L.rz[i];
+    xy[i] = make_double2(L.rx[i], L.ry[i]);
+    z[i] = L.rz[i];
   }
   for (int i = threadIdx.x; i < ES; i += blockDim.x) {
-    const double sd = L.std[i];
-    tobs[i] = L.tobs[i];
-    iv[i] = __ddiv_rn(1.0, __dmul_rn(sd, sd));
-    is[i] = __ddiv_rn(1.0, sd);
+    const double sd = L.std[i], t = L.tobs[i];
+    const double iv = __ddiv_rn(1.0, __dmul_rn(sd, sd));
+    // nansum (SourceLocation.py:487-490, 519-523) drops a pair whose pick or uncertainty is
+    // NaN from every sum: a zero weight does the same without a per-term test
+    const bool missing = (t != t) || (iv != iv);
+    pick[i] = missing ? make_double2(0.0, 0.0) : make_double2(t, iv);
   }
   __syncthreads();
-  return SrcLocShared{rx, ry, rz, tobs, iv, is};
+  return SrcLocShared{xy, z, pick};
 }
 
 __device__ __forceinline__ double nan_to_zero(double v) { return (v != v) ? 0.0 : v; }
 
+// 1/sqrt(d2) for d2 >= 0 without special-case paths; 0 for d2 == 0, so that a source on top of
+// a station contributes no direction term (the reference drops its 0/0 through nansum).
+__device__ __forceinline__ double rsqrt_or_zero(double d2) {
+  double y = rsqrt_seed(d2);
+  const double h = 0.5 * d2;
+  y = fma(y, fma(-(h * y), y, 0.5), y);
+  y = fma(y, fma(-(h * y), y, 0.5), y);
+  return (d2 > 0.0) ? y : 0.0;
+}
+
 // The reference evaluates, per event-station pair, dist = sqrt(.), t = T + dist / v,
 // w = (t - t_obs) / sigma^2 and the direction terms dx / (v * dist) (SourceLocation.py:495-524):
 // six IEEE divisions and a square root.  Here one reciprocal square root per pair and
-// precomputed reciprocals (1/v, 1/sigma^2, 1/sigma) replace them; every product still rounds
-// once, so terms agree with the reference to a few ulp (the sums over stations already differ
-// from numpy's pairwise order at that level; parity tolerance is 1e-10).  NaN semantics of
-// nansum are kept term by term: a missing pick (NaN t_obs) drops the pair from every sum, a
-// zero distance (0/0 direction) drops only the direction terms.
+// precomputed reciprocals (1/v, 1/sigma^2) replace them and the sums are accumulated with FMAs;
+// terms agree with the reference to a few ulp (the sums over stations already differ from
+// numpy's pairwise order at that level; parity tolerance is 1e-10).
 template <int LPE>
 __device__ __forceinline__ void srcloc_gradient_partial(const SrcLocShared& M, int S, int e, int sub,
                                                         double x, double y, double z, double T,
@@ -62,21 +76,28 @@ __device__ __forceinline__ void srcloc_gradient_partial(const SrcLocShared& M, i
                                                         double& gy, double& gz, double& gT, double& gv) {
   gx = gy = gz = gT = gv = 0.0;
   const double neg_inv_vv = -__dmul_rn(inv_v, inv_v);
+  const double2* pick = M.pick + e * S;
 #pragma unroll 3
   for (int s = sub; s < S; s += LPE) {
-    const double dx = __dsub_rn(x, M.rx[s]), dy = __dsub_rn(y, M.ry[s]), dz = __dsub_rn(z, M.rz[s]);
-    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    const double rinv = rsqrt(d2);
+    const double2 r = M.xy[s];
+    const double2 pk = pick[s];
+    const double dx = __dsub_rn(x, r.x), dy = __dsub_rn(y, r.y), dz = __dsub_rn(z, M.z[s]);
+    const double d2 = fma(dx, dx, fma(dy, dy, __dmul_rn(dz, dz)));
+    const double rinv = rsqrt_or_zero(d2);
     const double dist = __dmul_rn(d2, rinv);
-    const double tcalc = __dadd_rn(T, __dmul_rn(dist, inv_v));
-    const double w = __dmul_rn(__dsub_rn(tcalc, M.tobs[e * S + s]), M.inv_var[e * S + s]);
+    const double tcalc = fma(dist, inv_v, T);
+    const double w = __dmul_rn(__dsub_rn(tcalc, pk.x), pk.y);
     const double u = __dmul_rn(w, __dmul_rn(inv_v, rinv));  // w / (v * dist)
-    gx = __dadd_rn(gx, nan_to_zero(__dmul_rn(u, dx)));
-    gy = __dadd_rn(gy, nan_to_zero(__dmul_rn(u, dy)));
-    gz = __dadd_rn(gz, nan_to_zero(__dmul_rn(u, dz)));
-    gT = __dadd_rn(gT, nan_to_zero(w));
-    if (want_gv) gv = __dadd_rn(gv, nan_to_zero(__dmul_rn(w, __dmul_rn(dist, neg_inv_vv))));
+    gx = fma(u, dx, gx);
+    gy = fma(u, dy, gy);
+    gz = fma(u, dz, gz);
+    gT = __dadd_rn(gT, w);
+    if (want_gv) gv = fma(w, __dmul_rn(dist, neg_inv_vv), gv);
   }
+  // A trajectory that has already diverged (non-finite coordinates) makes every term NaN;
+  // nansum returns 0 for such a sum, and the bounds term then decides (+inf).
+  gx = nan_to_zero(gx); gy = nan_to_zero(gy); gz = nan_to_zero(gz); gT = nan_to_zero(gT);
+  gv = nan_to_zero(gv);
 }
 
 // Partial sum of squared standardised residuals of event e (SourceLocation.py:482-493).
@@ -85,16 +106,18 @@ __device__ __forceinline__ double srcloc_misfit_partial(const SrcLocShared& M, i
                                                         double x, double y, double z, double T,
                                                         double inv_v) {
   double acc = 0.0;
+  const double2* pick = M.pick + e * S;
 #pragma unroll 3
   for (int s = sub; s < S; s += LPE) {
-    const double dx = __dsub_rn(x, M.rx[s]), dy = __dsub_rn(y, M.ry[s]), dz = __dsub_rn(z, M.rz[s]);
-    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    const double dist = sqrt(d2);
-    const double r = __dmul_rn(__dsub_rn(M.tobs[e * S + s], __dadd_rn(T, __dmul_rn(dist, inv_v))),
-                               M.inv_sigma[e * S + s]);
-    acc = __dadd_rn(acc, nan_to_zero(__dmul_rn(r, r)));
+    const double2 r = M.xy[s];
+    const double2 pk = pick[s];
+    const double dx = __dsub_rn(x, r.x), dy = __dsub_rn(y, r.y), dz = __dsub_rn(z, M.z[s]);
+    const double d2 = fma(dx, dx, fma(dy, dy, __dmul_rn(dz, dz)));
+    const double dist = __dmul_rn(d2, rsqrt_or_zero(d2));
+    const double res = __dsub_rn(pk.x, fma(dist, inv_v, T));
+    acc = fma(__dmul_rn(res, res), pk.y, acc);
   }
-  return acc;
+  return nan_to_zero(acc);
 }
 
 template <int LPE>
@@ -171,7 +194,7 @@ __device__ __forceinline__ unsigned srcloc_violations(const DevTarget& T, const 
 template <int TPC, int LPE>
 __global__ void __launch_bounds__((TPC <= 32 ? 256 : TPC), (TPC <= 256 ? 2 : 1))
 hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
-  extern __shared__ double dyn_smem[];
+  extern __shared__ __align__(16) double dyn_smem[];
   __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(TPC <= 32 ? 256 : TPC)];
   const ChainReduce<TPC> red{scratch};
   const SrcLocShared M = srcloc_stage(L, dyn_smem);
@@ -342,7 +365,7 @@ template <int TPC, int LPE>
 __global__ void __launch_bounds__((TPC <= 32 ? 256 : TPC))
 srcloc_eval_kernel(const DevTarget T, const SrcLocDev L, int chains, int mode,
                    const double* __restrict__ qin, double* __restrict__ out) {
-  extern __shared__ double dyn_smem[];
+  extern __shared__ __align__(16) double dyn_smem[];
   __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(TPC <= 32 ? 256 : TPC)];
   const ChainReduce<TPC> red{scratch};
   const SrcLocShared M = srcloc_stage(L, dyn_smem);
