@@ -41,10 +41,11 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                : "d"(a), "d"(b));
 }
 
-// Epilogue concept:
-//   __device__ void tile_begin(int m0, int n0);
-//   __device__ void operator()(int m, int n, double v0, double v1);   // Y[m][n], Y[m][n+1]
-//   __device__ void tile_end(int m0, int n0, double* smem);           // block-wide, after a sync
+// Epilogue concept (GEMM side):
+//   __device__ void tile(int m0, int n0, int base_m, int base_n, const double (&acc)[8][4][2],
+//                        double* smem);
+// called once per thread with its 64 accumulators: acc[i][j][h] = Y[base_m + 8 i][base_n + 8 j + h];
+// `smem` is the (now idle) pipeline buffer for block-wide reductions.
 template <class Epilogue>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
@@ -116,39 +117,36 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
   cp_async_wait<0>();
   __syncthreads();
 
-  // C frag: row = lane/4, cols = 2*(lane%4) + {0,1}
-  epi.tile_begin(m0, n0);
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      epi(m0 + wm * 64 + i * 8 + (lane >> 2), n0 + wn * 32 + j * 8 + 2 * (lane & 3), acc[i][j][0],
-          acc[i][j][1]);
-  epi.tile_end(m0, n0, gemm_smem);
+  // C frag of sub-tile (i, j): row = base_m + 8 i, columns base_n + 8 j + {0, 1}
+  epi.tile(m0, n0, m0 + wm * 64 + (lane >> 2), n0 + wn * 32 + 2 * (lane & 3), acc, gemm_smem);
 }
 
 // ------------------------------------------------------------------------ CSR SpMM ---
-// Y[i][c] = sum_k data[k] * B[indices[k]][c] for rows i of a CSR matrix; thread = chain,
-// block = 128 chains x one chunk of rows.  (col, val) loads are warp-uniform, the gather of
-// a B row is one coalesced 1 KB line per block.  The row chunk is the fast grid index, so
-// the blocks resident at any time work on two or three 128-chain slabs of B (10 MB each at
-// 10 000 rows), which then stay in L2 instead of being re-fetched from HBM by every chunk.
+// Y[i][c] = sum_k data[k] * B[indices[k]][c] for rows i of a CSR matrix.
+// lane = chain inside a 32-chain slab, the 4 warps of a block interleave the rows of one row
+// chunk.  (col, val) loads are warp-uniform; the gather of a B row is one coalesced 256 B
+// segment per warp.  The gathers are the traffic that matters (nnz x chains x 8 B per product,
+// 383 GB at config 4) and nothing on chip can hold a slab of B, so the grid is ordered to keep
+// them in L2: the chunk index is the fast one and the host sizes the chunks so that the few
+// slabs in flight at any time (rows(B) x 256 B each) fit in L2 together.
 constexpr int SPMM_THREADS = 128;
+constexpr int SPMM_WARPS = SPMM_THREADS / 32;
+constexpr int SPMM_SLAB = 32;
 
 template <class Epilogue>
 __global__ void __launch_bounds__(SPMM_THREADS)
 csr_spmm_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
                 const double* __restrict__ data, int rows, int rows_per_chunk,
                 const double* __restrict__ B, int ldb, Epilogue epi) {
-  const int chunk = blockIdx.x;
-  const int c = blockIdx.y * SPMM_THREADS + threadIdx.x;
+  const int chunk = blockIdx.x, warp = threadIdx.x >> 5;
+  const int c = blockIdx.y * SPMM_SLAB + (threadIdx.x & 31);
   const int r_begin = chunk * rows_per_chunk;
   const int r_end = min(rows, r_begin + rows_per_chunk);
   const double* Bc = B + c;
-  epi.tile_begin(r_begin, blockIdx.y * SPMM_THREADS);
-  for (int i = r_begin; i < r_end; ++i) {
+  epi.tile_begin(r_begin, blockIdx.y * SPMM_SLAB);
+  for (int i = r_begin + warp; i < r_end; i += SPMM_WARPS) {
     const int k0 = __ldg(indptr + i), k1 = __ldg(indptr + i + 1);
-    double acc = 0.0;
+    double acc0 = 0.0, acc1 = 0.0;
     int k = k0;
     for (; k + 4 <= k1; k += 4) {
       const int j0 = __ldg(indices + k), j1 = __ldg(indices + k + 1), j2 = __ldg(indices + k + 2),
@@ -157,12 +155,12 @@ csr_spmm_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
                    v3 = __ldg(data + k + 3);
       const double b0 = Bc[(size_t)j0 * ldb], b1 = Bc[(size_t)j1 * ldb], b2 = Bc[(size_t)j2 * ldb],
                    b3 = Bc[(size_t)j3 * ldb];
-      acc = fma(v0, b0, acc); acc = fma(v1, b1, acc); acc = fma(v2, b2, acc); acc = fma(v3, b3, acc);
+      acc0 = fma(v0, b0, acc0); acc1 = fma(v1, b1, acc1); acc0 = fma(v2, b2, acc0); acc1 = fma(v3, b3, acc1);
     }
-    for (; k < k1; ++k) acc = fma(__ldg(data + k), Bc[(size_t)__ldg(indices + k) * ldb], acc);
-    epi.row(i, c, acc);
+    for (; k < k1; ++k) acc0 = fma(__ldg(data + k), Bc[(size_t)__ldg(indices + k) * ldb], acc0);
+    epi.row(i, c, acc0 + acc1);
   }
-  epi.chunk_end(chunk, c);
+  epi.chunk_end(chunk * SPMM_WARPS + warp, c);
 }
 
 }  // namespace hmcb

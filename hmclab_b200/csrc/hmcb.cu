@@ -206,8 +206,15 @@ int upload_csr(hmcb_engine* e, const HostCsr& m, CsrDev* out) {
   if (dev_upload(e, m.indptr, &ip) || dev_upload(e, m.indices, &ix) || dev_upload(e, m.data, &dv)) return -1;
   out->indptr = ip; out->indices = ix; out->data = dv;
   out->rows = (int)m.rows;
-  out->rows_per_chunk = 64;
-  out->chunks = (int)((m.rows + 63) / 64);
+  // Row chunks (one per block, 4 warps interleaving its rows) are sized so that the chain
+  // slabs of the gathered operand in flight at any time fit in L2 together: a slab is
+  // cols x 256 B, about 148 SMs x 16 blocks are resident, slabs in flight = resident / chunks.
+  const double slab_bytes = (double)m.cols * SPMM_SLAB * sizeof(double);
+  const double min_chunks = std::max(1.0, 2368.0 * slab_bytes / (48.0 * 1024 * 1024));
+  int64_t rpc = (int64_t)((double)m.rows / min_chunks);
+  rpc = std::max<int64_t>(SPMM_WARPS, std::min<int64_t>(64, rpc / SPMM_WARPS * SPMM_WARPS));
+  out->rows_per_chunk = (int)rpc;
+  out->chunks = (int)((m.rows + rpc - 1) / rpc);
   return 0;
 }
 
@@ -722,13 +729,13 @@ int hmcb_finalize(hmcb_engine* e) {
         break;
       case LK_CSR_DIRECT:
         if (upload_csr(e, e->csr, &e->csr_dev) || upload_csr(e, e->csr_t, &e->csr_t_dev)) return -1;
-        e->ltiles = e->csr_dev.chunks;
+        e->ltiles = e->csr_dev.chunks * SPMM_WARPS;
         break;
       case LK_CSR_PREMULT:
         if (upload_csr(e, e->csr, &e->csr_dev)) return -1;
         if (dev_upload(e, e->h_vec, &tmp)) return -1;
         e->dvec = const_cast<double*>(tmp);
-        e->ltiles = e->csr_dev.chunks;
+        e->ltiles = e->csr_dev.chunks * SPMM_WARPS;
         break;
       default: return fail("internal: bad likelihood kind");
     }

@@ -44,7 +44,7 @@ cudaError_t launch_gemm_misfit(const double* A, int lda, int M, const double* B,
 template <class Epi>
 static cudaError_t launch_spmm(const CsrDev& M, const double* B, int ldb, const Epi& epi,
                                cudaStream_t s) {
-  const dim3 grid(M.chunks, ldb / SPMM_THREADS);  // chunk index fastest: L2-resident chain slabs
+  const dim3 grid(M.chunks, ldb / SPMM_SLAB);  // chunk index fastest: L2-resident chain slabs
   csr_spmm_kernel<Epi><<<grid, SPMM_THREADS, 0, s>>>(M.indptr, M.indices, M.data, M.rows,
                                                      M.rows_per_chunk, B, ldb, epi);
   return cudaGetLastError();

@@ -61,14 +61,72 @@ struct UpdateEpi {
       if (m) atomicOr(flags_out + c, m);
     }
   }
-  // GEMM interface
-  __device__ __forceinline__ void tile_begin(int, int) {}
-  __device__ __forceinline__ void operator()(int m, int n, double v0, double v1) const {
-    apply(m, n, v0);
-    apply(m, n + 1, v1);
+  // GEMM interface: the thread's fragment is 8 rows x 4 column pairs.  Everything that
+  // depends only on the coordinate (prior slot, Gtd0, mass, reflection bounds) is loaded once
+  // per row, everything that depends only on the chain (eps, bound flags) once per column
+  // pair, and q / p move as 16-byte pairs.
+  __device__ __forceinline__ void tile(int, int, int base_m, int base_n, const double (&acc)[8][4][2],
+                                       double*) const {
+    if (T.n_terms > 1 || grad_only || trace_q) {   // generic element-wise path
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          apply(base_m + 8 * i, base_n + 8 * j, acc[i][j][0]);
+          apply(base_m + 8 * i, base_n + 8 * j + 1, acc[i][j][1]);
+        }
+      return;
+    }
+    double2 e2[4];
+    uint2 fl[4];
+    bool col_ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = base_n + 8 * j;
+      col_ok[j] = c < C;
+      e2[j] = col_ok[j] ? *reinterpret_cast<const double2*>(eps + c) : make_double2(0.0, 0.0);
+      fl[j] = (flags_in && col_ok[j]) ? *reinterpret_cast<const uint2*>(flags_in + c) : make_uint2(0u, 0u);
+    }
+    const bool has_refl = T.refl_lb != nullptr || T.refl_ub != nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = base_m + 8 * i;
+      if (m >= T.dims) continue;
+      const int kind = T.n_terms ? (int)__ldg(T.t_kind + m) : TERM_NONE;
+      const double ta = T.n_terms ? __ldg(T.t_a + m) : 0.0, tb = T.n_terms ? __ldg(T.t_b + m) : 0.0;
+      const double sub_m = sub ? __ldg(sub + m) : 0.0;
+      const double im = T.invm ? __ldg(T.invm + m) : 1.0;
+      const double lb = T.refl_lb ? __ldg(T.refl_lb + m) : -CUDART_INF;
+      const double ub = T.refl_ub ? __ldg(T.refl_ub + m) : CUDART_INF;
+      const unsigned cover = (T.grad_check_mask && T.n_checks) ? (unsigned)__ldg(T.c_cover + m) & T.grad_check_mask : 0u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!col_ok[j]) continue;
+        const size_t o = (size_t)m * ld + base_n + 8 * j;
+        double2 q2 = *reinterpret_cast<const double2*>(q_in + o);
+        double2 p2 = *reinterpret_cast<double2*>(p + o);
+        auto one = [&](double y, double& q, double& pp, double e, unsigned flag, int c) {
+          const double lik = sub ? __dsub_rn(y, sub_m) : y;
+          double g = kind ? __dadd_rn(0.0, term_gradient(kind, ta, tb, q)) : 0.0;
+          if (flag & cover) g = __dadd_rn(g, CUDART_INF);
+          g = __dadd_rn(g, lik);
+          momentum_update(__dmul_rn(b_mult, e), g, pp);
+          q = __dadd_rn(q, __dmul_rn(__dmul_rn(a_mult, e), T.invm ? __dmul_rn(im, pp) : pp));
+          if (has_refl) reflect_on(lb, ub, q, pp);
+          if (flags_out) {
+            const unsigned v = bound_violations(T, m, q);
+            if (v) atomicOr(flags_out + c, v);
+          }
+        };
+        one(acc[i][j][0], q2.x, p2.x, e2[j].x, fl[j].x, base_n + 8 * j);
+        one(acc[i][j][1], q2.y, p2.y, e2[j].y, fl[j].y, base_n + 8 * j + 1);
+        *reinterpret_cast<double2*>(p + o) = p2;
+        *reinterpret_cast<double2*>(q_out + o) = q2;
+      }
+    }
   }
-  __device__ __forceinline__ void tile_end(int, int, double*) {}
   // SpMM interface
+  __device__ __forceinline__ void tile_begin(int, int) {}
   __device__ __forceinline__ void row(int i, int c, double y) const { apply(i, c, y); }
   __device__ __forceinline__ void chunk_end(int, int) {}
 };
@@ -83,12 +141,23 @@ struct ResidualEpi {
     if (i >= N || c >= C) return;
     R[(size_t)i * ld + c] = __ddiv_rn(__dsub_rn(y, __ldg(dvec + i)), __ldg(var + i));
   }
-  __device__ __forceinline__ void tile_begin(int, int) {}
-  __device__ __forceinline__ void operator()(int m, int n, double v0, double v1) const {
-    apply(m, n, v0);
-    apply(m, n + 1, v1);
+  __device__ __forceinline__ void tile(int, int, int base_m, int base_n, const double (&acc)[8][4][2],
+                                       double*) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = base_m + 8 * i;
+      if (m >= N) continue;
+      const double dm = __ldg(dvec + m), vm = __ldg(var + m);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = base_n + 8 * j;
+        if (c >= C) continue;   // c + 1 may be a padding column: harmless, never read back
+        *reinterpret_cast<double2*>(R + (size_t)m * ld + c) =
+            make_double2(__ddiv_rn(__dsub_rn(acc[i][j][0], dm), vm), __ddiv_rn(__dsub_rn(acc[i][j][1], dm), vm));
+      }
+    }
   }
-  __device__ __forceinline__ void tile_end(int, int, double*) {}
+  __device__ __forceinline__ void tile_begin(int, int) {}
   __device__ __forceinline__ void row(int i, int c, double y) const { apply(i, c, y); }
   __device__ __forceinline__ void chunk_end(int, int) {}
 };
@@ -103,7 +172,6 @@ struct MisfitEpi {
   const double* sigma;  // [N] (direct)
   const double* q;      // working positions [dpad x ld] (premult)
   double* part;         // [tiles x ld]
-  double cs[4][2];      // GEMM: this thread's column sums
   double acc;           // SpMM: this thread's (= chain's) sum
 
   __device__ __forceinline__ double term(int i, int c, double y) const {
@@ -115,25 +183,17 @@ struct MisfitEpi {
     const double r = __ddiv_rn(__dsub_rn(y, __ldg(vec + i)), __ldg(sigma + i));
     return __dmul_rn(r, r);
   }
-  __device__ __forceinline__ void tile_begin(int, int) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) cs[j][0] = cs[j][1] = 0.0;
-    acc = 0.0;
-  }
-  __device__ __forceinline__ void operator()(int m, int n, double v0, double v1) {
-    // called with j (the N sub-tile index) fixed per 8 consecutive calls pattern: recover it
-    const int j = ((n - (int)blockIdx.x * GEMM_BN) >> 3) & 3;
-    cs[j][0] = __dadd_rn(cs[j][0], term(m, n, v0));
-    cs[j][1] = __dadd_rn(cs[j][1], term(m, n + 1, v1));
-  }
-  __device__ __forceinline__ void tile_end(int m0, int n0, double* smem) {
+  __device__ __forceinline__ void tile(int m0, int n0, int base_m, int base_n, const double (&a)[8][4][2],
+                                       double* smem) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wm = warp >> 2, wn = warp & 3;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        double v = cs[j][h];
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v = __dadd_rn(v, term(base_m + 8 * i, base_n + 8 * j + h, a[i][j][h]));
         v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
         v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 8));
         v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 16));
@@ -145,6 +205,7 @@ struct MisfitEpi {
       part[(size_t)(m0 / GEMM_BM) * ld + n0 + threadIdx.x] = v;
     }
   }
+  __device__ __forceinline__ void tile_begin(int, int) { acc = 0.0; }
   __device__ __forceinline__ void row(int i, int c, double y) { acc = __dadd_rn(acc, term(i, c, y)); }
   __device__ __forceinline__ void chunk_end(int chunk, int c) { part[(size_t)chunk * ld + c] = acc; }
 };
