@@ -349,11 +349,18 @@ def main():
     # ---- roofline of the dominant kernel ---------------------------------------------------
     peaks = measured_peaks()
     ms_per_step = total_ms / args.steps
+    traffic = None   # dram bytes of one launch from the committed ncu capture, if it matches this run
+    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            rec = json.load(f).get(args.workload)
+        if rec and rec["proposals_per_launch"] == B and thin == 1 and not args.chains:
+            traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
     if eng.path in ("fused_priors", "fused_srcloc"):
         abytes = algorithmic_bytes_per_step(w, B, thin)
         achieved = abytes / (ms_per_step * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                     "kernel": "hmc_fused_priors_kernel" if eng.path == "fused_priors" else "hmc_fused_srcloc_kernel",
                     "algorithmic_bytes_per_launch": abytes, "peak_source": peaks["source"],
                     "note": "one launch per step; fp64 SIMT pipe, not HBM, limits this kernel (see DESIGN.md)"}
