@@ -10,9 +10,10 @@ stored samples to the reference's ``Samples`` file format and checks ``max_time`
 Ctrl-C, so an interrupted run leaves a valid file exactly like the reference
 (:684-704).
 
-Not offered on this path (they raise): ``autotuning`` (Samplers.py:1494-1522, a "next"
-item) and ``diagnostic_mode`` (the per-function timers make no sense for fused kernels;
-use ``get_diagnostics()`` for block-level timings).
+``autotuning=True`` adapts one step size per chain on the device with the reference's
+update rule (Samplers.py:1494-1522).  Not offered on this path (it raises):
+``diagnostic_mode`` (the per-function timers make no sense for fused kernels; use
+``get_diagnostics()`` for block-level timings).
 """
 from __future__ import annotations
 
@@ -259,8 +260,10 @@ class HMC:
         if len(kwargs) != 0:
             raise TypeError(f"Unidentified argument(s) not applicable to sampler: {kwargs}")
         if self.autotuning:
-            raise NotImplementedError(
-                "Step-size autotuning (Samplers.py:1494-1522) is not part of the batched path yet.")
+            # Samplers.py:1334-1341; every chain adapts its own step size on the device
+            assert self.learning_rate > 0.5 and self.learning_rate <= 1.0, (
+                f"The learning rate should be larger than 0.5 and smaller than or equal to 1.0, "
+                f"otherwise the Markov chain does not converge. Chosen: {self.learning_rate}")
         self.stepsize = float(self.stepsize)
         assert self.stepsize > 0.0, "Stepsize should be a float larger than zero."
         assert type(self.amount_of_steps) == int, (
@@ -323,6 +326,19 @@ class HMC:
         hbuf = [torch.empty(rows_max, C, d + 1, dtype=torch.float64).pin_memory() for _ in range(2)]
         accepted = torch.zeros(C, dtype=torch.int32, device=dev)
         copy_stream = torch.cuda.Stream(device=dev)
+        tune = {}
+        history = None
+        self._history = None
+        if self.autotuning:
+            self._stepsize_chain = torch.full((C,), self.stepsize, dtype=torch.float64, device=dev)
+            tune = dict(stepsize_chain=self._stepsize_chain, autotune=True,
+                        target_acceptance_rate=self.target_acceptance_rate,
+                        learning_rate=self.learning_rate)
+            # per-proposal histories like the reference's (Samplers.py:1340-1341), kept on the
+            # host; skipped when they would be larger than ~32 MB
+            if self.proposals * C <= 4_000_000:
+                history = {"stepsizes": [], "h0": [], "h1": []}
+                self._history = history
         copied = [None, None]      # event: D2H of slot finished
         pending = None             # (slot, rows) waiting to be written to disk
         # the device RNG key: one draw from the sampler's Generator (reproducible per seed)
@@ -357,7 +373,11 @@ class HMC:
                 eng.run_block(self._q, self._x, B, stepsize=self.stepsize,
                               randomize_stepsize=self.randomize_stepsize, thinning=thin,
                               proposal_offset=done, chain_offset=self.chain_offset, seed=device_seed,
-                              out_samples=dbuf[slot][:rows], accepted_total=accepted, **draws)
+                              out_samples=dbuf[slot][:rows], accepted_total=accepted, **draws,
+                              **tune, **self._history_buffers(history, B))
+                if history is not None:
+                    for key in history:
+                        history[key].append(self._hist[key][:B].cpu().numpy())
                 produced = torch.cuda.Event()
                 produced.record(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(copy_stream):
@@ -389,8 +409,31 @@ class HMC:
             self.end_time = _datetime.now()
             self._close_sampler(accepted)
 
+    def _history_buffers(self, history, B):
+        if history is None:
+            return {}
+        torch, dev = self._torch, self.engine.device
+        if (not hasattr(self, "_hist") or self._hist["h0"].shape[0] < B
+                or self._hist["h0"].shape[1] != self.chains or self._hist["h0"].device != dev):
+            self._hist = {k: torch.empty(self.block_proposals, self.chains, dtype=torch.float64, device=dev)
+                          for k in ("stepsizes", "h0", "h1")}
+        return dict(out_stepsize=self._hist["stepsizes"][:B], out_h0=self._hist["h0"][:B],
+                    out_h1=self._hist["h1"][:B])
+
     def _close_sampler(self, accepted):
         per_chain = accepted.cpu().numpy().astype(_numpy.int64)
+        if self.autotuning:
+            final = self._stepsize_chain.cpu().numpy()
+            self.stepsize = float(final[0]) if self.chains == 1 else final
+            self.samples.write_attribute("final_stepsizes", final)
+            hist = getattr(self, "_history", None)
+            if hist is not None and len(hist["stepsizes"]):
+                self.stepsizes = _numpy.concatenate(hist["stepsizes"])          # [proposals, chains]
+                with _numpy.errstate(all="ignore"):
+                    self.acceptance_rates = _numpy.exp(_numpy.concatenate(hist["h0"])
+                                                       - _numpy.concatenate(hist["h1"]))
+                self.samples.write_attribute("acceptance_rates", self.acceptance_rates)
+                self.samples.write_attribute("stepsizes", self.stepsizes)
         x_local = self._x
         if self.world_size > 1:
             acc_all, x_all = _parallel.gather_diagnostics(accepted, self._x, self.total_chains)

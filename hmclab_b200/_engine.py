@@ -38,6 +38,9 @@ class _Block(C.Structure):
         ("out_h1", C.c_void_p), ("accepted_total", C.c_void_p),
         ("out_q_prop", C.c_void_p), ("out_p_prop", C.c_void_p),
         ("trace_q", C.c_void_p), ("trace_g", C.c_void_p),
+        ("stepsize_chain", C.c_void_p), ("autotune", C.c_int32), ("reserved2", C.c_int32),
+        ("target_acceptance_rate", C.c_double), ("learning_rate", C.c_double),
+        ("out_stepsize", C.c_void_p),
     ]
 
 
@@ -104,7 +107,7 @@ def load_library(path: Optional[str] = None):
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = restype, argtypes
-    if lib.hmcb_abi_version() != 1:
+    if lib.hmcb_abi_version() != 2:
         raise HmcbError("libhmcb.so ABI version mismatch; rebuild the library")
     _LIB = lib
     return lib
@@ -297,7 +300,8 @@ class Engine:
                   thinning: int = 1, proposal_offset: int = 0, chain_offset: int = 0, seed: int = 0,
                   z=None, u_step=None, u_accept=None, out_samples=None, out_accept=None,
                   out_h0=None, out_h1=None, accepted_total=None, out_q_prop=None, out_p_prop=None,
-                  trace_q=None, trace_g=None):
+                  trace_q=None, trace_g=None, stepsize_chain=None, autotune=False,
+                  target_acceptance_rate=0.65, learning_rate=0.75, out_stepsize=None):
         """Advance every chain by ``proposals`` proposals in place (q [C,d], x [C])."""
         torch = self.torch
         self._check_batch(q, "q")
@@ -329,6 +333,10 @@ class Engine:
             out_p_prop=ptr(out_p_prop, (B, Cn, d), f64, "out_p_prop"),
             trace_q=ptr(trace_q, (B, G, Cn, d), f64, "trace_q"),
             trace_g=ptr(trace_g, (B, G, Cn, d), f64, "trace_g"),
+            stepsize_chain=ptr(stepsize_chain, (Cn,), f64, "stepsize_chain"),
+            autotune=int(bool(autotune)), reserved2=0,
+            target_acceptance_rate=float(target_acceptance_rate), learning_rate=float(learning_rate),
+            out_stepsize=ptr(out_stepsize, (B, Cn), f64, "out_stepsize"),
         )
         self._ok(self.lib.hmcb_run_block(self._handle, C.byref(blk), self._stream()))
 

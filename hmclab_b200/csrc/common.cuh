@@ -145,6 +145,21 @@ __device__ __forceinline__ bool metropolis_accept(double h0, double h1, double u
   return exp(__dsub_rn(h0, h1)) > u;
 }
 
+// Step-size autotuning (HMC.autotune, Samplers.py:1494-1522) after proposal k (global index).
+struct AutotuneArgs {
+  int enabled;
+  double target, learning_rate;
+};
+__device__ __forceinline__ double autotune_stepsize(const AutotuneArgs& at, double stepsize, double h0,
+                                                    double h1, long long k) {
+  double rate = exp(__dsub_rn(h0, h1));
+  if (rate != rate) rate = 0.0;
+  const double weight = pow((double)(k + 1), -at.learning_rate);
+  stepsize = __dsub_rn(stepsize, __dmul_rn(weight, __dsub_rn(at.target, fmin(rate, 1.0))));
+  if (stepsize <= 0.0) stepsize = fmax(stepsize, 1e-18);
+  return stepsize;
+}
+
 // -------------------------------------------------------------------------- Philox ---
 
 struct Philox4 { uint32_t x, y, z, w; };

@@ -43,6 +43,9 @@ struct FusedArgs {
   double* out_p_prop;
   double* trace_q;
   double* trace_g;
+  double* stepsize_chain;  // [C] in/out or null
+  double* out_stepsize;    // [B x C] or null
+  AutotuneArgs tune;
 };
 
 // ------------------------------------------------------------------- priors only ---
@@ -159,6 +162,7 @@ hmc_fused_priors_kernel(const FusedArgs A) {
 
   UniformPairCache<TPC> ucache;
   ucache.us = ucache.ua = 0.0;
+  double eps0 = A.stepsize_chain ? A.stepsize_chain[c] : A.stepsize;  // this chain's step size
   // stored proposals: global index k with k % thinning == 0 (no division inside the loop)
   long long next_store = (A.proposal_offset + A.thinning - 1) / A.thinning * A.thinning;
   size_t store_row = 0;
@@ -177,7 +181,8 @@ hmc_fused_priors_kernel(const FusedArgs A) {
       if (A.u_step_in) u_step = A.u_step_in[kc];
       if (A.u_accept_in) u_acc = A.u_accept_in[kc];
     }
-    const double eps = A.randomize ? __dmul_rn(u_step, A.stepsize) : A.stepsize;
+    const double eps = A.randomize ? __dmul_rn(u_step, eps0) : eps0;
+    if (A.out_stepsize && live && t == 0) A.out_stepsize[kc] = eps0;
 
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
@@ -223,6 +228,7 @@ hmc_fused_priors_kernel(const FusedArgs A) {
     const double h0 = __dadd_rn(x, __dmul_rn(0.5, k0));
     const double h1 = __dadd_rn(x1, __dmul_rn(0.5, k1));
     const bool acc = metropolis_accept(h0, h1, u_acc);
+    if (A.tune.enabled) eps0 = autotune_stepsize(A.tune, eps0, h0, h1, kglob);
 
     if (live) {
       if (A.out_q_prop) {
@@ -264,6 +270,7 @@ hmc_fused_priors_kernel(const FusedArgs A) {
     if (t == 0) {
       A.x[c] = x;
       if (A.accepted_total) A.accepted_total[c] += accepted;
+      if (A.tune.enabled && A.stepsize_chain) A.stepsize_chain[c] = eps0;
     }
   }
 }

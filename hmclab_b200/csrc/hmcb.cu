@@ -224,6 +224,7 @@ StagedCommon staged_common(const hmcb_engine* e, const hmcb_block* b) {
   if (b) {
     S.chain_offset = b->chain_offset; S.seed = b->seed; S.stepsize = b->stepsize;
     S.randomize = b->randomize_stepsize;
+    S.stepsize_chain = b->stepsize_chain;
   }
   return S;
 }
@@ -338,7 +339,8 @@ int staged_run_block(hmcb_engine* e, const hmcb_block* b, cudaStream_t s) {
                               b->z_in ? b->z_in + kc * d : nullptr,
                               b->u_step_in ? b->u_step_in + kc : nullptr,
                               b->u_accept_in ? b->u_accept_in + kc : nullptr, e->eps, e->uacc,
-                              e->k0part, grad_checks ? e->flags[fcur] : nullptr, s));
+                              e->k0part, grad_checks ? e->flags[fcur] : nullptr,
+                              b->out_stepsize ? b->out_stepsize + kc : nullptr, s));
     e->launches += 1;
     int gi = 0;
     for (size_t o = 1; o < e->ops.size(); ++o) {
@@ -380,6 +382,9 @@ int staged_run_block(hmcb_engine* e, const hmcb_block* b, cudaStream_t s) {
     D.out_h0 = b->out_h0 ? b->out_h0 + kc : nullptr;
     D.out_h1 = b->out_h1 ? b->out_h1 + kc : nullptr;
     D.accepted_total = b->accepted_total;
+    D.stepsize_chain = b->stepsize_chain;
+    D.tune = AutotuneArgs{b->autotune ? 1 : 0, b->target_acceptance_rate, b->learning_rate};
+    D.kglob = kglob;
     double* sample_rows = nullptr;
     if (b->out_samples && (kglob % b->thinning) == 0) {
       sample_rows = b->out_samples + (size_t)(kglob / b->thinning - first_row) * C * (size_t)(d + 1);
@@ -406,6 +411,8 @@ FusedArgs fused_args(const hmcb_engine* e, const hmcb_block* b) {
   A.out_samples = b->out_samples; A.out_accept = b->out_accept; A.out_h0 = b->out_h0; A.out_h1 = b->out_h1;
   A.accepted_total = b->accepted_total; A.out_q_prop = b->out_q_prop; A.out_p_prop = b->out_p_prop;
   A.trace_q = b->trace_q; A.trace_g = b->trace_g;
+  A.stepsize_chain = b->stepsize_chain; A.out_stepsize = b->out_stepsize;
+  A.tune = AutotuneArgs{b->autotune ? 1 : 0, b->target_acceptance_rate, b->learning_rate};
   return A;
 }
 
@@ -862,7 +869,10 @@ int hmcb_run_block(hmcb_engine* e, const hmcb_block* b, void* stream) {
   HMCB_CHECK(b->proposals > 0 && b->proposals < (1ll << 31), "hmcb_run_block: proposals must be positive");
   HMCB_CHECK(b->thinning > 0, "hmcb_run_block: thinning must be positive");
   HMCB_CHECK(b->proposal_offset >= 0 && b->chain_offset >= 0, "hmcb_run_block: negative offset");
-  HMCB_CHECK(b->stepsize > 0.0, "hmcb_run_block: stepsize must be positive");
+  HMCB_CHECK(b->stepsize > 0.0 || b->stepsize_chain, "hmcb_run_block: stepsize must be positive");
+  HMCB_CHECK(!b->autotune || b->stepsize_chain, "hmcb_run_block: autotune needs stepsize_chain");
+  HMCB_CHECK(!b->autotune || (b->learning_rate > 0.5 && b->learning_rate <= 1.0),
+             "The learning rate should be larger than 0.5 and smaller than or equal to 1.0");
   HMCB_CHECK(b->q && b->x, "hmcb_run_block: q and x are required");
   HMCB_CHECK((b->trace_q == nullptr) == (b->trace_g == nullptr), "hmcb_run_block: trace_q and trace_g go together");
   HMCB_CHECK((b->out_q_prop == nullptr) == (b->out_p_prop == nullptr),

@@ -55,7 +55,7 @@ cudaError_t launch_spmm_misfit(const CsrDev& M, const double* B, int ldb, const 
 cudaError_t launch_st_begin(const StagedCommon& S, long long kglob, double a_mult, const double* q_cur,
                             double* q_w, double* p, const double* z_in, const double* u_step_in,
                             const double* u_acc_in, double* eps_out, double* uacc_out, double* k0part,
-                            unsigned* flags_out, cudaStream_t s);
+                            unsigned* flags_out, double* stepsize_out, cudaStream_t s);
 cudaError_t launch_st_position(const StagedCommon& S, double a_mult, double* q_w, double* p,
                                const double* eps, unsigned* flags_out, cudaStream_t s);
 cudaError_t launch_st_update(const StagedCommon& S, const UpdateEpi& epi, cudaStream_t s);

@@ -68,9 +68,10 @@ static dim3 st_grid(const StagedCommon& S) { return dim3(S.ld / ST_THREADS, S.jt
 cudaError_t launch_st_begin(const StagedCommon& S, long long kglob, double a_mult, const double* q_cur,
                             double* q_w, double* p, const double* z_in, const double* u_step_in,
                             const double* u_acc_in, double* eps_out, double* uacc_out, double* k0part,
-                            unsigned* flags_out, cudaStream_t s) {
+                            unsigned* flags_out, double* stepsize_out, cudaStream_t s) {
   st_begin_kernel<<<st_grid(S), ST_THREADS, 0, s>>>(S, kglob, a_mult, q_cur, q_w, p, z_in, u_step_in,
-                                                    u_acc_in, eps_out, uacc_out, k0part, flags_out);
+                                                    u_acc_in, eps_out, uacc_out, k0part, flags_out,
+                                                    stepsize_out);
   return cudaGetLastError();
 }
 

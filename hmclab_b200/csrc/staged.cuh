@@ -220,6 +220,7 @@ struct StagedCommon {
   unsigned long long seed;
   double stepsize;
   int randomize;
+  const double* stepsize_chain;  // [C] per-chain step sizes or null
 };
 
 #ifdef HMCB_STAGED_KERNELS
@@ -230,7 +231,8 @@ st_begin_kernel(const StagedCommon S, long long kglob, double a_mult,
                 const double* __restrict__ z_in /* [C x d] of this proposal or null */,
                 const double* __restrict__ u_step_in, const double* __restrict__ u_acc_in,
                 double* __restrict__ eps_out, double* __restrict__ uacc_out,
-                double* __restrict__ k0part, unsigned* __restrict__ flags_out) {
+                double* __restrict__ k0part, unsigned* __restrict__ flags_out,
+                double* __restrict__ stepsize_out /* [C] slice of out_stepsize or null */) {
   const int c = blockIdx.x * ST_THREADS + threadIdx.x;
   if (c >= S.C) return;
   const DevTarget& T = S.T;
@@ -240,8 +242,12 @@ st_begin_kernel(const StagedCommon S, long long kglob, double a_mult,
   uniform_pair(S.seed, cg, kg, u_step, u_acc);
   if (u_step_in) u_step = u_step_in[c];
   if (u_acc_in) u_acc = u_acc_in[c];
-  const double eps = S.randomize ? __dmul_rn(u_step, S.stepsize) : S.stepsize;
-  if (jt == 0) { eps_out[c] = eps; uacc_out[c] = u_acc; }
+  const double eps0 = S.stepsize_chain ? S.stepsize_chain[c] : S.stepsize;
+  const double eps = S.randomize ? __dmul_rn(u_step, eps0) : eps0;
+  if (jt == 0) {
+    eps_out[c] = eps; uacc_out[c] = u_acc;
+    if (stepsize_out) stepsize_out[c] = eps0;
+  }
   const double ca = __dmul_rn(a_mult, eps);
   double k0 = 0.0;
   unsigned mask = 0;
@@ -343,6 +349,9 @@ struct DecideArgs {
   double* sample_misfit;  // out_samples + row*C*(d+1) + d, stride (d+1), or null
   int sample_stride;
   int misfit_only;
+  double* stepsize_chain;  // [C] in/out when tune.enabled
+  AutotuneArgs tune;
+  long long kglob;
 };
 
 #ifdef HMCB_STAGED_KERNELS
@@ -376,6 +385,7 @@ st_decide_kernel(const DecideArgs D) {
   const double h0 = __dadd_rn(x0, __dmul_rn(0.5, k0));
   const double h1 = __dadd_rn(x1, __dmul_rn(0.5, k1));
   const bool acc = metropolis_accept(h0, h1, D.uacc[c]);
+  if (D.tune.enabled) D.stepsize_chain[c] = autotune_stepsize(D.tune, D.stepsize_chain[c], h0, h1, D.kglob);
   D.acc[c] = acc ? 1 : 0;
   const double xn = acc ? x1 : x0;
   if (acc) {

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HMCB_ABI_VERSION 1
+#define HMCB_ABI_VERSION 2
 
 typedef struct hmcb_engine hmcb_engine;
 
@@ -158,6 +158,15 @@ typedef struct hmcb_block {
   double *out_p_prop;       /* [B x C x d] end-of-trajectory momenta */
   double *trace_q;          /* [B x G x C x d] position at every gradient evaluation */
   double *trace_g;          /* [B x G x C x d] gradient at every gradient evaluation */
+  /* per-chain step sizes and their autotuning (HMC.autotune, Samplers.py:1494-1522):
+   * eps_c -= (k+1)^-learning_rate * (target_acceptance_rate - min(exp(H0-H1), 1)) after every
+   * proposal k (NaN rate counts as 0; a non-positive result is floored at 1e-18). */
+  double *stepsize_chain;   /* [C] in/out; NULL = the scalar `stepsize` for every chain */
+  int32_t autotune;         /* 1: update stepsize_chain (which must then be non-NULL) */
+  int32_t reserved2;
+  double target_acceptance_rate;
+  double learning_rate;
+  double *out_stepsize;     /* [B x C] step size of each proposal before randomisation, or NULL */
 } hmcb_block;
 
 int hmcb_run_block(hmcb_engine *e, const hmcb_block *block, void *stream);

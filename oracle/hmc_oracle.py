@@ -352,7 +352,9 @@ class GeneratorDraws:
 
 
 def run_chain(tree, mass, *, integrator="lf", steps=10, stepsize=0.1, randomize=True,
-              q0=None, proposals=1, draws=None, thinning=1, record_trace=False):
+              q0=None, proposals=1, draws=None, thinning=1, record_trace=False,
+              autotuning=False, target_acceptance_rate=0.65, learning_rate=0.75,
+              proposal_offset=0):
     """Single Markov chain, ``proposals`` HMC proposals (Samplers.py:579-587, 675-678,
     1463-1492).  Returns a dict of per-proposal arrays; ``samples`` holds the stored
     (d+1)-rows [model, misfit] after every ``thinning``-th proposal."""
@@ -360,8 +362,9 @@ def run_chain(tree, mass, *, integrator="lf", steps=10, stepsize=0.1, randomize=
     q = np.zeros((d, 1)) if q0 is None else np.array(q0, dtype=np.float64).reshape(d, 1)
     x = misfit(tree, q)
     out = {"accept": [], "H0": [], "H1": [], "samples": [], "q_prop": [], "p_prop": [],
-           "trace_q": [], "trace_g": []}
+           "trace_q": [], "trace_g": [], "stepsizes": []}
     for k in range(proposals):
+        out["stepsizes"].append(stepsize)
         p0 = momentum_from_normal(mass, draws.normal(d))
         eps = draws.step_factor() * stepsize if randomize else stepsize
         trace = [] if record_trace else None
@@ -373,6 +376,13 @@ def run_chain(tree, mass, *, integrator="lf", steps=10, stepsize=0.1, randomize=
         h1 = x1 + kinetic_energy(mass, p1)
         with np.errstate(all="ignore"):
             rate = np.exp(h0 - h1)
+        if autotuning:
+            # HMC.autotune, Samplers.py:1494-1522 (called before the Metropolis test)
+            weight = (proposal_offset + k + 1) ** (-learning_rate)
+            r = 0 if np.isnan(rate) else rate
+            stepsize -= weight * (target_acceptance_rate - min(r, 1))
+            if stepsize <= 0:
+                stepsize = max(stepsize, 1e-18)
         accepted = bool(rate > draws.accept_uniform())
         if accepted:
             q, x = q1.copy(), x1
@@ -391,6 +401,7 @@ def run_chain(tree, mass, *, integrator="lf", steps=10, stepsize=0.1, randomize=
     res = {k_: np.array(v) for k_, v in out.items() if len(v)}
     res["final_q"] = q[:, 0].copy()
     res["final_x"] = x
+    res["final_stepsize"] = stepsize
     return res
 
 
@@ -410,7 +421,7 @@ def run_chains(tree, mass, *, q0, z, u_step, u_acc, **kw):
     out = {}
     for key in per_chain[0]:
         stacked = np.stack([r[key] for r in per_chain])  # [C, ...]
-        if key in ("final_q", "final_x"):
+        if key in ("final_q", "final_x", "final_stepsize"):
             out[key] = stacked
         elif key in ("trace_q", "trace_g"):
             out[key] = np.transpose(stacked, (1, 2, 0, 3))

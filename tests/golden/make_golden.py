@@ -163,15 +163,58 @@ def seeded_public_runs(hmclab, tmpdir):
     print("seeded_public_runs", {k: v.shape for k, v in out.items() if k.endswith("samples")})
 
 
+AUTOTUNE_CASES = ("normal_unit_lf", "dense_direct_4s", "srcloc_fixed_v", "sparse_laplace_lf")
+
+
+def autotuned_runs(hmclab, tmpdir):
+    """Reference chains with autotuning=True (Samplers.py:1494-1522), replayed draws."""
+    out = {}
+    for name in AUTOTUNE_CASES:
+        s = cases.SETTINGS[name]
+        inp = cases.make_inputs(name)
+        C, K, d = s["chains"], s["proposals"], int(inp["dims"])
+        post, mass = cases.build(name, inp, hmclab)
+        accept = np.zeros((K, C), dtype=bool)
+        stepsizes = np.zeros((K, C))
+        samples = np.zeros((K, C, d + 1))
+        final = np.zeros(C)
+        for c in range(C):
+            sampler = hmclab.Samplers.HMC(seed=0)
+            sampler.rng = ReplayRNG(inp["z"][:, c], inp["u_step"][:, c], inp["u_acc"][:, c])
+            fn = os.path.join(tmpdir, f"auto_{name}_{c}.npy")
+            with np.errstate(all="ignore"):
+                sampler.sample(fn, post, stepsize=s["stepsize"], randomize_stepsize=s["randomize"],
+                               amount_of_steps=s["steps"], mass_matrix=mass, integrator=s["integrator"],
+                               initial_model=inp["q0"][c].copy(), proposals=K, autotuning=True,
+                               target_acceptance_rate=0.65, learning_rate=0.75,
+                               overwrite_existing_file=True, disable_progressbar=True)
+            samples[:, c] = np.load(fn)
+            accept[1:, c] = np.any(np.diff(samples[:, c], axis=0) != 0, axis=1)
+            accept[0, c] = np.any(samples[0, c, :d] != inp["q0"][c])
+            stepsizes[: len(sampler.stepsizes), c] = sampler.stepsizes[:, 0]
+            # the reference truncates its histories to current_proposal entries (off by one)
+            stepsizes[len(sampler.stepsizes):, c] = np.nan
+            final[c] = sampler.stepsize
+        out[f"{name}__samples"] = samples
+        out[f"{name}__stepsizes"] = stepsizes
+        out[f"{name}__final_stepsize"] = final
+        print("autotuned", name, "final stepsizes", np.round(final, 4))
+    np.savez_compressed(os.path.join(HERE, "autotuned_runs.npz"), **out)
+
+
 def main():
     hmclab = import_reference()
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
     from hmclab_b200._lowering import describe, describe_mass
 
     with tempfile.TemporaryDirectory() as tmpdir:
+        if "--autotune-only" in sys.argv:
+            autotuned_runs(hmclab, tmpdir)
+            return
         seeded_public_runs(hmclab, tmpdir)
         if "--seeded-only" in sys.argv:
             return
+        autotuned_runs(hmclab, tmpdir)
         for name in cases.CASES:
             inp = cases.make_inputs(name)
             golden, post, mass = drive_reference(hmclab, name, inp, tmpdir)

@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_abi_version_and_error_channel(lib):
-    assert lib.hmcb_abi_version() == 1
+    assert lib.hmcb_abi_version() == 2
     assert isinstance(lib.hmcb_last_error(), bytes)
 
 

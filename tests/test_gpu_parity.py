@@ -156,3 +156,42 @@ def test_engine_refuses_bad_configuration():
     bad = dict(mplan, dims=mplan["dims"] + 1)
     with pytest.raises(ValueError):
         Engine(plan, bad, 4)
+
+
+@pytest.mark.parametrize("name", ["normal_unit_lf", "dense_direct_4s", "srcloc_fixed_v", "sparse_laplace_lf"])
+def test_autotuned_chains_match_reference(name):
+    """Per-chain step-size adaptation on the device vs reference chains run with
+    autotuning=True and the same replayed draws (tests/golden/autotuned_runs.npz); in two
+    blocks, so the adapted step sizes also have to survive the block boundary."""
+    import os
+
+    from helpers import GOLDEN_DIR
+
+    gold = np.load(os.path.join(GOLDEN_DIR, "autotuned_runs.npz"))
+    inp, _ = load_golden(name)
+    s = cases.SETTINGS[name]
+    K, C, d = inp["z"].shape
+    eng, torch = _engine(name, inp, C)
+    q = _dev(torch, inp["q0"])
+    x = eng.misfit(q)
+    z, us, ua = _dev(torch, inp["z"]), _dev(torch, inp["u_step"]), _dev(torch, inp["u_acc"])
+    eps = torch.full((C,), s["stepsize"], dtype=torch.float64, device="cuda")
+    samples, steps = [], []
+    for lo, hi in ((0, 2), (2, K)):
+        buf = torch.zeros(hi - lo, C, d + 1, dtype=torch.float64, device="cuda")
+        hist = torch.zeros(hi - lo, C, dtype=torch.float64, device="cuda")
+        eng.run_block(q, x, hi - lo, stepsize=s["stepsize"], randomize_stepsize=s["randomize"],
+                      proposal_offset=lo, z=z[lo:hi].contiguous(), u_step=us[lo:hi].contiguous(),
+                      u_accept=ua[lo:hi].contiguous(), out_samples=buf, stepsize_chain=eps,
+                      autotune=True, target_acceptance_rate=0.65, learning_rate=0.75,
+                      out_stepsize=hist)
+        samples.append(buf.cpu().numpy())
+        steps.append(hist.cpu().numpy())
+    got, got_steps = np.concatenate(samples), np.concatenate(steps)
+    ref = gold[f"{name}__samples"]
+    assert np.array_equal(np.all(np.diff(got, axis=0) == 0, axis=2), np.all(np.diff(ref, axis=0) == 0, axis=2))
+    assert rel_err(got, ref) < TOL
+    assert rel_err(eps.cpu().numpy(), gold[f"{name}__final_stepsize"]) < TOL
+    ref_steps = gold[f"{name}__stepsizes"]
+    known = ~np.isnan(ref_steps)
+    assert rel_err(got_steps[known], ref_steps[known]) < TOL

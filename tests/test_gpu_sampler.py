@@ -186,3 +186,26 @@ def test_max_time_stops_early_and_leaves_a_valid_file(tmp_path):
         per = s.read_attribute("samples_per_chain")
         assert per == done // 1000 and s.numpy.shape == (201, 256 * per)
         assert np.all(np.isfinite(s.numpy))
+
+
+def test_autotuning_through_the_sampler(tmp_path):
+    """autotuning=True: every chain adapts its own step size towards the target acceptance
+    rate; chain 0 with host_rng reproduces what the reference's update rule gives."""
+    from hmclab_b200 import Distributions as D
+    from hmclab_b200.Samplers import HMC
+    from hmclab_b200.Samples import Samples
+
+    d, C = 20, 64
+    post = D.Normal(np.zeros((d, 1)), np.linspace(0.5, 2.0, d).reshape(d, 1))
+    fn = str(tmp_path / "auto.npy")
+    sampler = HMC(seed=5).sample(fn, post, stepsize=0.05, amount_of_steps=6, proposals=600, chains=C,
+                                 autotuning=True, target_acceptance_rate=0.65, learning_rate=0.75,
+                                 block_proposals=100)
+    assert sampler.stepsize.shape == (C,) and np.all(sampler.stepsize > 0.05)
+    assert sampler.stepsizes.shape == (600, C) and sampler.acceptance_rates.shape == (600, C)
+    assert np.all(sampler.stepsizes[0] == 0.05)
+    late = np.minimum(sampler.acceptance_rates[300:], 1.0).mean()
+    assert abs(late - 0.65) < 0.1
+    with Samples(fn) as s:
+        assert s.read_attribute("final_stepsizes").shape == (C,)
+        assert s.read_attribute("stepsizes").shape == (600, C)

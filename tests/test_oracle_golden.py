@@ -48,3 +48,31 @@ def test_golden_cases_exercise_both_decisions_and_bounds():
         mixed += 0 < ref["accept"].mean() < 1
         nonfinite += (~np.isfinite(ref["H1"])).any()
     assert mixed >= 10 and nonfinite >= 2
+
+
+AUTOTUNE_CASES = ("normal_unit_lf", "dense_direct_4s", "srcloc_fixed_v", "sparse_laplace_lf")
+
+
+@pytest.mark.parametrize("name", AUTOTUNE_CASES)
+def test_oracle_autotuning_reproduces_reference(name):
+    """Reference chains run with autotuning=True (tests/golden/autotuned_runs.npz)."""
+    import os
+
+    from helpers import GOLDEN_DIR
+
+    gold = np.load(os.path.join(GOLDEN_DIR, "autotuned_runs.npz"))
+    inp, _ = load_golden(name)
+    s = cases.SETTINGS[name]
+    post, mass = build_mirror(name, inp)
+    tree, mtree = describe(post), describe_mass(mass)
+    with np.errstate(all="ignore"):
+        got = oracle.run_chains(
+            tree, mtree, q0=inp["q0"], z=inp["z"], u_step=inp["u_step"], u_acc=inp["u_acc"],
+            integrator=s["integrator"], steps=s["steps"], stepsize=s["stepsize"],
+            randomize=s["randomize"], autotuning=True, target_acceptance_rate=0.65, learning_rate=0.75)
+    assert rel_err(got["samples"], gold[f"{name}__samples"]) < TOL
+    assert rel_err(got["final_stepsize"], gold[f"{name}__final_stepsize"]) < TOL
+    ref_steps = gold[f"{name}__stepsizes"]
+    known = ~np.isnan(ref_steps)       # the reference drops the last entry of its history
+    assert rel_err(got["stepsizes"][known], ref_steps[known]) < TOL
+    assert (gold[f"{name}__final_stepsize"] != s["stepsize"]).all()
