@@ -1,0 +1,96 @@
+"""Host-side contracts the reference's own tests pin (no device needed):
+bounds validation texts (reference tests/test_distributions.py:147-166), momentum shape
+errors (tests/test_mass_matrices.py:74-77,114-117), LinearMatrix constructor quirks
+(tests/test_linear_dense_simple.py), lowering rules for bounds."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from hmclab_b200 import Distributions as D
+from hmclab_b200 import MassMatrices as M
+from hmclab_b200._lowering import describe, describe_mass, flatten
+
+
+def test_swapped_bounds_raise_the_reference_message():
+    dist = D.Normal(np.zeros((3, 1)), 1.0)
+    lo, hi = np.full((3, 1), -1.0), np.full((3, 1), 1.0)
+    dist.update_bounds(lo, hi)
+    with pytest.raises(ValueError, match="Bounds vectors are incompatible."):
+        dist.update_bounds(hi, lo)
+    assert dist.lower_bounds is lo and dist.upper_bounds is hi     # restored on failure
+    with pytest.raises(ValueError, match="incorrect size"):
+        dist.update_bounds(np.zeros((2, 1)), None)
+    with pytest.raises(ValueError, match="not understood"):
+        dist.update_bounds("low", None)
+
+
+@pytest.mark.parametrize("mass", [M.Unit(4), M.Diagonal(np.ones((4, 1)) * 2.0)])
+def test_wrong_momentum_shape_raises_value_error(mass):
+    with pytest.raises(ValueError):
+        mass.kinetic_energy(np.ones((5, 1)))
+    with pytest.raises(ValueError):
+        mass.kinetic_energy_gradient(np.ones((4,)))
+    assert mass.dimensions == 4 and mass.matrix.shape == (4, 4)
+
+
+def test_diagonal_mass_uses_the_rounded_reciprocal():
+    diag = np.array([[3.0], [7.0], [0.1]])
+    plan = describe_mass(M.Diagonal(diag))
+    assert np.array_equal(plan["inverse_diagonal"], (1.0 / diag)[:, 0])
+    assert describe_mass(M.Unit(3)) == {"kind": "unit", "dims": 3}
+    with pytest.raises(NotImplementedError):
+        describe_mass(type("Full", (), {"dimensions": 3})())
+
+
+def test_linear_matrix_dtype_quirks_are_inherited():
+    rng = np.random.default_rng(0)
+    G, d = rng.normal(size=(7, 3)), rng.normal(size=(7, 1))
+    lik = D.LinearMatrix(G, d, 2.0)                        # N > d -> premultiplied by default
+    inner = lik.Distribution
+    assert inner.premultiplication and inner.GtG.shape == (3, 3)
+    G32 = G.astype(np.float32).astype(np.float64)
+    assert np.allclose(inner.GtG, G32.T @ G32 / 2.0, rtol=1e-15)      # float32-rounded G in f64 math
+    assert not np.allclose(inner.GtG, G.T @ G / 2.0, rtol=1e-12)
+    lik = D.LinearMatrix(G, d, 2.0, premultiplication=False)
+    assert lik.Distribution.G.dtype == np.float32 and lik.Distribution.Gt.dtype == np.float64
+    with pytest.raises(ValueError, match="data vector"):
+        D.LinearMatrix(G, d[:, 0], 2.0)
+    with pytest.raises(ValueError, match="forward model matrix"):
+        D.LinearMatrix(G[:5], d, 2.0)
+    with pytest.raises(ValueError, match="covariance"):
+        D.LinearMatrix(G, d, np.ones((3, 1)))
+    with pytest.raises(NotImplementedError):
+        D.LinearMatrix(G, d, np.eye(7))
+    sparse = D.LinearMatrix(sp.csr_matrix(G), d, 0.5, premultiplication=False)
+    node = describe(sparse)
+    assert node["kind"] == "linear_csr" and node["indices"].dtype == np.int32
+    assert node["t_indptr"].size == 4 and node["indptr"].size == 8
+
+
+def test_bayesrule_reflects_on_direct_children_only():
+    lo, hi = np.full((4, 1), -1.0), np.full((4, 1), 2.0)
+    rng = np.random.default_rng(1)
+    lik = D.LinearMatrix(rng.normal(size=(3, 4)), rng.normal(size=(3, 1)), 1.0)
+    direct = flatten(describe(D.BayesRule([D.Uniform(lo, hi), lik])))
+    assert np.array_equal(direct["reflect_lb"], lo[:, 0]) and np.array_equal(direct["reflect_ub"], hi[:, 0])
+    nested = D.CompositeDistribution([D.Uniform(lo[:2], hi[:2]), D.Normal(np.zeros((2, 1)), 1.0)])
+    inside = flatten(describe(D.BayesRule([nested, lik])))
+    assert inside["reflect_lb"] is None and inside["reflect_ub"] is None      # rejection only
+    assert any(c["in_gradient"] and c["len"] == 2 for c in inside["checks"])
+    top = flatten(describe(nested))                         # bound-less composite: children's bounds
+    assert np.array_equal(top["reflect_lb"], [-1.0, -1.0, -np.inf, -np.inf])
+    two = D.BayesRule([D.Uniform(lo, hi), D.Normal(np.zeros((4, 1)), 1.0, lower_bounds=lo + 0.5)])
+    collapsed = flatten(describe(two))
+    assert np.array_equal(collapsed["reflect_lb"], (lo + 0.5)[:, 0])          # max of the lowers
+
+
+def test_unsupported_objects_are_refused_by_name():
+    with pytest.raises(NotImplementedError, match="full covariance|Full-covariance"):
+        D.Normal(np.zeros((2, 1)), np.eye(2))
+    with pytest.raises(AttributeError):
+        D.Laplace(np.zeros((2, 1)), 1.0)                   # dispersions must be an ndarray
+    lik = D.SourceLocation3D(np.zeros((1, 3)), np.ones((1, 3)), np.zeros((1, 3)), np.ones((2, 3)),
+                             np.ones((2, 3)), infer_velocity=True)
+    assert lik.dimensions == 9
+    with pytest.raises(NotImplementedError, match="Only one coupled likelihood"):
+        flatten(describe(D.BayesRule([lik, lik])))
