@@ -68,6 +68,7 @@ class HMC:
         self.amount_of_writes = 0
         self.engine = None
         self._timings = {}
+        self._between_blocks = None
 
     # ------------------------------------------------------------------------- API ----
     def sample(
@@ -210,6 +211,9 @@ class HMC:
         self.max_time = max_time
         self.disable_progressbar = disable_progressbar
         self.host_rng = bool(host_rng)
+        # private knobs of ParallelSampleSMP: exact block boundaries for the exchange schedule
+        self._first_block = kwargs.pop("_first_block", None)
+        exact_blocks = kwargs.pop("_exact_blocks", False)
 
         self._init_sampler_specific(**kwargs)
 
@@ -243,6 +247,8 @@ class HMC:
             assert type(block_proposals) == int and block_proposals > 0
             rows = max(1, min(self.proposals_after_thinning, block_proposals // online_thinning))
         self.block_proposals = rows * online_thinning
+        if exact_blocks:
+            self.block_proposals = int(block_proposals)
 
         self.samples.allocate(self.chains, self.proposals_after_thinning, d)
         self._write_tuning_settings()
@@ -321,7 +327,7 @@ class HMC:
         torch, eng = self._torch, self.engine
         C, d, thin = self.chains, self.dimensions, self.online_thinning
         dev = eng.device
-        rows_max = self.block_proposals // thin
+        rows_max = self.block_proposals // thin + 1
         dbuf = [torch.empty(rows_max, C, d + 1, dtype=torch.float64, device=dev) for _ in range(2)]
         hbuf = [torch.empty(rows_max, C, d + 1, dtype=torch.float64).pin_memory() for _ in range(2)]
         accepted = torch.zeros(C, dtype=torch.int32, device=dev)
@@ -353,14 +359,17 @@ class HMC:
             slot, rows = item
             copied[slot].synchronize()
             t0 = _time.time()
-            self.samples.write_block(hbuf[slot][:rows].numpy())
+            if rows:
+                self.samples.write_block(hbuf[slot][:rows].numpy())
             self.amount_of_writes += rows
             self._timings["host_write_s"] += _time.time() - t0
 
         try:
             while done < self.proposals:
                 B = min(self.block_proposals, self.proposals - done)
-                rows = B // thin
+                if nblock == 0 and self._first_block:
+                    B = min(int(self._first_block), B)
+                rows = eng.stored_rows(B, thin, done)
                 slot = nblock & 1
                 draws = {}
                 if self.host_rng:
@@ -373,16 +382,20 @@ class HMC:
                 eng.run_block(self._q, self._x, B, stepsize=self.stepsize,
                               randomize_stepsize=self.randomize_stepsize, thinning=thin,
                               proposal_offset=done, chain_offset=self.chain_offset, seed=device_seed,
-                              out_samples=dbuf[slot][:rows], accepted_total=accepted, **draws,
+                              out_samples=dbuf[slot][:rows] if rows else None, accepted_total=accepted,
+                              **draws,
                               **tune, **self._history_buffers(history, B))
                 if history is not None:
                     for key in history:
                         history[key].append(self._hist[key][:B].cpu().numpy())
+                if self._between_blocks is not None:   # e.g. replica exchange: permute chain states
+                    self._between_blocks(done + B, dbuf[slot], rows)
                 produced = torch.cuda.Event()
                 produced.record(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(produced)
-                    hbuf[slot][:rows].copy_(dbuf[slot][:rows], non_blocking=True)
+                    if rows:
+                        hbuf[slot][:rows].copy_(dbuf[slot][:rows], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(copy_stream)
                 copied[slot] = ev
@@ -468,3 +481,139 @@ class HMC:
         return {"proposals": self.proposals, "chains": self.chains,
                 "acceptance_rate": self.accepted_proposals / max(1, (self.current_proposal + 1) * self.chains),
                 "path": self.engine.path if self.engine else None}
+
+
+class ParallelSampleSMP:
+    """Front end with the reference's multi-chain API (hmclab/Samplers.py:1807-1998).
+
+    The reference starts one OS process per chain; here the chains of one call become ONE
+    batch on the GPU and every chain still gets its own samples file.  All chains must share
+    the posterior object and the tuning ``kwargs`` (that is what a batch is).
+
+    ``exchange=True``: the reference swaps the models of scheduled chain pairs when
+    ``exp((x_i(m_i) - x_i(m_j)) + (x_j(m_j) - x_j(m_i))) > u`` (Samplers.py:589-669).  With one
+    shared posterior the exponent is exactly zero, so every scheduled swap is accepted: the
+    exchange is a permutation of chain states after every ``exchange_interval``-th proposal,
+    following a schedule drawn like the reference's (``rng.choice`` without replacement per
+    exchange round, :1872-1880).  Exchange between *different* posteriors (tempering) is not
+    offered.
+    """
+
+    def __init__(self, seed=None):
+        self.rng = _numpy.random.default_rng(seed)
+
+    def sample(self, samplers, filenames, posteriors, overwrite_existing_files=False,
+               proposals: int = 100, exchange: bool = True, exchange_interval: int = 1,
+               initial_model=None, kwargs=None):
+        import os
+        import tempfile
+
+        assert overwrite_existing_files, (
+            "You have to manually enable overwriting samples. This is for safety. The existing "
+            "file dialog doesn't work in the parallel case. Set `overwrite_existing_files=True`.")
+        n = len(samplers)
+        assert len(filenames) == n, (
+            f"The number of supplied initial models ({len(filenames)}) is not equal to the amount "
+            f"of chains ({n}). Supply {n} models.")
+        assert len(posteriors) == n, (
+            f"The number of supplied initial models ({len(posteriors)}) is not equal to the amount "
+            f"of chains ({n}). Supply {n} posteriors.")
+        if type(initial_model) == list:
+            assert len(initial_model) == n, (
+                f"The number of supplied initial models ({len(initial_model)}) is not equal to the "
+                f"amount of chains ({n}). Supply either 1 or {n} models.")
+        if type(kwargs) == list:
+            assert len(kwargs) == n, (
+                f"The number of supplied kwargs dictionaries ({len(kwargs)}) is not equal to the "
+                f"amount of chains ({n}). Supply either 1 or {n} kwargs.")
+            if any(k != kwargs[0] for k in kwargs[1:]):
+                raise NotImplementedError("A batch of chains shares one set of tuning kwargs.")
+            kwargs = kwargs[0]
+        kwargs = dict(kwargs or {})
+        if any(p is not posteriors[0] for p in posteriors[1:]):
+            raise NotImplementedError(
+                "ParallelSampleSMP on the batched engine needs one shared posterior object for all "
+                "chains (exchange between different posteriors is not offered).")
+        if not all(isinstance(smp, HMC) for smp in samplers):
+            raise NotImplementedError("Only HMC samplers run on the batched engine.")
+        kwargs.pop("overwrite_existing_file", None)
+        d = int(posteriors[0].dimensions)
+        if initial_model is None:
+            q0 = _numpy.zeros((n, d))
+        elif type(initial_model) == list:
+            q0 = _numpy.stack([_numpy.asarray(m, dtype=_numpy.float64).reshape(d) for m in initial_model])
+        else:
+            q0 = _numpy.repeat(_numpy.asarray(initial_model, dtype=_numpy.float64).reshape(1, d), n, axis=0)
+
+        driver = samplers[0]
+        self.samplers = list(samplers)
+        self.exchange_schedule = None
+        if exchange:
+            assert type(exchange_interval) == int and exchange_interval > 0
+            pairs = n // 2
+            rounds = proposals // exchange_interval
+            self.exchange_schedule = (
+                _numpy.vstack([self.rng.choice(n, pairs * 2, replace=False) for _ in range(rounds)])
+                if pairs and rounds else _numpy.zeros((0, 0), dtype=int))
+            kwargs["block_proposals"] = exchange_interval
+            kwargs["_exact_blocks"] = True
+
+            thinning = int(kwargs.get("online_thinning", 1))
+
+            def swap(done, block_rows, rows, schedule=self.exchange_schedule):
+                # proposal k = done - 1 just finished; the reference exchanges when k % interval == 0
+                # and stores the sample of proposal k after the exchange (Samplers.py:589-678)
+                k = done - 1
+                if schedule.size == 0 or k % exchange_interval != 0:
+                    return
+                row = k // exchange_interval
+                if row >= schedule.shape[0]:
+                    return
+                perm = _numpy.arange(n)
+                for a, b in schedule[row].reshape(-1, 2):
+                    perm[a], perm[b] = b, a
+                idx = driver._torch.as_tensor(perm, device=driver.engine.device)
+                driver._q.copy_(driver._q[idx])
+                driver._x.copy_(driver._x[idx])
+                if rows and k % thinning == 0:
+                    # the stored row of proposal k shows the exchanged state; unlike the reference,
+                    # whose misfit column keeps the value of the model that left the chain, model
+                    # and misfit stay a consistent pair here
+                    block_rows[rows - 1] = block_rows[rows - 1][idx]
+
+            driver._between_blocks = swap
+            if exchange_interval != 1:
+                # blocks must end right after proposals k with k % interval == 0: k = 0, I, 2I, ...
+                # -> first block of one proposal, then blocks of `interval`; done by the sampler
+                # when block boundaries are requested explicitly
+                kwargs["_first_block"] = 1
+        try:
+            with tempfile.TemporaryDirectory() as tmp:
+                combined = os.path.join(tmp, "batch.npy")
+                driver.sample(combined, posteriors[0], proposals=proposals, initial_model=q0,
+                              chains=n, overwrite_existing_file=True, **kwargs)
+                self._split(driver, combined, filenames)
+        finally:
+            driver._between_blocks = None
+        return self
+
+    @staticmethod
+    def _split(driver, combined, filenames):
+        """One reference-format samples file per chain."""
+        with _Samples(combined) as src:
+            attrs = dict(src._attributes)
+            per = int(attrs["samples_per_chain"])
+            done = driver.current_proposal + 1
+            for c, name in enumerate(filenames):
+                out = _Samples(name, mode="w", overwrite=True)
+                rows = _numpy.ascontiguousarray(src.chain(c).T)           # [per, d+1]
+                out.allocate(1, per, rows.shape[1] - 1)
+                out.write_block(rows[:, None, :])
+                for key, value in attrs.items():
+                    if key not in ("write_index", "last_written_sample", "chains", "samples_per_chain",
+                                   "acceptance_rate", "final_stepsizes", "stepsizes", "acceptance_rates"):
+                        out.write_attribute(key, value)
+                out.write_attribute("acceptance_rate",
+                                    float(driver.accepted_proposals_per_chain[c]) / max(1, done))
+                out.write_attribute("chain_index", c)
+                out.close()

@@ -209,3 +209,57 @@ def test_autotuning_through_the_sampler(tmp_path):
     with Samples(fn) as s:
         assert s.read_attribute("final_stepsizes").shape == (C,)
         assert s.read_attribute("stepsizes").shape == (600, C)
+
+
+def test_parallel_sample_smp_front_end(tmp_path):
+    """The reference's multi-chain API: one file per chain, one batch on the GPU."""
+    from hmclab_b200 import workloads
+    from hmclab_b200.Samplers import HMC, ParallelSampleSMP
+    from hmclab_b200.Samples import Samples
+
+    w = workloads.dense_small(chains=6)
+    n, d = 6, w.dims
+    names = [str(tmp_path / f"chain_{i}.npy") for i in range(n)]
+    kw = dict(stepsize=w.stepsize, amount_of_steps=5, online_thinning=2, disable_progressbar=True)
+    models = [w.initial_models[i].reshape(d, 1) for i in range(n)]
+
+    def run(exchange, interval=1, seed=4):
+        samplers = [HMC(seed=9) for _ in range(n)]
+        par = ParallelSampleSMP(seed=seed).sample(samplers, names, [w.posterior] * n,
+                                                   overwrite_existing_files=True, proposals=20,
+                                                   exchange=exchange, exchange_interval=interval,
+                                                   initial_model=models, kwargs=kw)
+        out = []
+        for name in names:
+            with Samples(name) as smp:
+                assert smp.numpy.shape == (d + 1, 10)
+                assert smp.read_attribute("write_index") == 10
+                assert 0.0 <= smp.read_attribute("acceptance_rate") <= 1.0
+                out.append(np.array(smp.numpy))
+        return np.stack(out), par
+
+    plain, _ = run(False)
+    batched = HMC(seed=9).sample(str(tmp_path / "b.npy"), w.posterior, proposals=20, chains=n,
+                                 initial_model=w.initial_models, **kw)
+    with Samples(batched.samples_filename) as smp:
+        for c in range(n):
+            assert np.array_equal(plain[c], smp.chain(c))
+    swapped, par = run(True, interval=4)
+    assert par.exchange_schedule.shape == (5, 6)
+    assert all(sorted(row) == list(range(6)) for row in par.exchange_schedule)
+    # proposal 0 is stored after the first exchange round: the same rows, permuted over the chains
+    perm = np.arange(n)
+    for a, b in par.exchange_schedule[0].reshape(-1, 2):
+        perm[a], perm[b] = b, a
+    assert np.array_equal(swapped[:, :, 0], plain[perm][:, :, 0])
+    assert not np.array_equal(swapped, plain)
+    again, _ = run(True, interval=4)
+    assert np.array_equal(again, swapped)                       # same seeds -> same run
+    far, _ = run(True, interval=50)                            # no exchange round inside 20 proposals
+    assert np.array_equal(far, plain)
+    with pytest.raises(AssertionError, match="overwriting"):
+        ParallelSampleSMP().sample([HMC()], names[:1], [w.posterior])
+    with pytest.raises(NotImplementedError):
+        other = workloads.dense_small(chains=1).posterior
+        ParallelSampleSMP().sample([HMC(), HMC()], names[:2], [w.posterior, other],
+                                   overwrite_existing_files=True)
