@@ -364,6 +364,18 @@ def main():
                     "kernel": "hmc_fused_priors_kernel" if eng.path == "fused_priors" else "hmc_fused_srcloc_kernel",
                     "algorithmic_bytes_per_launch": abytes, "peak_source": peaks["source"],
                     "note": "one launch per step; fp64 SIMT pipe, not HBM, limits this kernel (see DESIGN.md)"}
+        ops = w.extra.get("fp64_ops_per_grad")
+        if ops:
+            # the pipe that actually binds: fp64 instructions (an FMA counts once) against the
+            # measured DFMA issue rate of this pool's B200 (profiles/fp64_peak_r01.json)
+            peak_path = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+            ginst = 16940.0
+            if os.path.exists(peak_path):
+                with open(peak_path) as f:
+                    ginst = float(json.load(f).get("dfma_ginst_per_s", ginst))
+            rate = ops * value / world / 1e9
+            roofline["fp64_pipe"] = {"achieved_ginst_per_s": rate, "peak_ginst_per_s": ginst,
+                                     "frac": rate / ginst, "fp64_ops_per_grad_eval": ops}
     else:
         peak, src = fp64_peak_tflops()
         flops = w.extra.get("flops_per_grad")
@@ -372,7 +384,8 @@ def main():
         achieved = flops * value / world / 1e12
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": None,
-                    "kernel": "dmma_gemm_kernel / csr_spmm_kernel (whole step time attributed)",
+                    "kernel": {"fused_dense": "hmc_fused_dense_kernel (one launch per step)"}.get(
+                        eng.path, "dmma_gemm_kernel / csr_spmm_kernel (whole step time attributed)"),
                     "algorithmic_flops_per_grad_eval": flops, "peak_source": src}
 
     cpu = None

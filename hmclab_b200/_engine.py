@@ -17,7 +17,7 @@ from hmclab_b200 import _build
 
 INTEGRATORS = {"lf": 0, "3s": 1, "4s": 2}
 GRADS_PER_STEP = {"lf": 1, "3s": 3, "4s": 4}
-PATH_NAMES = {0: "fused_priors", 1: "fused_srcloc", 2: "staged"}
+PATH_NAMES = {0: "fused_priors", 1: "fused_srcloc", 2: "staged", 3: "fused_dense"}
 
 _c_double_p = C.POINTER(C.c_double)
 _c_int32_p = C.POINTER(C.c_int32)

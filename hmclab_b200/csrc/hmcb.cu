@@ -89,6 +89,7 @@ struct hmcb_engine {
 
   bool finalized = false;
   int path = -1;
+  bool fused_dense = false;  // run_block uses the whole-proposal small-dense kernel
   int64_t launches = 0;
 
   // device state ---------------------------------------------------------------------
@@ -753,6 +754,10 @@ int hmcb_finalize(hmcb_engine* e) {
       if (dev_alloc(e, (size_t)e->npad * e->ld, &e->R)) return -1;
     }
     if (e->ltiles && dev_alloc(e, (size_t)e->ltiles * e->ld, &e->lpart)) return -1;
+    // small premultiplied dense models: the whole block of proposals runs in one kernel with
+    // GtG resident in shared memory (the staged workspaces still serve hmcb_misfit/gradient)
+    e->fused_dense = e->lik == LK_DENSE_PREMULT && e->dpad == 128 && T.n_terms <= 1 &&
+                     T.grad_check_mask == 0u && !std::getenv("HMCB_FORCE_STAGED");
     // the host copies of the big operands are no longer needed
     std::vector<double>().swap(e->h_A);
     std::vector<double>().swap(e->h_At);
@@ -762,7 +767,10 @@ int hmcb_finalize(hmcb_engine* e) {
   return 0;
 }
 
-int hmcb_path(const hmcb_engine* e) { return e ? e->path : -1; }
+int hmcb_path(const hmcb_engine* e) {
+  if (!e) return -1;
+  return (e->path == HMCB_PATH_STAGED && e->fused_dense) ? HMCB_PATH_FUSED_DENSE : e->path;
+}
 int64_t hmcb_grads_per_proposal(const hmcb_engine* e) { return e ? e->S.grads_per_proposal : -1; }
 int64_t hmcb_launch_count(const hmcb_engine* e) { return e ? e->launches : -1; }
 
@@ -885,6 +893,11 @@ int hmcb_run_block(hmcb_engine* e, const hmcb_block* b, void* stream) {
   }
   if (e->path == HMCB_PATH_FUSED_SRCLOC) {
     HMCB_CUDA(launch_fused_srcloc(fused_args(e, b), e->L, s));
+    e->launches += 1;
+    return 0;
+  }
+  if (e->fused_dense) {
+    HMCB_CUDA(launch_fused_dense(fused_args(e, b), e->dA, e->dvec, e->dtd, s));
     e->launches += 1;
     return 0;
   }

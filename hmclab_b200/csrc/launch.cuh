@@ -30,6 +30,11 @@ cudaError_t launch_fused_srcloc(const FusedArgs& A, const SrcLocDev& L, cudaStre
 cudaError_t launch_srcloc_eval(const DevTarget& T, const SrcLocDev& L, int chains, int mode,
                                const double* q, double* out, cudaStream_t s);
 
+// ---- launch_fused_dense.cu -------------------------------------------------------------
+// premultiplied dense likelihood with dims <= 128: GtG is the zero padded [128 x 128] matrix
+cudaError_t launch_fused_dense(const FusedArgs& A, const double* GtG, const double* Gtd0, double dtd,
+                               cudaStream_t s);
+
 // ---- launch_staged.cu ------------------------------------------------------------------
 cudaError_t staged_init();  // opt-in shared memory sizes
 cudaError_t launch_gemm_update(const double* A, int lda, int M, const double* B, int ldb, int K,

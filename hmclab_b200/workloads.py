@@ -52,7 +52,8 @@ def dense_small(chains: int = 1) -> Workload:
     post = D.BayesRule([D.Normal(np.zeros((100, 1)), 1.0), D.LinearMatrix(G, d, 2.0)])
     q0 = np.zeros((chains, 100)) if chains == 1 else rng.normal(size=(chains, 100)) * 0.1
     return Workload("dense_small", post, M.Unit(100), chains, "lf", 10, 0.01, q0,
-                    "LinearMatrix dense 100 params x 200 data (premultiplied GtG), Normal prior, lf L=10")
+                    "LinearMatrix dense 100 params x 200 data (premultiplied GtG), Normal prior, lf L=10",
+                    extra={"flops_per_grad": 2.0 * 100 * 100, "form": "premult"})
 
 
 def normal_iid(dims: int = 1000, chains: int = 4096) -> Workload:
@@ -60,8 +61,13 @@ def normal_iid(dims: int = 1000, chains: int = 4096) -> Workload:
     rng = np.random.default_rng(1)
     post = D.Normal(np.zeros((dims, 1)), 1.0)
     q0 = rng.normal(size=(chains, dims))
+    # fp64 instructions per gradient evaluation per chain, from the executed-instruction counts
+    # of the fused kernel (profiles/ncu_fused_priors_r01.txt: 162 M warp-level DADD/DMUL/DFMA per
+    # 4.1e7 coordinate-proposals): 6 unfused ops per coordinate and leapfrog step plus ~63 per
+    # coordinate and proposal for Box-Muller, energies and reductions, spread over L=10
     return Workload("normal_iid", post, M.Unit(dims), chains, "lf", 10, 0.05, q0,
-                    f"StandardNormal {dims}-dim posterior, {chains} chains, lf L=10, Unit mass")
+                    f"StandardNormal {dims}-dim posterior, {chains} chains, lf L=10, Unit mass",
+                    extra={"fp64_ops_per_grad": dims * (6.0 + 63.0 / 10)})
 
 
 # ----------------------------------------------------------------------------- config 3 --
@@ -178,9 +184,12 @@ def source_location(events: int = 16, stations: int = 30, chains: int = 8192) ->
     mass = M.Diagonal(rng.uniform(0.5, 2.0, size=(dims, 1)))
     truth = np.hstack([ex, ey, ez, eT]).reshape(-1)
     q0 = np.clip(truth[None, :] + 0.05 * rng.normal(size=(chains, dims)), lo[:, 0] + 1e-3, hi[:, 0] - 1e-3)
+    # fp64 instructions per gradient evaluation per chain: 24 per event-station pair in the
+    # gradient loop (profiles/ncu_fused_srcloc_r01.txt) + 1/10 of the 16-op misfit loop
     return Workload("source_location", post, mass, chains, "lf", 10, 0.004, q0,
                     f"SourceLocation3D {events} events x {stations} stations ({dims} params), Uniform box "
-                    f"prior, {chains} chains per GPU, lf L=10, Diagonal mass")
+                    f"prior, {chains} chains per GPU, lf L=10, Diagonal mass",
+                    extra={"fp64_ops_per_grad": events * stations * (24.0 + 1.6) + 12.0 * dims})
 
 
 BUILDERS = {

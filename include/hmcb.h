@@ -39,7 +39,8 @@ enum { HMCB_INTEGRATOR_LF = 0, HMCB_INTEGRATOR_3S = 1, HMCB_INTEGRATOR_4S = 2 };
 /* elementwise priors: base.py:539-574 (Normal, diagonal), base.py:689-710 (Laplace) */
 enum { HMCB_PRIOR_NORMAL = 0, HMCB_PRIOR_LAPLACE = 1 };
 /* execution path chosen by hmcb_finalize (reported by hmcb_path) */
-enum { HMCB_PATH_FUSED_PRIORS = 0, HMCB_PATH_FUSED_SRCLOC = 1, HMCB_PATH_STAGED = 2 };
+enum { HMCB_PATH_FUSED_PRIORS = 0, HMCB_PATH_FUSED_SRCLOC = 1, HMCB_PATH_STAGED = 2,
+       HMCB_PATH_FUSED_DENSE = 3 /* staged workspaces + whole-proposal kernel for dims <= 128 */ };
 
 int hmcb_abi_version(void);
 const char *hmcb_last_error(void);

@@ -85,7 +85,55 @@ def test_config5_source_location_vs_oracle():
 
 
 def test_config1_shape_vs_oracle():
-    _compare_with_oracle(workloads.dense_small(chains=9), K=4, randomize=False)
+    eng, _ = _compare_with_oracle(workloads.dense_small(chains=9), K=4, randomize=False)
+    assert eng.path == "fused_dense"
+    eng, _ = _compare_with_oracle(workloads.dense_small(chains=1000), K=3, chains_checked=5)
+    assert eng.path == "fused_dense"
+
+
+def test_fused_dense_kernel_equals_staged_pipeline():
+    """Small premultiplied dense models: the whole-proposal tensor-core kernel and the staged
+    multi-launch pipeline are independent implementations; same device random streams, same
+    chains (also with thinning, two blocks, a 4-stage integrator and a diagonal mass)."""
+    import torch
+
+    from hmclab_b200 import Distributions as D
+    from hmclab_b200 import MassMatrices as M
+    from hmclab_b200._engine import Engine
+
+    rng = np.random.default_rng(8)
+    dims, data, C = 77, 150, 333
+    G = rng.normal(size=(data, dims)) / np.sqrt(data)
+    dvec = G @ rng.normal(size=(dims, 1)) + 0.3 * rng.normal(size=(data, 1))
+    var = rng.uniform(0.5, 1.5, size=(data, 1))
+    post = D.BayesRule([D.Laplace(np.zeros((dims, 1)), np.full((dims, 1), 2.0)),
+                        D.LinearMatrix(G, dvec, var)])
+    mass = M.Diagonal(rng.uniform(0.5, 2.0, size=(dims, 1)))
+    plan, mplan = flatten(describe(post)), describe_mass(mass)
+    q0 = rng.normal(size=(C, dims))
+    results = {}
+    for label, force in (("fused", None), ("staged", "1")):
+        if force:
+            os.environ["HMCB_FORCE_STAGED"] = force
+        try:
+            eng = Engine(plan, mplan, C, integrator="4s", amount_of_steps=3)
+        finally:
+            os.environ.pop("HMCB_FORCE_STAGED", None)
+        assert eng.path == ("staged" if force else "fused_dense")
+        q = torch.as_tensor(q0).cuda().contiguous()
+        x = eng.misfit(q)
+        acc = torch.zeros(C, dtype=torch.int32, device="cuda")
+        rows = []
+        for lo, hi in ((0, 5), (5, 12)):
+            n = eng.stored_rows(hi - lo, 3, lo)
+            buf = torch.zeros(n, C, dims + 1, dtype=torch.float64, device="cuda")
+            eng.run_block(q, x, hi - lo, stepsize=0.25, seed=31, thinning=3, proposal_offset=lo,
+                          out_samples=buf, accepted_total=acc)
+            rows.append(buf.cpu().numpy())
+        results[label] = (np.concatenate(rows), q.cpu().numpy(), x.cpu().numpy(), acc.cpu().numpy())
+    f, s = results["fused"], results["staged"]
+    assert np.array_equal(f[3], s[3]) and 0.1 < f[3].mean() / 12 < 0.999
+    assert rel_err(f[0], s[0]) < 1e-11 and rel_err(f[1], s[1]) < 1e-11 and rel_err(f[2], s[2]) < 1e-11
 
 
 def test_large_dims_priors_only_uses_staged_path_and_matches_oracle():
