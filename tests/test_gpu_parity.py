@@ -195,3 +195,40 @@ def test_autotuned_chains_match_reference(name):
     ref_steps = gold[f"{name}__stepsizes"]
     known = ~np.isnan(ref_steps)
     assert rel_err(got_steps[known], ref_steps[known]) < TOL
+
+
+def test_clear_target_allows_a_new_configuration_on_the_same_engine():
+    """hmcb_clear_target frees the device constants; the engine can be described again."""
+    import ctypes as C
+
+    import torch
+
+    from hmclab_b200._engine import load_library
+
+    lib = load_library()
+    dp = C.POINTER(C.c_double)
+    h = C.c_void_p()
+    d, n = 5, 4
+    assert lib.hmcb_create(0, n, d, C.byref(h)) == 0
+    q = torch.linspace(-1, 1, n * d, dtype=torch.float64, device="cuda").reshape(n, d).contiguous()
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    for scale in (1.0, 4.0):
+        a = np.zeros(d)
+        b = np.full(d, 1.0 / scale)
+        assert lib.hmcb_add_prior(h, 0, 0, d, a.ctypes.data_as(dp), b.ctypes.data_as(dp), 0.0) == 0
+        assert lib.hmcb_finalize(h) == 0
+        assert lib.hmcb_finalize(h) != 0 and b"twice" in lib.hmcb_last_error()
+        assert lib.hmcb_add_prior(h, 0, 0, d, a.ctypes.data_as(dp), b.ctypes.data_as(dp), 0.0) != 0
+        assert lib.hmcb_misfit(h, q.data_ptr(), x.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        assert rel_err(x.cpu().numpy(), 0.5 * (q.cpu().numpy() ** 2).sum(axis=1) / scale) < 1e-14
+        assert lib.hmcb_clear_target(h) == 0
+        assert lib.hmcb_misfit(h, q.data_ptr(), x.data_ptr(), None) != 0    # not finalized any more
+    # bad arguments are refused with a message, not dereferenced
+    assert lib.hmcb_add_prior(h, 7, 0, d, a.ctypes.data_as(dp), b.ctypes.data_as(dp), 0.0) != 0
+    assert lib.hmcb_add_prior(h, 0, 3, d, a.ctypes.data_as(dp), b.ctypes.data_as(dp), 0.0) != 0
+    assert lib.hmcb_set_likelihood_srcloc3d(h, 2, 3, a.ctypes.data_as(dp), a.ctypes.data_as(dp),
+                                            a.ctypes.data_as(dp), a.ctypes.data_as(dp),
+                                            a.ctypes.data_as(dp), 0, 3.0) != 0   # dims != 4 * events
+    assert b"4*events" in lib.hmcb_last_error()
+    assert lib.hmcb_destroy(h) == 0
