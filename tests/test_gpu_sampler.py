@@ -263,3 +263,38 @@ def test_parallel_sample_smp_front_end(tmp_path):
         other = workloads.dense_small(chains=1).posterior
         ParallelSampleSMP().sample([HMC(), HMC()], names[:2], [w.posterior, other],
                                    overwrite_existing_files=True)
+
+
+@pytest.mark.parametrize("builder,kw", [("normal_iid", dict(dims=130, chains=70)),
+                                        ("dense_small", dict(chains=40)),
+                                        ("tomography", dict(nx=12, ny=9, rays=200, chains=33))])
+def test_sample_host_equals_device_blocks(builder, kw):
+    """hmcb_sample_host (host buffers, private streams, double-buffered D2H) returns exactly
+    what hmcb_run_block produces on device tensors for the same seed."""
+    import torch
+
+    from hmclab_b200 import workloads
+    from hmclab_b200._engine import Engine
+    from hmclab_b200._lowering import describe, describe_mass, flatten
+
+    w = workloads.BUILDERS[builder](**kw)
+    C, d = w.chains, w.dims
+    eng = Engine(flatten(describe(w.posterior)), describe_mass(w.mass_matrix), C,
+                 integrator=w.integrator, amount_of_steps=w.amount_of_steps)
+    P, thin = 12, 3
+    q0 = torch.as_tensor(w.initial_models).contiguous().pin_memory()
+    samples = torch.empty(P // thin, C, d + 1, dtype=torch.float64).pin_memory()
+    acc = torch.empty(C, dtype=torch.int32).pin_memory()
+    fq = torch.empty(C, d, dtype=torch.float64).pin_memory()
+    fx = torch.empty(C, dtype=torch.float64).pin_memory()
+    eng.sample_host(q0, P, stepsize=w.stepsize, thinning=thin, block_proposals=6, seed=17,
+                    chain_offset=5, samples=samples, accepted=acc, final_q=fq, final_x=fx)
+    q = q0.cuda()
+    x = eng.misfit(q)
+    ref = torch.zeros(P // thin, C, d + 1, dtype=torch.float64, device="cuda")
+    racc = torch.zeros(C, dtype=torch.int32, device="cuda")
+    eng.run_block(q, x, P, stepsize=w.stepsize, thinning=thin, seed=17, chain_offset=5,
+                  out_samples=ref, accepted_total=racc)
+    assert np.array_equal(samples.numpy(), ref.cpu().numpy())
+    assert np.array_equal(acc.numpy(), racc.cpu().numpy())
+    assert np.array_equal(fq.numpy(), q.cpu().numpy()) and np.array_equal(fx.numpy(), x.cpu().numpy())
