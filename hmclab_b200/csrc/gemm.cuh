@@ -2,17 +2,18 @@
 // chain batch, both with fused epilogues.
 //
 //   Y[M x N] = A[M x K] * B[K x N]
-//   A : model matrix (GtG, G or G^T), row-major, K contiguous, engine-private, zero padded
-//       to M % 128 == 0 and K % 16 == 0
+//   A : model matrix (GtG, G or G^T), engine-private, zero padded to M % 128 == 0 and
+//       K % 16 == 0, stored tile-major: [M/128][K/16] tiles of 128 rows x 20 doubles (16 values
+//       + the 4 padding doubles of the shared-memory layout), see pack in hmcb.cu
 //   B : chain batch in the transposed working layout [K x chains], chains contiguous,
 //       leading dimension ldb % 128 == 0, padded rows/columns are zero
 //   Y is never stored as such: an epilogue functor consumes the accumulator fragments
 //       (momentum/position update, residual scaling, or misfit partial sums).
 //
 // tcgen05 has no f64 kind; the fp64 tensor path on sm_100a is the warp-level DMMA.
-// Block tile 128x128x16, 8 warps (2 along M x 4 along N), warp tile 64x32, 3-stage
-// cp.async pipeline, padded shared tiles (A: 20 doubles/row, B: 132 doubles/row) so both
-// fragment loads are bank-conflict free.
+// Block tile 128x128x16, 8 warps (2 along M x 4 along N), warp tile 64x32, multi-stage
+// pipeline fed by TMA bulk copies completing on mbarriers, padded shared tiles (A: 20
+// doubles/row, B: 132 doubles/row) so both fragment loads are bank-conflict free.
 #pragma once
 #include "common.cuh"
 
@@ -21,19 +22,38 @@ namespace hmcb {
 constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 16;
 constexpr int GEMM_LDA_S = GEMM_BK + 4;   // 20 doubles
 constexpr int GEMM_LDB_S = GEMM_BN + 4;   // 132 doubles
-constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_THREADS = 256;
 constexpr int GEMM_A_STAGE = GEMM_BM * GEMM_LDA_S;  // doubles
 constexpr int GEMM_B_STAGE = GEMM_BK * GEMM_LDB_S;
 constexpr size_t GEMM_SMEM_BYTES = (size_t)GEMM_STAGES * (GEMM_A_STAGE + GEMM_B_STAGE) * sizeof(double);
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+// ---- bulk asynchronous copies (the TMA engine, SASS UBLKCP) completing on an mbarrier -----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_LOOP;\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+               "l"(gmem), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -59,48 +79,17 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
   const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * GEMM_BN;
   const int ktiles = K / GEMM_BK;
 
-  auto load_stage = [&](int stage, int kt) {
-    const int k0 = kt * GEMM_BK;
-    double* as = As + stage * GEMM_A_STAGE;
-    double* bs = Bs + stage * GEMM_B_STAGE;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {                    // A: 128 rows x 8 chunks of 2 doubles
-      const int chunk = tid + i * GEMM_THREADS;
-      const int r = chunk >> 3, cc = (chunk & 7) * 2;
-      cp_async16(as + r * GEMM_LDA_S + cc, A + (size_t)(m0 + r) * lda + k0 + cc);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {                    // B: 16 rows x 64 chunks
-      const int chunk = tid + i * GEMM_THREADS;
-      const int r = chunk >> 6, cc = (chunk & 63) * 2;
-      cp_async16(bs + r * GEMM_LDB_S + cc, B + (size_t)(k0 + r) * ldb + n0 + cc);
-    }
-  };
-
   double acc[8][4][2];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-#pragma unroll
-  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
-    if (s < ktiles) load_stage(s, s);
-    cp_async_commit();
-  }
-
   const int arow = lane >> 2, acol = lane & 3;       // A frag: row = lane/4, k = lane%4
   const int brow = lane & 3, bcol = lane >> 2;       // B frag: k = lane%4, col = lane/4
-  for (int kt = 0; kt < ktiles; ++kt) {
-    cp_async_wait<GEMM_STAGES - 2>();
-    __syncthreads();
-    {
-      const int nk = kt + GEMM_STAGES - 1;
-      if (nk < ktiles) load_stage(nk % GEMM_STAGES, nk);
-      cp_async_commit();
-    }
-    const double* as = As + (kt % GEMM_STAGES) * GEMM_A_STAGE + (wm * 64 + arow) * GEMM_LDA_S + acol;
-    const double* bs = Bs + (kt % GEMM_STAGES) * GEMM_B_STAGE + brow * GEMM_LDB_S + wn * 32 + bcol;
+  auto compute_stage = [&](int stage) {
+    const double* as = As + stage * GEMM_A_STAGE + (wm * 64 + arow) * GEMM_LDA_S + acol;
+    const double* bs = Bs + stage * GEMM_B_STAGE + brow * GEMM_LDB_S + wn * 32 + bcol;
 #pragma unroll
     for (int kk = 0; kk < GEMM_BK; kk += 4) {
       double a[8], b[4];
@@ -113,8 +102,49 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+  };
+
+  // Operand tiles are staged by the bulk asynchronous copy engine (TMA, SASS UBLKCP).  The
+  // model matrix A is engine-private, so hmcb_finalize stores it tile-major with the shared-
+  // memory padding baked in ([M/128][K/16] tiles of 128 x 20 doubles): one 20 KB copy lands a
+  // whole A tile in its conflict-free layout.  B (the chain batch, chains contiguous) takes one
+  // 1 KB copy per k-row.  Every stage completes on its own mbarrier (expect_tx = 36 KB).
+  __shared__ uint64_t full_bar[GEMM_STAGES];
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < GEMM_STAGES; ++st) mbar_init(&full_bar[st], 1);
+    fence_async_proxy();
   }
-  cp_async_wait<0>();
+  __syncthreads();
+  constexpr unsigned kStageBytes = (GEMM_A_STAGE + GEMM_BK * GEMM_BN) * sizeof(double);
+  const double* a_tiles = A + (size_t)blockIdx.y * ktiles * GEMM_A_STAGE;
+  auto load_stage = [&](int stage, int kt) {   // called by warp 0 only
+    const int k0 = kt * GEMM_BK;
+    double* as = As + stage * GEMM_A_STAGE;
+    double* bs = Bs + stage * GEMM_B_STAGE;
+    if (lane == 0) {
+      mbar_expect_tx(&full_bar[stage], kStageBytes);
+      bulk_copy_g2s(as, a_tiles + (size_t)kt * GEMM_A_STAGE, GEMM_A_STAGE * sizeof(double), &full_bar[stage]);
+    }
+    __syncwarp();
+    if (lane < GEMM_BK)
+      bulk_copy_g2s(bs + lane * GEMM_LDB_S, B + (size_t)(k0 + lane) * ldb + n0, GEMM_BN * sizeof(double),
+                    &full_bar[stage]);
+  };
+  if (warp == 0) {
+#pragma unroll
+    for (int st = 0; st < GEMM_STAGES - 1; ++st)
+      if (st < ktiles) load_stage(st, st);
+  }
+  for (int kt = 0; kt < ktiles; ++kt) {
+    mbar_wait(&full_bar[kt % GEMM_STAGES], (unsigned)((kt / GEMM_STAGES) & 1));
+    __syncthreads();   // everyone is done with the stage that is refilled next
+    if (warp == 0) {
+      const int nk = kt + GEMM_STAGES - 1;
+      if (nk < ktiles) load_stage(nk % GEMM_STAGES, nk);
+    }
+    compute_stage(kt % GEMM_STAGES);
+  }
   __syncthreads();
 
   // C frag of sub-tile (i, j): row = base_m + 8 i, columns base_n + 8 j + {0, 1}

@@ -100,6 +100,7 @@ struct hmcb_engine {
   SrcLocDev L{};
   // staged path
   int ld = 0, dpad = 0, npad = 0, jtiles = 0, ltiles = 0;
+  double *dA_rowmajor = nullptr;  // [128 x 128] GtG for the fused small-dense kernel
   double *dA = nullptr, *dAt = nullptr, *dvec = nullptr, *dvar = nullptr, *dsigma = nullptr;
   CsrDev csr_dev{}, csr_t_dev{};
   double *q_cur = nullptr, *q_w[2] = {nullptr, nullptr}, *p_w = nullptr, *R = nullptr;
@@ -144,6 +145,26 @@ int dev_upload_padded(hmcb_engine* e, const double* src, int64_t rows, int64_t c
   if (dev_alloc(e, (size_t)rows_pad * cols_pad, &p, true)) return -1;
   HMCB_CUDA(cudaMemcpy2D(p, (size_t)cols_pad * sizeof(double), src, (size_t)cols * sizeof(double),
                          (size_t)cols * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice));
+  *out = p;
+  return 0;
+}
+
+// rows x cols host matrix -> tile-major device copy for the DMMA GEMM's bulk-copy staging:
+// [rows_pad/128][cols_pad/16] tiles of GEMM_BM x GEMM_LDA_S doubles (zero padded)
+int dev_upload_tiled(hmcb_engine* e, const double* src, int64_t rows, int64_t cols, int64_t rows_pad,
+                     int64_t cols_pad, double** out) {
+  const int64_t mt = rows_pad / GEMM_BM, kt = cols_pad / GEMM_BK;
+  std::vector<double> host((size_t)mt * kt * GEMM_A_STAGE, 0.0);
+  for (int64_t i = 0; i < rows; ++i) {
+    const int64_t tm = i / GEMM_BM, r = i % GEMM_BM;
+    for (int64_t j = 0; j < cols; ++j) {
+      const int64_t tk = j / GEMM_BK, c = j % GEMM_BK;
+      host[(size_t)((tm * kt + tk) * GEMM_A_STAGE + r * GEMM_LDA_S + c)] = src[(size_t)i * cols + j];
+    }
+  }
+  double* p = nullptr;
+  if (dev_alloc(e, host.size(), &p, false)) return -1;
+  HMCB_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice));
   *out = p;
   return 0;
 }
@@ -725,14 +746,15 @@ int hmcb_finalize(hmcb_engine* e) {
     switch (e->lik) {
       case LK_NONE: e->ltiles = 0; break;
       case LK_DENSE_PREMULT:
-        if (dev_upload_padded(e, e->h_A.data(), d, d, e->dpad, e->dpad, &e->dA)) return -1;
+        if (dev_upload_tiled(e, e->h_A.data(), d, d, e->dpad, e->dpad, &e->dA)) return -1;
+        if (e->dpad == 128 && dev_upload_padded(e, e->h_A.data(), d, d, 128, 128, &e->dA_rowmajor)) return -1;
         if (dev_upload(e, e->h_vec, &tmp)) return -1;
         e->dvec = const_cast<double*>(tmp);
         e->ltiles = e->dpad / GEMM_BM;
         break;
       case LK_DENSE_DIRECT:
-        if (dev_upload_padded(e, e->h_A.data(), e->N, d, e->npad, e->dpad, &e->dA)) return -1;
-        if (dev_upload_padded(e, e->h_At.data(), d, e->N, e->dpad, e->npad, &e->dAt)) return -1;
+        if (dev_upload_tiled(e, e->h_A.data(), e->N, d, e->npad, e->dpad, &e->dA)) return -1;
+        if (dev_upload_tiled(e, e->h_At.data(), d, e->N, e->dpad, e->npad, &e->dAt)) return -1;
         e->ltiles = e->npad / GEMM_BM;
         break;
       case LK_CSR_DIRECT:
@@ -897,7 +919,7 @@ int hmcb_run_block(hmcb_engine* e, const hmcb_block* b, void* stream) {
     return 0;
   }
   if (e->fused_dense) {
-    HMCB_CUDA(launch_fused_dense(fused_args(e, b), e->dA, e->dvec, e->dtd, s));
+    HMCB_CUDA(launch_fused_dense(fused_args(e, b), e->dA_rowmajor, e->dvec, e->dtd, s));
     e->launches += 1;
     return 0;
   }
