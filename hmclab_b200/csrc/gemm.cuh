@@ -23,7 +23,8 @@ constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 16;
 constexpr int GEMM_LDA_S = GEMM_BK + 4;   // 20 doubles
 constexpr int GEMM_LDB_S = GEMM_BN + 4;   // 132 doubles
 constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 256;                      // 8 consumer warps
+constexpr int GEMM_LAUNCH_THREADS = GEMM_THREADS + 32;  // + 1 producer warp
 constexpr int GEMM_A_STAGE = GEMM_BM * GEMM_LDA_S;  // doubles
 constexpr int GEMM_B_STAGE = GEMM_BK * GEMM_LDB_S;
 constexpr size_t GEMM_SMEM_BYTES = (size_t)GEMM_STAGES * (GEMM_A_STAGE + GEMM_B_STAGE) * sizeof(double);
@@ -53,6 +54,12 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem, const void* gmem, unsi
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
                "l"(gmem), "r"(bytes), "r"(b) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(a) : "memory");
+}
+// barrier among the 256 consumer threads of the GEMM (the producer warp has left by then)
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
@@ -67,7 +74,9 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
 // called once per thread with its 64 accumulators: acc[i][j][h] = Y[base_m + 8 i][base_n + 8 j + h];
 // `smem` is the (now idle) pipeline buffer for block-wide reductions.
 template <class Epilogue>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// 288 threads are budgeted like 384 by the launch check (168 registers per thread): asking for
+// more with __maxnreg__ fails at launch with 'too many resources requested'
+__global__ void __launch_bounds__(GEMM_LAUNCH_THREADS, 1)
 dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
                  int K, Epilogue epi) {
   extern __shared__ __align__(16) double gemm_smem[];
@@ -109,43 +118,46 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
   // memory padding baked in ([M/128][K/16] tiles of 128 x 20 doubles): one 20 KB copy lands a
   // whole A tile in its conflict-free layout.  B (the chain batch, chains contiguous) takes one
   // 1 KB copy per k-row.  Every stage completes on its own mbarrier (expect_tx = 36 KB).
-  __shared__ uint64_t full_bar[GEMM_STAGES];
+  // Warp 8 is the producer: it waits for a stage to be released by the 8 consumer warps
+  // (empty barrier, one arrival per warp) and refills it; the consumers never meet at a
+  // block-wide barrier inside the main loop.
+  __shared__ uint64_t full_bar[GEMM_STAGES], empty_bar[GEMM_STAGES];
   if (tid == 0) {
 #pragma unroll
-    for (int st = 0; st < GEMM_STAGES; ++st) mbar_init(&full_bar[st], 1);
+    for (int st = 0; st < GEMM_STAGES; ++st) {
+      mbar_init(&full_bar[st], 1);
+      mbar_init(&empty_bar[st], GEMM_THREADS / 32);
+    }
     fence_async_proxy();
   }
   __syncthreads();
   constexpr unsigned kStageBytes = (GEMM_A_STAGE + GEMM_BK * GEMM_BN) * sizeof(double);
-  const double* a_tiles = A + (size_t)blockIdx.y * ktiles * GEMM_A_STAGE;
-  auto load_stage = [&](int stage, int kt) {   // called by warp 0 only
-    const int k0 = kt * GEMM_BK;
-    double* as = As + stage * GEMM_A_STAGE;
-    double* bs = Bs + stage * GEMM_B_STAGE;
-    if (lane == 0) {
-      mbar_expect_tx(&full_bar[stage], kStageBytes);
-      bulk_copy_g2s(as, a_tiles + (size_t)kt * GEMM_A_STAGE, GEMM_A_STAGE * sizeof(double), &full_bar[stage]);
+  if (warp == GEMM_THREADS / 32) {
+    const double* a_tiles = A + (size_t)blockIdx.y * ktiles * GEMM_A_STAGE;
+    for (int kt = 0; kt < ktiles; ++kt) {
+      const int stage = kt % GEMM_STAGES, use = kt / GEMM_STAGES;
+      if (use > 0) mbar_wait(&empty_bar[stage], (unsigned)((use - 1) & 1));
+      double* as = As + stage * GEMM_A_STAGE;
+      double* bs = Bs + stage * GEMM_B_STAGE;
+      if (lane == 0) {
+        mbar_expect_tx(&full_bar[stage], kStageBytes);
+        bulk_copy_g2s(as, a_tiles + (size_t)kt * GEMM_A_STAGE, GEMM_A_STAGE * sizeof(double), &full_bar[stage]);
+      }
+      __syncwarp();
+      if (lane < GEMM_BK)
+        bulk_copy_g2s(bs + lane * GEMM_LDB_S, B + (size_t)(kt * GEMM_BK + lane) * ldb + n0,
+                      GEMM_BN * sizeof(double), &full_bar[stage]);
     }
-    __syncwarp();
-    if (lane < GEMM_BK)
-      bulk_copy_g2s(bs + lane * GEMM_LDB_S, B + (size_t)(k0 + lane) * ldb + n0, GEMM_BN * sizeof(double),
-                    &full_bar[stage]);
-  };
-  if (warp == 0) {
-#pragma unroll
-    for (int st = 0; st < GEMM_STAGES - 1; ++st)
-      if (st < ktiles) load_stage(st, st);
+    return;
   }
   for (int kt = 0; kt < ktiles; ++kt) {
-    mbar_wait(&full_bar[kt % GEMM_STAGES], (unsigned)((kt / GEMM_STAGES) & 1));
-    __syncthreads();   // everyone is done with the stage that is refilled next
-    if (warp == 0) {
-      const int nk = kt + GEMM_STAGES - 1;
-      if (nk < ktiles) load_stage(nk % GEMM_STAGES, nk);
-    }
-    compute_stage(kt % GEMM_STAGES);
+    const int stage = kt % GEMM_STAGES;
+    mbar_wait(&full_bar[stage], (unsigned)((kt / GEMM_STAGES) & 1));
+    compute_stage(stage);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
   }
-  __syncthreads();
+  consumer_barrier();   // the pipeline buffers are free for the epilogue
 
   // C frag of sub-tile (i, j): row = base_m + 8 i, columns base_n + 8 j + {0, 1}
   epi.tile(m0, n0, m0 + wm * 64 + (lane >> 2), n0 + wn * 32 + 2 * (lane & 3), acc, gemm_smem);

@@ -24,7 +24,7 @@ static cudaError_t launch_gemm(const double* A, int lda, int M, const double* B,
                                const Epi& epi, cudaStream_t s) {
   if (M % GEMM_BM || ldb % GEMM_BN || K % GEMM_BK) return cudaErrorInvalidValue;
   const dim3 grid(ldb / GEMM_BN, M / GEMM_BM);
-  dmma_gemm_kernel<Epi><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, s>>>(A, lda, B, ldb, K, epi);
+  dmma_gemm_kernel<Epi><<<grid, GEMM_LAUNCH_THREADS, GEMM_SMEM_BYTES, s>>>(A, lda, B, ldb, K, epi);
   return cudaGetLastError();
 }
 

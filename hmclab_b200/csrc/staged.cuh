@@ -199,7 +199,7 @@ struct MisfitEpi {
         v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 16));
         if ((lane >> 2) == 0) smem[wm * GEMM_BN + wn * 32 + j * 8 + 2 * (lane & 3) + h] = v;
       }
-    __syncthreads();
+    consumer_barrier();
     if (threadIdx.x < GEMM_BN) {
       const double v = __dadd_rn(smem[threadIdx.x], smem[GEMM_BN + threadIdx.x]);
       part[(size_t)(m0 / GEMM_BM) * ld + n0 + threadIdx.x] = v;
