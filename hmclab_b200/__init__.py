@@ -8,15 +8,16 @@ batch container.  There is no CPU fallback: without the compiled engine library 
 CUDA device every evaluation raises.
 """
 from hmclab_b200 import Distributions, MassMatrices  # noqa: F401
+from hmclab_b200.Samples import Samples, combine_samples  # noqa: F401  (as hmclab/__init__.py:11)
 
-__all__ = ["Distributions", "MassMatrices", "Samplers", "Samples"]
+__all__ = ["Distributions", "MassMatrices", "Samplers", "Samples", "combine_samples"]
 __version__ = "0.1.0"
 
 
 def __getattr__(name):
-    # Samplers / Samples import torch; keep `import hmclab_b200` light.
-    if name in ("Samplers", "Samples"):
+    # Samplers pulls in torch; keep `import hmclab_b200` light.
+    if name == "Samplers":
         import importlib
 
-        return importlib.import_module(f"hmclab_b200.{name}")
+        return importlib.import_module("hmclab_b200.Samplers")
     raise AttributeError(name)
