@@ -12,7 +12,7 @@ namespace hmcb {
 
 template <int TPC, int LPE>
 static cudaError_t launch_fs(const FusedArgs& A, const SrcLocDev& L, cudaStream_t s) {
-  constexpr int BLOCK = TPC <= 32 ? 256 : TPC;
+  constexpr int BLOCK = TPC <= 32 ? SRCLOC_SMALL_BLOCK : TPC;
   constexpr int CPB = BLOCK / TPC;
   const size_t smem = srcloc_smem_bytes(L);
   if (smem > 48 * 1024) {
@@ -27,7 +27,7 @@ static cudaError_t launch_fs(const FusedArgs& A, const SrcLocDev& L, cudaStream_
 template <int TPC, int LPE>
 static cudaError_t launch_ev(const DevTarget& T, const SrcLocDev& L, int chains, int mode,
                              const double* q, double* out, cudaStream_t s) {
-  constexpr int BLOCK = TPC <= 32 ? 256 : TPC;
+  constexpr int BLOCK = TPC <= 32 ? SRCLOC_SMALL_BLOCK : TPC;
   constexpr int CPB = BLOCK / TPC;
   const size_t smem = srcloc_smem_bytes(L);
   if (smem > 48 * 1024) {

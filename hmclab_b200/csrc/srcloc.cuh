@@ -12,6 +12,11 @@
 
 namespace hmcb {
 
+// Chains that fit inside a warp are packed into blocks of 64 threads: with equal work per
+// block and an fp64-bound SM, small blocks let the hardware balance the last wave (8192 chains
+// of config 5 in 256-thread blocks ran in the time of 9472).
+constexpr int SRCLOC_SMALL_BLOCK = 64;
+
 struct SrcLocDev {
   int events, stations, infer_velocity, pad;
   double velocity;
@@ -134,7 +139,7 @@ struct SrcLocLane {
   bool has_event, lead, vlead, live;
 
   __device__ __forceinline__ void init(int chains, int E) {
-    constexpr int BLOCK = TPC <= 32 ? 256 : TPC;
+    constexpr int BLOCK = TPC <= 32 ? SRCLOC_SMALL_BLOCK : TPC;
     constexpr int CPB = BLOCK / TPC;
     const int t = threadIdx.x % TPC;
     c = blockIdx.x * CPB + threadIdx.x / TPC;
@@ -192,10 +197,10 @@ __device__ __forceinline__ unsigned srcloc_violations(const DevTarget& T, const 
 }
 
 template <int TPC, int LPE>
-__global__ void __launch_bounds__((TPC <= 32 ? 256 : TPC), (TPC <= 256 ? 2 : 1))
+__global__ void __launch_bounds__((TPC <= 32 ? SRCLOC_SMALL_BLOCK : TPC), (TPC <= 32 ? 8 : (TPC <= 256 ? 2 : 1)))
 hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
   extern __shared__ __align__(16) double dyn_smem[];
-  __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(TPC <= 32 ? 256 : TPC)];
+  __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(TPC <= 32 ? SRCLOC_SMALL_BLOCK : TPC)];
   const ChainReduce<TPC> red{scratch};
   const SrcLocShared M = srcloc_stage(L, dyn_smem);
   const DevTarget& T = A.T;
@@ -366,11 +371,11 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
 
 // mode 0: x[c] = misfit ; mode 1: g[c,:] = gradient
 template <int TPC, int LPE>
-__global__ void __launch_bounds__((TPC <= 32 ? 256 : TPC))
+__global__ void __launch_bounds__((TPC <= 32 ? SRCLOC_SMALL_BLOCK : TPC))
 srcloc_eval_kernel(const DevTarget T, const SrcLocDev L, int chains, int mode,
                    const double* __restrict__ qin, double* __restrict__ out) {
   extern __shared__ __align__(16) double dyn_smem[];
-  __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(TPC <= 32 ? 256 : TPC)];
+  __shared__ double scratch[ChainReduce<TPC>::scratch_doubles(TPC <= 32 ? SRCLOC_SMALL_BLOCK : TPC)];
   const ChainReduce<TPC> red{scratch};
   const SrcLocShared M = srcloc_stage(L, dyn_smem);
   const int d = T.dims, E = L.events;
