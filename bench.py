@@ -219,8 +219,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
-    assert args.warmup >= 3 or args.impl == "reference" or os.environ.get("HMCB_BENCH_ALLOW_SHORT"), \
-        "timing rules: at least 3 warm-up steps"
+    if args.impl != "reference" and args.warmup < 3:
+        args.warmup = 3   # timing rules: at least 3 warm-up steps (the line reports what was run)
+    args.steps = max(1, args.steps)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
