@@ -379,7 +379,7 @@ class HMC:
                 if copied[slot] is not None:
                     torch.cuda.current_stream(dev).wait_event(copied[slot])
                 t0 = _time.time()
-                eng.run_block(self._q, self._x, B, stepsize=self.stepsize,
+                self._run_block(self._q, self._x, B, stepsize=self.stepsize,
                               randomize_stepsize=self.randomize_stepsize, thinning=thin,
                               proposal_offset=done, chain_offset=self.chain_offset, seed=device_seed,
                               out_samples=dbuf[slot][:rows] if rows else None, accepted_total=accepted,
@@ -421,6 +421,9 @@ class HMC:
             torch.cuda.synchronize(dev)
             self.end_time = _datetime.now()
             self._close_sampler(accepted)
+
+    def _run_block(self, q, x, B, **kw):
+        self.engine.run_block(q, x, B, **kw)
 
     def _history_buffers(self, history, B):
         if history is None:
@@ -481,6 +484,106 @@ class HMC:
         return {"proposals": self.proposals, "chains": self.chains,
                 "acceptance_rate": self.accepted_proposals / max(1, (self.current_proposal + 1) * self.chains),
                 "path": self.engine.path if self.engine else None}
+
+
+class RWMH(HMC):
+    """Random Walk Metropolis-Hastings over a batch of chains (hmclab/Samplers.py:777-1102):
+    ``proposed = current + stepsize * normal``, accepted iff ``exp(x - x') > u``.  ``stepsize`` is
+    a positive float or a ``(dimensions, 1)`` array of per-coordinate steps; autotuning adapts a
+    scalar step per chain (with an array step the array becomes the fixed per-coordinate factor
+    and the adapted scalar starts at 1.0, as in the reference :935-944)."""
+
+    name = "Random Walk Metropolis Hastings"
+
+    def sample(self, samples_filename: str, distribution, stepsize=1.0, initial_model=None,
+               proposals: int = 100, online_thinning: int = 1, diagnostic_mode: bool = False,
+               overwrite_existing_file: bool = False, max_time: float = None,
+               autotuning: bool = False, target_acceptance_rate: float = 0.65,
+               learning_rate: float = 0.75, queue=None, disable_progressbar=False, *,
+               chains: Optional[int] = None, block_proposals: Optional[int] = None,
+               host_rng: bool = False, device: Optional[int] = None, distributed: bool = False,
+               **kwargs):
+        self.samples = None
+        try:
+            self._init_sampler(
+                samples_filename=samples_filename, distribution=distribution,
+                initial_model=initial_model, proposals=proposals, online_thinning=online_thinning,
+                overwrite_existing_file=overwrite_existing_file, max_time=max_time,
+                disable_progressbar=disable_progressbar, diagnostic_mode=diagnostic_mode,
+                chains=chains, block_proposals=block_proposals, host_rng=host_rng, device=device,
+                distributed=distributed, stepsize=stepsize, autotuning=autotuning,
+                target_acceptance_rate=target_acceptance_rate, learning_rate=learning_rate, **kwargs)
+        except Exception:
+            if self.samples is not None:
+                self.samples.close()
+            raise
+        self._sample_loop()
+        if queue is not None:
+            queue.put({"0": self._summary()})
+        return self
+
+    def _init_sampler_specific(self, **kwargs):
+        for key in ("stepsize", "autotuning", "target_acceptance_rate", "learning_rate"):
+            setattr(self, key, kwargs.pop(key))
+        self._step_vector = None
+        if self.autotuning:
+            assert self.learning_rate > 0.5 and self.learning_rate <= 1.0, (
+                f"The learning rate should be larger than 0.5 and smaller than or equal to 1.0, "
+                f"otherwise the Markov chain does not converge. Chosen: {self.learning_rate}")
+            if type(self.stepsize) == _numpy.ndarray:
+                self._step_vector = self.stepsize
+                self.stepsize = 1.0
+            assert type(self.stepsize) == float, (
+                "Autotuning RWMH is only implemented for scalar stepsizes. If you need it for "
+                "non-scalar steps, write us an email.")
+        if len(kwargs) != 0:
+            raise TypeError(f"Unidentified argument(s) not applicable to sampler: {kwargs}")
+        try:
+            self.stepsize = float(self.stepsize)
+            assert self.stepsize > 0.0, (
+                "RW-MH step length should be a positive float or a numpy.ndarray. The passed "
+                "argument is a float equal to or smaller than zero.")
+        except TypeError:
+            vec = _numpy.asarray(self.stepsize)
+            assert vec.shape == (self.dimensions, 1), (
+                "RW-MH step length should be a numpy.ndarray of shape (dimensions, 1) or a "
+                "positive float. The passed argument is an ndarray of the wrong shape.")
+            self._step_vector = vec
+            self.stepsize = 1.0     # proposed = current + stepsize_array * 1.0 * normal (:1064-1069)
+        if self._step_vector is not None:
+            assert _numpy.asarray(self._step_vector).shape == (self.dimensions, 1)
+        # the engine object also carries the HMC settings; they are not used by RWMH
+        self.mass_matrix = _Unit(self.dimensions)
+        self.integrator, self.amount_of_steps, self.randomize_stepsize = "lf", 1, False
+
+    def _write_tuning_settings(self):
+        self.samples.write_attribute(
+            "stepsize", self.stepsize if self._step_vector is None else "ndarray")
+
+    def _host_draws(self, k0, B):
+        """normal(d,1) then uniform(0,1) per proposal (Samplers.py:1064-1081)."""
+        C, d = self.chains, self.dimensions
+        if not hasattr(self, "_chain_rngs"):
+            base = self.seed if isinstance(self.seed, (int, _numpy.integer)) else None
+            self._chain_rngs = [
+                self.rng if self.chain_offset + c == 0
+                else _numpy.random.default_rng(None if base is None else base + self.chain_offset + c)
+                for c in range(C)]
+        z, ua = _numpy.empty((B, C, d)), _numpy.empty((B, C))
+        for c, rng in enumerate(self._chain_rngs):
+            for k in range(B):
+                z[k, c] = rng.normal(size=(d, 1))[:, 0]
+                ua[k, c] = rng.uniform(0, 1)
+        return z, _numpy.ones((B, C)), ua
+
+    def _run_block(self, q, x, B, **kw):
+        kw.pop("randomize_stepsize", None)
+        kw.pop("u_step", None)
+        if self._step_vector is not None and not hasattr(self, "_step_vector_dev"):
+            self._step_vector_dev = self._torch.as_tensor(
+                _numpy.ascontiguousarray(self._step_vector, dtype=_numpy.float64).reshape(-1)
+            ).to(self.engine.device)
+        self.engine.run_block_rwmh(q, x, B, step_vector=getattr(self, "_step_vector_dev", None), **kw)
 
 
 class ParallelSampleSMP:

@@ -86,6 +86,7 @@ SIGNATURES = {
     "hmcb_kinetic_energy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmcb_kinetic_gradient": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmcb_run_block": (C.c_int, [C.c_void_p, C.POINTER(_Block), C.c_void_p]),
+    "hmcb_run_block_rwmh": (C.c_int, [C.c_void_p, C.POINTER(_Block), C.c_void_p, C.c_void_p]),
     "hmcb_sample_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                    C.c_double, C.c_int, C.c_uint64, C.c_int64, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -301,7 +302,8 @@ class Engine:
                   z=None, u_step=None, u_accept=None, out_samples=None, out_accept=None,
                   out_h0=None, out_h1=None, accepted_total=None, out_q_prop=None, out_p_prop=None,
                   trace_q=None, trace_g=None, stepsize_chain=None, autotune=False,
-                  target_acceptance_rate=0.65, learning_rate=0.75, out_stepsize=None):
+                  target_acceptance_rate=0.65, learning_rate=0.75, out_stepsize=None,
+                  rwmh=False, step_vector=None):
         """Advance every chain by ``proposals`` proposals in place (q [C,d], x [C])."""
         torch = self.torch
         self._check_batch(q, "q")
@@ -338,7 +340,19 @@ class Engine:
             target_acceptance_rate=float(target_acceptance_rate), learning_rate=float(learning_rate),
             out_stepsize=ptr(out_stepsize, (B, Cn), f64, "out_stepsize"),
         )
-        self._ok(self.lib.hmcb_run_block(self._handle, C.byref(blk), self._stream()))
+        if rwmh:
+            sv = None
+            if step_vector is not None:
+                sv = ptr(step_vector, (d,), f64, "step_vector")
+            self._ok(self.lib.hmcb_run_block_rwmh(self._handle, C.byref(blk), sv, self._stream()))
+        else:
+            self._ok(self.lib.hmcb_run_block(self._handle, C.byref(blk), self._stream()))
+
+    def run_block_rwmh(self, q, x, proposals: int, *, stepsize: float, step_vector=None, **kw):
+        """Random Walk Metropolis-Hastings proposals (hmcb_run_block_rwmh); same arguments as
+        run_block, plus ``step_vector`` [dims] per-coordinate step factors."""
+        self.run_block(q, x, proposals, stepsize=stepsize, randomize_stepsize=False, rwmh=True,
+                       step_vector=step_vector, **kw)
 
     def sample_host(self, q0, proposals: int, *, stepsize: float, randomize_stepsize: bool = True,
                     thinning: int = 1, block_proposals: int = 0, seed: int = 0, chain_offset: int = 0,

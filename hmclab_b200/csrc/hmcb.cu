@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "launch.cuh"
+#include "rwmh.cuh"
 
 using namespace hmcb;
 
@@ -108,6 +109,7 @@ struct hmcb_engine {
          *lpart = nullptr;
   unsigned* flags[3] = {nullptr, nullptr, nullptr};
   unsigned char* accbuf = nullptr;
+  double *rw_qp = nullptr, *rw_x1 = nullptr;  // hmcb_run_block_rwmh scratch
   // hmcb_sample_host: streams, events and device buffers are created once and reused
   cudaStream_t s_compute = nullptr, s_copy = nullptr;
   cudaEvent_t ev_produced[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
@@ -924,6 +926,52 @@ int hmcb_run_block(hmcb_engine* e, const hmcb_block* b, void* stream) {
     return 0;
   }
   return staged_run_block(e, b, s);
+}
+
+int hmcb_run_block_rwmh(hmcb_engine* e, const hmcb_block* b, const double* step_vector, void* stream) {
+  HMCB_READY(e);
+  HMCB_CHECK(b, "hmcb_run_block_rwmh: block is NULL");
+  HMCB_CHECK(b->proposals > 0 && b->proposals < (1ll << 31), "hmcb_run_block_rwmh: proposals must be positive");
+  HMCB_CHECK(b->thinning > 0, "hmcb_run_block_rwmh: thinning must be positive");
+  HMCB_CHECK(b->proposal_offset >= 0 && b->chain_offset >= 0, "hmcb_run_block_rwmh: negative offset");
+  HMCB_CHECK(b->stepsize > 0.0 || b->stepsize_chain, "hmcb_run_block_rwmh: stepsize must be positive");
+  HMCB_CHECK(b->q && b->x, "hmcb_run_block_rwmh: q and x are required");
+  HMCB_CHECK(!b->autotune || b->stepsize_chain, "hmcb_run_block_rwmh: autotune needs stepsize_chain");
+  HMCB_CHECK(!b->autotune || (b->learning_rate > 0.5 && b->learning_rate <= 1.0),
+             "The learning rate should be larger than 0.5 and smaller than or equal to 1.0");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int C = (int)e->C, d = (int)e->d;
+  if (!e->rw_qp) {
+    if (dev_alloc(e, (size_t)C * d, &e->rw_qp) || dev_alloc(e, (size_t)C, &e->rw_x1)) return -1;
+  }
+  const int64_t first_row = (b->proposal_offset + b->thinning - 1) / b->thinning;
+  for (int64_t kb = 0; kb < b->proposals; ++kb) {
+    const int64_t kglob = b->proposal_offset + kb;
+    const size_t kc = (size_t)kb * C;
+    HMCB_CUDA(launch_rwmh_propose(C, d, b->q, e->rw_qp, step_vector, b->stepsize_chain, b->stepsize,
+                                  b->z_in ? b->z_in + kc * d : nullptr, b->seed, b->chain_offset, kglob, s));
+    e->launches += 1;
+    if (hmcb_misfit(e, e->rw_qp, e->rw_x1, stream)) return -1;
+    if (b->out_q_prop)
+      HMCB_CUDA(cudaMemcpyAsync(b->out_q_prop + kc * d, e->rw_qp, sizeof(double) * (size_t)C * d,
+                                cudaMemcpyDeviceToDevice, s));
+    RwmhDecide D{};
+    D.chains = C; D.dims = d; D.q = b->q; D.qp = e->rw_qp; D.x = b->x; D.x1 = e->rw_x1;
+    D.u_in = b->u_accept_in ? b->u_accept_in + kc : nullptr;
+    D.seed = b->seed; D.chain_offset = b->chain_offset; D.kglob = kglob;
+    if (b->out_samples && (kglob % b->thinning) == 0)
+      D.sample_rows = b->out_samples + (size_t)(kglob / b->thinning - first_row) * C * (size_t)(d + 1);
+    D.out_accept = b->out_accept ? b->out_accept + kc : nullptr;
+    D.out_h0 = b->out_h0 ? b->out_h0 + kc : nullptr;
+    D.out_h1 = b->out_h1 ? b->out_h1 + kc : nullptr;
+    D.accepted_total = b->accepted_total;
+    D.stepsize_chain = b->stepsize_chain;
+    D.out_stepsize = b->out_stepsize ? b->out_stepsize + kc : nullptr;
+    D.tune = AutotuneArgs{b->autotune ? 1 : 0, b->target_acceptance_rate, b->learning_rate};
+    HMCB_CUDA(launch_rwmh_decide(D, s));
+    e->launches += 1;
+  }
+  return 0;
 }
 
 int hmcb_sample_host(hmcb_engine* e, const double* q0_host, int64_t proposals, int64_t thinning,

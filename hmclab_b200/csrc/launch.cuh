@@ -23,6 +23,14 @@ cudaError_t launch_mass_elementwise(const DevTarget& T, int chains, int mode, co
 cudaError_t launch_kinetic_energy(const DevTarget& T, int chains, const double* p, double* k,
                                   cudaStream_t s);
 
+// random walk Metropolis-Hastings (rwmh.cuh, compiled in launch_fused.cu)
+struct RwmhDecide;
+cudaError_t launch_rwmh_propose(int chains, int dims, const double* q, double* qp, const double* step_vec,
+                                const double* step_chain, double stepsize, const double* z_in,
+                                unsigned long long seed, long long chain_offset, long long kglob,
+                                cudaStream_t s);
+cudaError_t launch_rwmh_decide(const RwmhDecide& D, cudaStream_t s);
+
 // ---- launch_srcloc.cu ------------------------------------------------------------------
 bool srcloc_supported(int events, int stations);
 size_t srcloc_smem_bytes(const SrcLocDev& L);

@@ -2,6 +2,7 @@
 // the standalone prior / mass-matrix kernels.
 #define HMCB_FUSED_AUX_KERNELS
 #include "launch.cuh"
+#include "rwmh.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -99,6 +100,21 @@ cudaError_t launch_mass_elementwise(const DevTarget& T, int chains, int mode, co
                                     double* out, cudaStream_t s) {
   const size_t total = (size_t)chains * T.dims;
   mass_elementwise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(T, total, mode, in, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rwmh_propose(int chains, int dims, const double* q, double* qp, const double* step_vec,
+                                const double* step_chain, double stepsize, const double* z_in,
+                                unsigned long long seed, long long chain_offset, long long kglob,
+                                cudaStream_t s) {
+  const long long work = (long long)chains * ((dims + 1) / 2);
+  rwmh_propose_kernel<<<(unsigned)((work + 255) / 256), 256, 0, s>>>(chains, dims, q, qp, step_vec, step_chain,
+                                                                    stepsize, z_in, seed, chain_offset, kglob);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rwmh_decide(const RwmhDecide& D, cudaStream_t s) {
+  rwmh_decide_kernel<<<D.chains, 128, 0, s>>>(D);
   return cudaGetLastError();
 }
 

@@ -172,6 +172,15 @@ typedef struct hmcb_block {
 
 int hmcb_run_block(hmcb_engine *e, const hmcb_block *block, void *stream);
 
+/* A block of Random Walk Metropolis-Hastings proposals for all chains (RWMH._propose /
+ * _evaluate_acceptance, Samplers.py:1060-1086): proposed = current + (stepsize * step_vector) *
+ * normal, accepted iff exp(x - x') > u.  Uses the same hmcb_block (randomize_stepsize, u_step_in,
+ * out_p_prop and the traces are ignored; out_h0 / out_h1 receive the current / proposed misfit;
+ * autotuning as in Samplers.py:1029-1058).  step_vector: DEVICE [dims] per-coordinate factors
+ * (the reference's ndarray stepsize / _stepsize_non_scalar_part) or NULL. */
+int hmcb_run_block_rwmh(hmcb_engine *e, const hmcb_block *block, const double *step_vector,
+                        void *stream);
+
 /* Whole sampling call with HOST buffers: q0_host [C x d] initial models (pinned or
  * pageable), samples_host [(proposals/thinning) x C x (d+1)] output.  Copies run on
  * private streams and overlap with the kernels of the next block; returns after the

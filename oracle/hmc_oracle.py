@@ -428,3 +428,40 @@ def run_chains(tree, mass, *, q0, z, u_step, u_acc, **kw):
         else:
             out[key] = np.moveaxis(stacked, 0, 1)
     return out
+
+
+# ------------------------------------------------------------------------------ RWMH ----
+
+
+def run_chain_rwmh(tree, *, stepsize=1.0, step_vector=None, q0=None, proposals=1, draws=None,
+                   thinning=1, autotuning=False, target_acceptance_rate=0.65, learning_rate=0.75):
+    """Random Walk Metropolis-Hastings chain (Samplers.py:1060-1086, autotune :1029-1058).
+    ``stepsize`` scalar, ``step_vector`` (d,) per-coordinate factors or None (the reference's
+    ``_stepsize_non_scalar_part``)."""
+    d = tree["dims"]
+    q = np.zeros((d, 1)) if q0 is None else np.array(q0, dtype=np.float64).reshape(d, 1)
+    x = misfit(tree, q)
+    nonscalar = 1.0 if step_vector is None else _col(step_vector)
+    out = {"accept": [], "samples": [], "stepsizes": [], "x_prop": []}
+    for k in range(proposals):
+        out["stepsizes"].append(stepsize)
+        qp = q + stepsize * nonscalar * draws.normal(d)
+        xp = misfit(tree, qp)
+        with np.errstate(all="ignore"):
+            rate = np.exp(x - xp)
+        if autotuning:
+            weight = (k + 1) ** (-learning_rate)
+            r = 0 if np.isnan(rate) else rate
+            stepsize -= weight * (target_acceptance_rate - min(r, 1))
+            if stepsize <= 0:
+                stepsize = max(stepsize, 1e-18)
+        accepted = bool(rate > draws.accept_uniform())
+        if accepted:
+            q, x = qp.copy(), xp
+        out["accept"].append(accepted)
+        out["x_prop"].append(xp)
+        if k % thinning == 0:
+            out["samples"].append(np.concatenate([q[:, 0], [x]]))
+    res = {k_: np.array(v) for k_, v in out.items()}
+    res["final_stepsize"] = stepsize
+    return res

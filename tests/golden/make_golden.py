@@ -202,6 +202,53 @@ def autotuned_runs(hmclab, tmpdir):
     np.savez_compressed(os.path.join(HERE, "autotuned_runs.npz"), **out)
 
 
+RWMH_CASES = {   # name -> (stepsize kind, autotuning)
+    "normal_bounded": ("scalar", False),
+    "dense_premult_cfg1": ("vector", False),
+    "srcloc_fixed_v": ("scalar", True),
+    "sparse_laplace_lf": ("vector", True),
+}
+
+
+def rwmh_step(name, dims):
+    rng = np.random.default_rng(len(name))
+    base = {"normal_bounded": 0.4, "dense_premult_cfg1": 0.02, "srcloc_fixed_v": 0.05,
+            "sparse_laplace_lf": 0.03}[name]
+    return base, base * rng.uniform(0.5, 1.5, size=(dims, 1))
+
+
+def rwmh_runs(hmclab, tmpdir):
+    """Reference RWMH chains (Samplers.py:777-1102) with replayed draws."""
+    out = {}
+    for name, (kind, tune) in RWMH_CASES.items():
+        s = cases.SETTINGS[name]
+        inp = cases.make_inputs(name)
+        C, K, d = s["chains"], s["proposals"], int(inp["dims"])
+        post, _ = cases.build(name, inp, hmclab)
+        scalar, vector = rwmh_step(name, d)
+        samples = np.zeros((K, C, d + 1))
+        accepted = np.zeros(C, dtype=np.int64)
+        final = np.zeros(C)
+        for c in range(C):
+            sampler = hmclab.Samplers.RWMH(seed=0)
+            sampler.rng = ReplayRNG(inp["z"][:, c], inp["u_step"][:, c], inp["u_acc"][:, c])
+            fn = os.path.join(tmpdir, f"rwmh_{name}_{c}.npy")
+            with np.errstate(all="ignore"):
+                sampler.sample(fn, post, stepsize=scalar if kind == "scalar" else vector.copy(),
+                               initial_model=inp["q0"][c].copy(), proposals=K, autotuning=tune,
+                               overwrite_existing_file=True, disable_progressbar=True)
+            samples[:, c] = np.load(fn)
+            accepted[c] = sampler.accepted_proposals
+            final[c] = sampler.stepsize if tune else np.nan
+        out[f"{name}__samples"] = samples
+        out[f"{name}__accepted"] = accepted
+        out[f"{name}__final_stepsize"] = final
+        out[f"{name}__step_scalar"] = np.float64(scalar)
+        out[f"{name}__step_vector"] = vector
+        print("rwmh", name, kind, "autotune" if tune else "", "accepted", accepted, np.round(final, 4))
+    np.savez_compressed(os.path.join(HERE, "rwmh_runs.npz"), **out)
+
+
 def main():
     hmclab = import_reference()
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
@@ -211,10 +258,14 @@ def main():
         if "--autotune-only" in sys.argv:
             autotuned_runs(hmclab, tmpdir)
             return
+        if "--rwmh-only" in sys.argv:
+            rwmh_runs(hmclab, tmpdir)
+            return
         seeded_public_runs(hmclab, tmpdir)
         if "--seeded-only" in sys.argv:
             return
         autotuned_runs(hmclab, tmpdir)
+        rwmh_runs(hmclab, tmpdir)
         for name in cases.CASES:
             inp = cases.make_inputs(name)
             golden, post, mass = drive_reference(hmclab, name, inp, tmpdir)

@@ -232,3 +232,37 @@ def test_clear_target_allows_a_new_configuration_on_the_same_engine():
                                             a.ctypes.data_as(dp), 0, 3.0) != 0   # dims != 4 * events
     assert b"4*events" in lib.hmcb_last_error()
     assert lib.hmcb_destroy(h) == 0
+
+
+@pytest.mark.parametrize("name,kind,tune", [("normal_bounded", "scalar", False),
+                                            ("dense_premult_cfg1", "vector", False),
+                                            ("srcloc_fixed_v", "scalar", True),
+                                            ("sparse_laplace_lf", "vector", True)])
+def test_rwmh_chains_match_reference(name, kind, tune):
+    """hmcb_run_block_rwmh vs reference RWMH chains with the same replayed draws."""
+    import os
+
+    from helpers import GOLDEN_DIR
+
+    gold = np.load(os.path.join(GOLDEN_DIR, "rwmh_runs.npz"))
+    inp, _ = load_golden(name)
+    K, C, d = inp["z"].shape
+    eng, torch = _engine(name, inp, C)
+    q = _dev(torch, inp["q0"])
+    x = eng.misfit(q)
+    vector = _dev(torch, gold[f"{name}__step_vector"][:, 0]) if kind == "vector" else None
+    scalar = 1.0 if kind == "vector" else float(gold[f"{name}__step_scalar"])
+    samples = torch.zeros(K, C, d + 1, dtype=torch.float64, device="cuda")
+    acc = torch.zeros(C, dtype=torch.int32, device="cuda")
+    extra = {}
+    if tune:
+        extra = dict(stepsize_chain=torch.full((C,), scalar, dtype=torch.float64, device="cuda"),
+                     autotune=True, target_acceptance_rate=0.65, learning_rate=0.75)
+    eng.run_block_rwmh(q, x, K, stepsize=scalar, step_vector=vector, z=_dev(torch, inp["z"]),
+                       u_accept=_dev(torch, inp["u_acc"]), out_samples=samples, accepted_total=acc,
+                       **extra)
+    got, ref = samples.cpu().numpy(), gold[f"{name}__samples"]
+    assert np.array_equal(acc.cpu().numpy(), gold[f"{name}__accepted"])
+    assert rel_err(got, ref) < TOL
+    if tune:
+        assert rel_err(extra["stepsize_chain"].cpu().numpy(), gold[f"{name}__final_stepsize"]) < TOL

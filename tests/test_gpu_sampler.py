@@ -298,3 +298,29 @@ def test_sample_host_equals_device_blocks(builder, kw):
     assert np.array_equal(samples.numpy(), ref.cpu().numpy())
     assert np.array_equal(acc.numpy(), racc.cpu().numpy())
     assert np.array_equal(fq.numpy(), q.cpu().numpy()) and np.array_equal(fx.numpy(), x.cpu().numpy())
+
+
+def test_rwmh_sampler_statistics_and_format(tmp_path):
+    from hmclab_b200 import Distributions as D
+    from hmclab_b200.Samplers import RWMH
+    from hmclab_b200.Samples import Samples
+
+    d, C = 4, 512
+    var = np.array([[0.5], [1.0], [2.0], [4.0]])
+    post = D.Normal(np.zeros((d, 1)), var)
+    fn = str(tmp_path / "rw.npy")
+    sampler = RWMH(seed=2).sample(fn, post, stepsize=np.sqrt(var) * 1.2, proposals=600,
+                                  online_thinning=3, chains=C, block_proposals=90)
+    with Samples(fn) as s:
+        assert s.read_attribute("sampler") == "Random Walk Metropolis Hastings"
+        assert s.read_attribute("stepsize") == "ndarray"
+        per = int(s.read_attribute("samples_per_chain"))
+        x = np.stack([s.chain(c)[:-1, per // 3:] for c in range(C)])
+        rate = s.read_attribute("acceptance_rate")
+    assert 0.15 < rate < 0.7
+    assert np.all(np.abs(x.var(axis=(0, 2)) / var[:, 0] - 1) < 0.15)
+    tuned = RWMH(seed=2).sample(str(tmp_path / "rw2.npy"), post, stepsize=0.01, proposals=400, chains=64,
+                                autotuning=True)
+    assert tuned.stepsize.shape == (64,) and np.median(tuned.stepsize) > 0.05
+    with pytest.raises(AssertionError, match="wrong shape"):
+        RWMH().sample(str(tmp_path / "rw3.npy"), post, stepsize=np.ones((3, 1)), proposals=4)

@@ -76,3 +76,33 @@ def test_oracle_autotuning_reproduces_reference(name):
     known = ~np.isnan(ref_steps)       # the reference drops the last entry of its history
     assert rel_err(got["stepsizes"][known], ref_steps[known]) < TOL
     assert (gold[f"{name}__final_stepsize"] != s["stepsize"]).all()
+
+
+RWMH_CASES = {"normal_bounded": ("scalar", False), "dense_premult_cfg1": ("vector", False),
+              "srcloc_fixed_v": ("scalar", True), "sparse_laplace_lf": ("vector", True)}
+
+
+@pytest.mark.parametrize("name", list(RWMH_CASES))
+def test_oracle_rwmh_reproduces_reference(name):
+    """Reference RWMH chains with replayed draws (tests/golden/rwmh_runs.npz)."""
+    import os
+
+    from helpers import GOLDEN_DIR
+
+    gold = np.load(os.path.join(GOLDEN_DIR, "rwmh_runs.npz"))
+    kind, tune = RWMH_CASES[name]
+    inp, _ = load_golden(name)
+    post, _ = build_mirror(name, inp)
+    tree = describe(post)
+    K, C, d = inp["z"].shape
+    vector = gold[f"{name}__step_vector"][:, 0] if kind == "vector" else None
+    scalar = 1.0 if kind == "vector" else float(gold[f"{name}__step_scalar"])
+    for c in range(C):
+        draws = oracle.ReplayDraws(inp["z"][:, c], inp["u_step"][:, c], inp["u_acc"][:, c])
+        with np.errstate(all="ignore"):
+            got = oracle.run_chain_rwmh(tree, stepsize=scalar, step_vector=vector, q0=inp["q0"][c],
+                                        proposals=K, draws=draws, autotuning=tune)
+        assert rel_err(got["samples"], gold[f"{name}__samples"][:, c]) < TOL
+        assert got["accept"].sum() == gold[f"{name}__accepted"][c]
+        if tune:
+            assert rel_err(got["final_stepsize"], gold[f"{name}__final_stepsize"][c]) < TOL
