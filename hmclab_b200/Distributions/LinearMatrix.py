@@ -6,6 +6,7 @@ the CUDA engine are the ones the reference would multiply with:
 * dispatcher ``LinearMatrix``  -- hmclab/Distributions/LinearMatrix.py:15-135
 * dense G, scalar/vector variance  -- LinearMatrix.py:139-222
 * sparse G, scalar/vector variance -- LinearMatrix.py:309-440
+* dense G, dense data covariance (premultiplied form) -- LinearMatrix.py:226-305
 
 Inherited quirks (they are part of the contract):
 
@@ -66,16 +67,17 @@ class LinearMatrix(_AbstractDistribution):
             simple = False
         else:
             raise ValueError("Didn't understand the data covariance object.")
-        if not simple:
+        if not simple and not dense:
             raise NotImplementedError(
-                "Full data-covariance LinearMatrix variants (LinearMatrix.py:226-305, "
-                "444-519) are outside the batched B200 path."
+                "The sparse-G / sparse-covariance LinearMatrix variant (LinearMatrix.py:444-519, a "
+                "sparse LU solve per evaluation) is outside the batched B200 path."
             )
-        inner = (
-            _LinearMatrix_dense_forward_simple_covariance
-            if dense
-            else _LinearMatrix_sparse_forward_simple_covariance
-        )
+        if not simple:
+            inner = _LinearMatrix_dense_forward_dense_covariance
+        elif dense:
+            inner = _LinearMatrix_dense_forward_simple_covariance
+        else:
+            inner = _LinearMatrix_sparse_forward_simple_covariance
         self.Distribution = inner(G, d, data_covariance, **kwargs)
 
     @staticmethod
@@ -130,6 +132,33 @@ class _LinearMatrix_dense_forward_simple_covariance(_AbstractDistribution):
             del self.G, self.d, self.data_variance, self.data_sigma
         else:
             self.Gt = G.T
+
+
+class _LinearMatrix_dense_forward_dense_covariance(_AbstractDistribution):
+    """Dense G with a dense (N x N) data covariance (LinearMatrix.py:226-305).  In its
+    premultiplied form (the default when N > dimensions) it reduces to the same GtG / Gtd0 /
+    dtd arithmetic as the simple-covariance class; the direct form (two N x N products per
+    evaluation) is not lowered."""
+
+    def __init__(self, G, d, data_covariance, dtype=_numpy.single, premultiplication=None):
+        self.name = "dense linear forward model, dense data covariance"
+        self.dimensions = int(G.shape[1])
+        self.G = G.astype(dtype)
+        self.d = d.astype(dtype)
+        self.data_covariance = data_covariance.astype(dtype)
+        if premultiplication is not None:
+            self.premultiplication = premultiplication
+        else:
+            self.premultiplication = self.G.shape[0] > self.G.shape[1]
+        if not self.premultiplication:
+            raise NotImplementedError(
+                "LinearMatrix with a dense data covariance is lowered in its premultiplied form "
+                "only (pass premultiplication=True).")
+        self.invcov = _numpy.linalg.inv(self.data_covariance)
+        self.GtG = self.G.T @ self.invcov @ self.G
+        self.Gtd0 = G.T @ self.invcov @ self.d
+        self.dtd = (self.d.T @ self.invcov @ self.d).item()
+        del self.G, self.d, self.data_covariance
 
 
 class _LinearMatrix_sparse_forward_simple_covariance(_AbstractDistribution):

@@ -91,8 +91,12 @@ def describe(dist) -> Dict[str, Any]:
         # wrapper adds its own misfit_bounds on top of the inner ones (LinearMatrix.py:114-116)
         inner["wrapper_lb"], inner["wrapper_ub"] = lb, ub
         return inner
-    elif cls == "_LinearMatrix_dense_forward_simple_covariance":
+    elif cls in ("_LinearMatrix_dense_forward_simple_covariance",
+                 "_LinearMatrix_dense_forward_dense_covariance"):
         node.update(kind="linear_dense", premult=bool(dist.premultiplication))
+        if cls.endswith("dense_covariance") and not dist.premultiplication:
+            raise NotImplementedError(
+                "LinearMatrix with a dense data covariance is lowered in its premultiplied form only.")
         if dist.premultiplication:
             node.update(
                 GtG=np.ascontiguousarray(dist.GtG, dtype=np.float64),

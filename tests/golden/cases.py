@@ -40,6 +40,8 @@ SETTINGS = {
     "composite_top": _settings("lf", 6, 0.4, True, 6, 8),
     # bounded Normal on its own: reflection and out-of-bounds rejection
     "normal_bounded": _settings("lf", 5, 0.9, True, 6, 8),
+    # dense (N x N) data covariance, premultiplied form (LinearMatrix.py:226-305)
+    "dense_fullcov_premult": _settings("3s", 2, 0.35, True, 4, 4),
 }
 
 CASES = tuple(SETTINGS)
@@ -64,6 +66,12 @@ def make_inputs(name: str) -> dict:
         inp.update(G=rng.normal(size=(90, dims)) / np.sqrt(90), d=rng.normal(size=(90, 1)),
                    var=rng.uniform(0.5, 1.5, size=(90, 1)),
                    mass=rng.uniform(0.5, 2.0, size=(dims, 1)))
+    elif name == "dense_fullcov_premult":
+        dims = 24
+        N = 40
+        A = rng.normal(size=(N, N)) / np.sqrt(N)
+        inp.update(G=rng.normal(size=(N, dims)) / np.sqrt(N), d=rng.normal(size=(N, 1)),
+                   cov=A @ A.T + 0.5 * np.eye(N), mass=rng.uniform(0.5, 2.0, size=(dims, 1)))
     elif name == "dense_direct_f64":
         dims = 33
         inp.update(G=rng.normal(size=(21, dims)), d=rng.normal(size=(21, 1)),
@@ -154,6 +162,10 @@ def build(name: str, inp: dict, ns):
     elif name == "dense_premult_vecvar_3s":
         post = D.BayesRule([D.Normal(np.zeros((dims, 1)), 4.0),
                             D.LinearMatrix(cp("G"), cp("d"), cp("var"))])
+        mass = M.Diagonal(cp("mass"))
+    elif name == "dense_fullcov_premult":
+        post = D.BayesRule([D.Normal(np.zeros((dims, 1)), 2.0),
+                            D.LinearMatrix(cp("G"), cp("d"), cp("cov"))])
         mass = M.Diagonal(cp("mass"))
     elif name == "dense_direct_f64":
         inner = D.LinearMatrix.__module__

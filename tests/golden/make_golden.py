@@ -261,12 +261,16 @@ def main():
         if "--rwmh-only" in sys.argv:
             rwmh_runs(hmclab, tmpdir)
             return
-        seeded_public_runs(hmclab, tmpdir)
-        if "--seeded-only" in sys.argv:
-            return
-        autotuned_runs(hmclab, tmpdir)
-        rwmh_runs(hmclab, tmpdir)
+        if not any(a.startswith("--only=") for a in sys.argv):
+            seeded_public_runs(hmclab, tmpdir)
+            if "--seeded-only" in sys.argv:
+                return
+            autotuned_runs(hmclab, tmpdir)
+            rwmh_runs(hmclab, tmpdir)
+        only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
         for name in cases.CASES:
+            if only and name not in only:
+                continue
             inp = cases.make_inputs(name)
             golden, post, mass = drive_reference(hmclab, name, inp, tmpdir)
             if name in ("dense_premult_cfg1", "srcloc_fixed_v"):

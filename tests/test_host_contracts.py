@@ -59,8 +59,10 @@ def test_linear_matrix_dtype_quirks_are_inherited():
         D.LinearMatrix(G[:5], d, 2.0)
     with pytest.raises(ValueError, match="covariance"):
         D.LinearMatrix(G, d, np.ones((3, 1)))
+    full = D.LinearMatrix(G, d, np.eye(7) * 2.0)            # dense covariance, premultiplied
+    assert np.allclose(full.Distribution.GtG, inner.GtG, rtol=1e-6)
     with pytest.raises(NotImplementedError):
-        D.LinearMatrix(G, d, np.eye(7))
+        D.LinearMatrix(G, d, np.eye(7), premultiplication=False)
     sparse = D.LinearMatrix(sp.csr_matrix(G), d, 0.5, premultiplication=False)
     node = describe(sparse)
     assert node["kind"] == "linear_csr" and node["indices"].dtype == np.int32
