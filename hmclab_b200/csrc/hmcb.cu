@@ -175,6 +175,15 @@ void free_device(hmcb_engine* e) {
   for (void* p : e->allocs) cudaFree(p);
   e->allocs.clear();
   e->finalized = false;
+  // every pointer into the freed pool is reset; hmcb_finalize / first use allocates again
+  e->fused_dense = false;
+  e->rw_qp = e->rw_x1 = nullptr;
+  e->dA = e->dAt = e->dA_rowmajor = e->dvec = e->dvar = e->dsigma = nullptr;
+  e->q_cur = e->q_w[0] = e->q_w[1] = e->p_w = e->R = nullptr;
+  e->eps = e->uacc = e->k0part = e->k1part = e->upart = e->lpart = nullptr;
+  e->flags[0] = e->flags[1] = e->flags[2] = nullptr;
+  e->accbuf = nullptr;
+  e->N = 0;
 }
 
 int check_csr(const HostCsr& m, const char* what) {

@@ -96,3 +96,40 @@ def test_unsupported_objects_are_refused_by_name():
     assert lik.dimensions == 9
     with pytest.raises(NotImplementedError, match="Only one coupled likelihood"):
         flatten(describe(D.BayesRule([lik, lik])))
+
+
+def _trees_equal(a, b, path="root"):
+    assert type(a) is type(b) or (np.isscalar(a) and np.isscalar(b)), path
+    if isinstance(a, dict):
+        assert sorted(a) == sorted(b), path
+        for k in a:
+            _trees_equal(a[k], b[k], f"{path}.{k}")
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _trees_equal(x, y, f"{path}[{i}]")
+    elif isinstance(a, np.ndarray):
+        assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True), path
+    elif isinstance(a, float) and np.isnan(a):
+        assert np.isnan(b), path
+    else:
+        assert a == b, path
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/hmclab"), reason="reference not mounted")
+def test_genuine_reference_objects_lower_to_the_same_plan():
+    """A posterior built with the reference's own classes is accepted as is: the lowering reads
+    it by class and attribute name and yields exactly what the mirror classes yield."""
+    import hmclab_b200
+    import cases
+    from _reference_shim import import_reference
+    from hmclab_b200.Samplers import _is_distribution, _is_mass_matrix
+
+    hmclab = import_reference()
+    for name in cases.CASES:
+        inp = cases.make_inputs(name)
+        ref_post, ref_mass = cases.build(name, inp, hmclab)
+        our_post, our_mass = cases.build(name, inp, hmclab_b200)
+        assert _is_distribution(ref_post) and _is_mass_matrix(ref_mass)
+        _trees_equal(describe(ref_post), describe(our_post), name)
+        _trees_equal(describe_mass(ref_mass), describe_mass(our_mass), name)
