@@ -11,9 +11,9 @@ Ctrl-C, so an interrupted run leaves a valid file exactly like the reference
 (:684-704).
 
 ``autotuning=True`` adapts one step size per chain on the device with the reference's
-update rule (Samplers.py:1494-1522).  Not offered on this path (it raises):
-``diagnostic_mode`` (the per-function timers make no sense for fused kernels; use
-``get_diagnostics()`` for block-level timings).
+update rule (Samplers.py:1494-1522).  ``diagnostic_mode=True`` prints block-level time shares
+at the end of the run (the reference's per-function timers have no counterpart once the calls
+are fused into kernels); ``get_diagnostics()`` returns the same numbers.
 """
 from __future__ import annotations
 
@@ -163,10 +163,9 @@ class HMC:
             "The amount of proposals (`proposals`) needs to be a multiple of the online "
             "thinning (`online_thinning`) number, to prevent sample wastage.")
         self.proposals_after_thinning = proposals // online_thinning
-        if diagnostic_mode:
-            raise NotImplementedError(
-                "diagnostic_mode wraps per-call Python functions in timers (Samplers.py:1386-1417); "
-                "the batched engine fuses those calls into kernels. Use get_diagnostics().")
+        # Samplers.py:449-460, 1386-1417 time individual Python calls; here the calls are fused
+        # into kernels, so diagnostic_mode reports the block-level shares instead (at close)
+        self.diagnostic_mode = bool(diagnostic_mode)
 
         # initial models: (d,), (d,1) -> one chain (or broadcast to `chains`); [C, d] -> C chains
         if initial_model is None:
@@ -469,6 +468,17 @@ class HMC:
         self.samples.write_attribute("runtime_seconds",
                                      (self.end_time - self.start_time).total_seconds())
         self.samples.close()
+        if getattr(self, "diagnostic_mode", False):
+            total = max((self.end_time - self.start_time).total_seconds(), 1e-12)
+            t = self._timings
+            print("Detailed statistics:")
+            print(f"Total runtime: {total:.2f} seconds")
+            print("{:<34} {:<20}".format("Component", "percentage of time"))
+            for label, key in (("device blocks (kernels, waited)", "device_blocks_s"),
+                               ("host sample writes", "host_write_s")):
+                print("{:<34} {:<20.2f}".format(label, 100 * t.get(key, 0.0) / total))
+            print("{:<34} {:<20}".format("kernel launches", self.engine.launch_count))
+            print("{:<34} {:<20}".format("engine path", self.engine.path))
 
     # ------------------------------------------------------------------ reporting ----
     def load_results(self, burn_in: int = 0) -> _numpy.ndarray:

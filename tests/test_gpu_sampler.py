@@ -324,3 +324,13 @@ def test_rwmh_sampler_statistics_and_format(tmp_path):
     assert tuned.stepsize.shape == (64,) and np.median(tuned.stepsize) > 0.05
     with pytest.raises(AssertionError, match="wrong shape"):
         RWMH().sample(str(tmp_path / "rw3.npy"), post, stepsize=np.ones((3, 1)), proposals=4)
+
+
+def test_diagnostic_mode_reports_block_shares(tmp_path, capsys):
+    from hmclab_b200 import Distributions as D
+    from hmclab_b200.Samplers import HMC
+
+    HMC(seed=1).sample(str(tmp_path / "diag.npy"), D.Normal(np.zeros((3, 1)), 1.0), proposals=20,
+                       chains=4, diagnostic_mode=True)
+    out = capsys.readouterr().out
+    assert "Detailed statistics" in out and "device blocks" in out and "fused_priors" in out

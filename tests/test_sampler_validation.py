@@ -64,8 +64,6 @@ def test_sampler_specific_arguments(tmp_path, target):
         _call(tmp_path, target, max_time=-1.0)
     with pytest.raises(AssertionError, match="learning rate"):
         _call(tmp_path, target, autotuning=True, learning_rate=0.4)
-    with pytest.raises(NotImplementedError):
-        _call(tmp_path, target, diagnostic_mode=True)
 
 
 def test_existing_file_is_not_overwritten(tmp_path, target):
