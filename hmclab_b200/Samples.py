@@ -25,9 +25,9 @@ import numpy as _numpy
 
 def _have_h5py():
     try:
-        import h5py  # noqa: F401
+        import h5py
 
-        return True
+        return isinstance(getattr(h5py, "__version__", None), str)   # not an import stub
     except Exception:
         return False
 

@@ -82,11 +82,10 @@ def test_error_behaviour(tmp_path):
 
 
 def test_hdf5_needs_h5py_and_says_so(tmp_path):
-    try:
-        import h5py  # noqa: F401
+    from hmclab_b200.Samples import _have_h5py
+
+    if _have_h5py():
         pytest.skip("h5py present")
-    except ImportError:
-        pass
     with pytest.raises(ImportError, match="h5py"):
         Samples(str(tmp_path / "run.h5"), mode="w")
 
