@@ -111,3 +111,38 @@ class SourceLocation3D(_AbstractDistribution):
             infer_velocity=infer_velocity,
             medium_velocity=None if infer_velocity else v,
         )
+
+
+class SourceLocation2D(_AbstractDistribution):
+    """Mirror of ``hmclab.Distributions.SourceLocation2D`` (SourceLocation.py:11-366):
+    parameters interleaved ``x, z, T`` per event, optionally followed by one medium velocity.
+    Evaluated by the same kernel as the 3-D problem (stations and sources in the plane y = 0)."""
+
+    name = "Earthquake source location in 2D"
+
+    def __init__(self, receiver_array_x, receiver_array_z, observed_data, data_std,
+                 infer_velocity: bool = True, medium_velocity=None):
+        self.receiver_array_x = _row(receiver_array_x)
+        self.receiver_array_z = _row(receiver_array_z)
+        self.number_of_stations = int(self.receiver_array_x.size)
+        assert self.receiver_array_z.size == self.number_of_stations, (
+            "Receiver coordinate arrays differ in length.")
+        self.infer_velocity = bool(infer_velocity)
+        self.medium_velocity = None
+        if not self.infer_velocity:
+            assert medium_velocity is not None
+            self.medium_velocity = medium_velocity
+        observed_data = _numpy.array(observed_data, dtype=_numpy.float64)
+        assert observed_data.size % self.number_of_stations == 0
+        self.number_of_events = int(observed_data.size // self.number_of_stations)
+        shape = (self.number_of_events, self.number_of_stations)
+        self.observed_data = _events_by_stations(observed_data, shape, "observed data")
+        if type(data_std) is float:
+            data_std = _numpy.ones(shape) * data_std
+        data_std = _numpy.array(data_std, dtype=_numpy.float64)
+        self.data_std = _events_by_stations(data_std, shape, "data uncertainty")
+        self.dimensions = self.number_of_events * 3 + int(self.infer_velocity)
+
+    @staticmethod
+    def forward(x, z, T, v, receiver_array_x, receiver_array_z):
+        return T + ((x - receiver_array_x) ** 2.0 + (z - receiver_array_z) ** 2.0) ** 0.5 / v

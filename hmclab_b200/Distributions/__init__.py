@@ -14,7 +14,7 @@ from hmclab_b200.Distributions.base import (
     _AbstractDistribution,
 )
 from hmclab_b200.Distributions.LinearMatrix import LinearMatrix
-from hmclab_b200.Distributions.SourceLocation import SourceLocation3D
+from hmclab_b200.Distributions.SourceLocation import SourceLocation2D, SourceLocation3D
 
 __all__ = [
     "_AbstractDistribution",
@@ -25,5 +25,6 @@ __all__ = [
     "AdditiveDistribution",
     "BayesRule",
     "LinearMatrix",
+    "SourceLocation2D",
     "SourceLocation3D",
 ]

@@ -75,6 +75,9 @@ SIGNATURES = {
     "hmcb_set_likelihood_srcloc3d": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _c_double_p,
                                                _c_double_p, _c_double_p, _c_double_p,
                                                _c_double_p, C.c_int, C.c_double]),
+    "hmcb_set_likelihood_srcloc2d": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _c_double_p,
+                                               _c_double_p, _c_double_p, _c_double_p, C.c_int,
+                                               C.c_double]),
     "hmcb_finalize": (C.c_int, [C.c_void_p]),
     "hmcb_path": (C.c_int, [C.c_void_p]),
     "hmcb_grads_per_proposal": (C.c_int64, [C.c_void_p]),
@@ -225,6 +228,12 @@ class Engine:
                 h, int(lik["events"]), int(lik["stations"]), _dp(_f64(lik["rx"])),
                 _dp(_f64(lik["ry"])), _dp(_f64(lik["rz"])), _dp(_f64(lik["tobs"])),
                 _dp(_f64(lik["std"])), int(bool(lik["infer_velocity"])), v))
+        elif kind == "srcloc2d":
+            v = float(lik["velocity"]) if not lik["infer_velocity"] else 0.0
+            self._ok(lib.hmcb_set_likelihood_srcloc2d(
+                h, int(lik["events"]), int(lik["stations"]), _dp(_f64(lik["rx"])),
+                _dp(_f64(lik["rz"])), _dp(_f64(lik["tobs"])), _dp(_f64(lik["std"])),
+                int(bool(lik["infer_velocity"])), v))
         else:
             raise NotImplementedError(kind)
 

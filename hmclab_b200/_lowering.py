@@ -18,7 +18,7 @@ from typing import Any, Dict, List, Optional
 
 import numpy as np
 
-LIKELIHOOD_KINDS = ("linear_dense", "linear_csr", "srcloc3d")
+LIKELIHOOD_KINDS = ("linear_dense", "linear_csr", "srcloc3d", "srcloc2d")
 
 
 def _vec(x, n: int, what: str) -> np.ndarray:
@@ -161,12 +161,29 @@ def describe(dist) -> Dict[str, Any]:
                 else float(np.asarray(dist.medium_velocity).reshape(-1)[0])
             ),
         )
+    elif cls == "SourceLocation2D":
+        E, S = int(dist.number_of_events), int(dist.number_of_stations)
+        node.update(
+            kind="srcloc2d",
+            events=E,
+            stations=S,
+            rx=_vec(dist.receiver_array_x, S, "receiver_array_x"),
+            rz=_vec(dist.receiver_array_z, S, "receiver_array_z"),
+            tobs=np.ascontiguousarray(dist.observed_data, dtype=np.float64).reshape(E, S),
+            std=np.ascontiguousarray(dist.data_std, dtype=np.float64).reshape(E, S),
+            infer_velocity=bool(dist.infer_velocity),
+            velocity=(
+                float("nan")
+                if dist.infer_velocity
+                else float(np.asarray(dist.medium_velocity).reshape(-1)[0])
+            ),
+        )
     else:
         raise NotImplementedError(
             f"Distribution type `{cls}` is not on the batched B200 path "
             "(supported: Normal (diagonal), Laplace, Uniform, CompositeDistribution, "
             "AdditiveDistribution/BayesRule, LinearMatrix with scalar/vector variance, "
-            "SourceLocation3D)."
+            "SourceLocation3D, SourceLocation2D)."
         )
     return node
 

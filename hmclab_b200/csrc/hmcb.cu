@@ -84,6 +84,7 @@ struct hmcb_engine {
   HostCsr csr, csr_t;
   // srcloc
   int64_t events = 0, stations = 0;
+  int srcloc_np = 4;  // 4: SourceLocation3D, 3: SourceLocation2D
   int infer_velocity = 0;
   double velocity = 0.0;
   std::vector<double> h_rx, h_ry, h_rz, h_tobs, h_std;
@@ -651,7 +652,28 @@ int hmcb_set_likelihood_srcloc3d(hmcb_engine* e, int64_t events, int64_t station
              "hmcb_set_likelihood_srcloc3d: events x stations exceeds the kernel's shared-memory staging");
   e->events = events; e->stations = stations; e->infer_velocity = infer_velocity ? 1 : 0;
   e->velocity = velocity;
+  e->srcloc_np = 4;
   copy_vec(e->h_rx, rx, stations); copy_vec(e->h_ry, ry, stations); copy_vec(e->h_rz, rz, stations);
+  copy_vec(e->h_tobs, tobs, events * stations); copy_vec(e->h_std, std, events * stations);
+  e->lik = LK_SRCLOC;
+  return 0;
+}
+
+int hmcb_set_likelihood_srcloc2d(hmcb_engine* e, int64_t events, int64_t stations, const double* rx,
+                                 const double* rz, const double* tobs, const double* std,
+                                 int infer_velocity, double velocity) {
+  HMCB_CHECK(e && rx && rz && tobs && std, "hmcb_set_likelihood_srcloc2d: NULL argument");
+  HMCB_CHECK(!e->finalized && e->lik == LK_NONE, "one likelihood per engine, set before hmcb_finalize");
+  HMCB_CHECK(events > 0 && stations > 0, "hmcb_set_likelihood_srcloc2d: bad sizes");
+  HMCB_CHECK(e->d == 3 * events + (infer_velocity ? 1 : 0),
+             "hmcb_set_likelihood_srcloc2d: dims must be 3*events (+1 when the velocity is inferred)");
+  HMCB_CHECK(srcloc_supported((int)events, (int)stations),
+             "hmcb_set_likelihood_srcloc2d: events x stations exceeds the kernel's shared-memory staging");
+  e->events = events; e->stations = stations; e->infer_velocity = infer_velocity ? 1 : 0;
+  e->velocity = velocity;
+  e->srcloc_np = 3;
+  copy_vec(e->h_rx, rx, stations); copy_vec(e->h_rz, rz, stations);
+  e->h_ry.assign((size_t)stations, 0.0);   // the 2-D problem is the 3-D one in the plane y = 0
   copy_vec(e->h_tobs, tobs, events * stations); copy_vec(e->h_std, std, events * stations);
   e->lik = LK_SRCLOC;
   return 0;
@@ -727,6 +749,7 @@ int hmcb_finalize(hmcb_engine* e) {
     e->path = HMCB_PATH_FUSED_SRCLOC;
     SrcLocDev& L = e->L;
     L.events = (int)e->events; L.stations = (int)e->stations; L.infer_velocity = e->infer_velocity;
+    L.np = e->srcloc_np;
     L.velocity = e->velocity;
     if (dev_upload(e, e->h_rx, &L.rx) || dev_upload(e, e->h_ry, &L.ry) || dev_upload(e, e->h_rz, &L.rz) ||
         dev_upload(e, e->h_tobs, &L.tobs) || dev_upload(e, e->h_std, &L.std))

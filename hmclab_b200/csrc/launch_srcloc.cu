@@ -33,19 +33,24 @@ bool srcloc_supported(int events, int stations) {
   return sizeof(double) * srcloc_smem_doubles(events, stations) <= 200 * 1024;
 }
 
-cudaError_t launch_fused_srcloc_lpe1(const FusedArgs&, const SrcLocDev&, int, cudaStream_t);
-cudaError_t launch_fused_srcloc_lpe2(const FusedArgs&, const SrcLocDev&, int, cudaStream_t);
-cudaError_t launch_fused_srcloc_lpe4(const FusedArgs&, const SrcLocDev&, int, cudaStream_t);
-cudaError_t launch_srcloc_eval_lpe1(const DevTarget&, const SrcLocDev&, int, int, const double*, double*, int, cudaStream_t);
-cudaError_t launch_srcloc_eval_lpe2(const DevTarget&, const SrcLocDev&, int, int, const double*, double*, int, cudaStream_t);
-cudaError_t launch_srcloc_eval_lpe4(const DevTarget&, const SrcLocDev&, int, int, const double*, double*, int, cudaStream_t);
+#define HMCB_DECLARE(L_, N_)                                                                              \
+  cudaError_t launch_fused_srcloc_lpe##L_##_np##N_(const FusedArgs&, const SrcLocDev&, int, cudaStream_t); \
+  cudaError_t launch_srcloc_eval_lpe##L_##_np##N_(const DevTarget&, const SrcLocDev&, int, int,            \
+                                                  const double*, double*, int, cudaStream_t);
+HMCB_DECLARE(1, 3) HMCB_DECLARE(2, 3) HMCB_DECLARE(4, 3)
+HMCB_DECLARE(1, 4) HMCB_DECLARE(2, 4) HMCB_DECLARE(4, 4)
+#undef HMCB_DECLARE
 
 cudaError_t launch_fused_srcloc(const FusedArgs& A, const SrcLocDev& L, cudaStream_t s) {
   const int epad = pow2_ceil(L.events);
-  switch (srcloc_lpe(L.stations)) {
-    case 1: return launch_fused_srcloc_lpe1(A, L, epad, s);
-    case 2: return launch_fused_srcloc_lpe2(A, L, epad, s);
-    case 4: return launch_fused_srcloc_lpe4(A, L, epad, s);
+  const int key = srcloc_lpe(L.stations) * 10 + L.np;
+  switch (key) {
+    case 13: return launch_fused_srcloc_lpe1_np3(A, L, epad, s);
+    case 23: return launch_fused_srcloc_lpe2_np3(A, L, epad, s);
+    case 43: return launch_fused_srcloc_lpe4_np3(A, L, epad, s);
+    case 14: return launch_fused_srcloc_lpe1_np4(A, L, epad, s);
+    case 24: return launch_fused_srcloc_lpe2_np4(A, L, epad, s);
+    case 44: return launch_fused_srcloc_lpe4_np4(A, L, epad, s);
   }
   return cudaErrorInvalidConfiguration;
 }
@@ -53,10 +58,14 @@ cudaError_t launch_fused_srcloc(const FusedArgs& A, const SrcLocDev& L, cudaStre
 cudaError_t launch_srcloc_eval(const DevTarget& T, const SrcLocDev& L, int chains, int mode,
                                const double* q, double* out, cudaStream_t s) {
   const int epad = pow2_ceil(L.events);
-  switch (srcloc_lpe(L.stations)) {
-    case 1: return launch_srcloc_eval_lpe1(T, L, chains, mode, q, out, epad, s);
-    case 2: return launch_srcloc_eval_lpe2(T, L, chains, mode, q, out, epad, s);
-    case 4: return launch_srcloc_eval_lpe4(T, L, chains, mode, q, out, epad, s);
+  const int key = srcloc_lpe(L.stations) * 10 + L.np;
+  switch (key) {
+    case 13: return launch_srcloc_eval_lpe1_np3(T, L, chains, mode, q, out, epad, s);
+    case 23: return launch_srcloc_eval_lpe2_np3(T, L, chains, mode, q, out, epad, s);
+    case 43: return launch_srcloc_eval_lpe4_np3(T, L, chains, mode, q, out, epad, s);
+    case 14: return launch_srcloc_eval_lpe1_np4(T, L, chains, mode, q, out, epad, s);
+    case 24: return launch_srcloc_eval_lpe2_np4(T, L, chains, mode, q, out, epad, s);
+    case 44: return launch_srcloc_eval_lpe4_np4(T, L, chains, mode, q, out, epad, s);
   }
   return cudaErrorInvalidConfiguration;
 }

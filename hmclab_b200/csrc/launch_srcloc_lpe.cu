@@ -1,12 +1,13 @@
 // launch_srcloc_lpe.cu -- instantiations of the SourceLocation3D kernels for one value of
-// LPE (lanes per event); compiled once per -DHMCB_LPE={1,2,4}.
+// LPE (lanes per event); compiled once per -DHMCB_LPE={1,2,4} x -DHMCB_NP={3,4}.
 #include "launch.cuh"
 
-#ifndef HMCB_LPE
-#error "compile with -DHMCB_LPE=<lanes per event>"
+#if !defined(HMCB_LPE) || !defined(HMCB_NP)
+#error "compile with -DHMCB_LPE=<lanes per event> -DHMCB_NP=<parameters per event: 3 or 4>"
 #endif
 #define HMCB_CAT2(a, b) a##b
 #define HMCB_CAT(a, b) HMCB_CAT2(a, b)
+#define HMCB_CAT4(a, b, c, d) HMCB_CAT(HMCB_CAT(a, b), HMCB_CAT(c, d))
 
 namespace hmcb {
 
@@ -16,11 +17,11 @@ static cudaError_t launch_fs(const FusedArgs& A, const SrcLocDev& L, cudaStream_
   constexpr int CPB = BLOCK / TPC;
   const size_t smem = srcloc_smem_bytes(L);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(hmc_fused_srcloc_kernel<TPC, LPE>,
+    cudaError_t e = cudaFuncSetAttribute(hmc_fused_srcloc_kernel<TPC, LPE, HMCB_NP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  hmc_fused_srcloc_kernel<TPC, LPE><<<(A.chains + CPB - 1) / CPB, BLOCK, smem, s>>>(A, L);
+  hmc_fused_srcloc_kernel<TPC, LPE, HMCB_NP><<<(A.chains + CPB - 1) / CPB, BLOCK, smem, s>>>(A, L);
   return cudaGetLastError();
 }
 
@@ -31,11 +32,11 @@ static cudaError_t launch_ev(const DevTarget& T, const SrcLocDev& L, int chains,
   constexpr int CPB = BLOCK / TPC;
   const size_t smem = srcloc_smem_bytes(L);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(srcloc_eval_kernel<TPC, LPE>,
+    cudaError_t e = cudaFuncSetAttribute(srcloc_eval_kernel<TPC, LPE, HMCB_NP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  srcloc_eval_kernel<TPC, LPE><<<(chains + CPB - 1) / CPB, BLOCK, smem, s>>>(T, L, chains, mode, q, out);
+  srcloc_eval_kernel<TPC, LPE, HMCB_NP><<<(chains + CPB - 1) / CPB, BLOCK, smem, s>>>(T, L, chains, mode, q, out);
   return cudaGetLastError();
 }
 
@@ -53,14 +54,14 @@ static cudaError_t launch_ev(const DevTarget& T, const SrcLocDev& L, int chains,
   }                                                   \
   return cudaErrorInvalidConfiguration;
 
-cudaError_t HMCB_CAT(launch_fused_srcloc_lpe, HMCB_LPE)(const FusedArgs& A, const SrcLocDev& L,
+cudaError_t HMCB_CAT4(launch_fused_srcloc_lpe, HMCB_LPE, _np, HMCB_NP)(const FusedArgs& A, const SrcLocDev& L,
                                                          int epad, cudaStream_t s) {
 #define HMCB_CALL(TPC_) launch_fs<TPC_, HMCB_LPE>(A, L, s)
   HMCB_EPAD_CASES(HMCB_CALL)
 #undef HMCB_CALL
 }
 
-cudaError_t HMCB_CAT(launch_srcloc_eval_lpe, HMCB_LPE)(const DevTarget& T, const SrcLocDev& L,
+cudaError_t HMCB_CAT4(launch_srcloc_eval_lpe, HMCB_LPE, _np, HMCB_NP)(const DevTarget& T, const SrcLocDev& L,
                                                         int chains, int mode, const double* q,
                                                         double* out, int epad, cudaStream_t s) {
 #define HMCB_CALL(TPC_) launch_ev<TPC_, HMCB_LPE>(T, L, chains, mode, q, out, s)

@@ -18,7 +18,8 @@ namespace hmcb {
 constexpr int SRCLOC_SMALL_BLOCK = 64;
 
 struct SrcLocDev {
-  int events, stations, infer_velocity, pad;
+  int events, stations, infer_velocity;
+  int np;  // parameters per event: 4 = (x, y, z, T) SourceLocation3D, 3 = (x, z, T) SourceLocation2D
   double velocity;
   const double* rx; const double* ry; const double* rz;  // [S]
   const double* tobs; const double* std;                 // [E x S]
@@ -77,8 +78,9 @@ __device__ __forceinline__ double rsqrt_or_zero(double d2) {
 template <int LPE>
 __device__ __forceinline__ void srcloc_gradient_partial(const SrcLocShared& M, int S, int e, int sub,
                                                         double x, double y, double z, double T,
-                                                        double inv_v, bool want_gv, double& gx,
-                                                        double& gy, double& gz, double& gT, double& gv) {
+                                                        double inv_v, bool want_gv, bool nansum,
+                                                        double& gx, double& gy, double& gz, double& gT,
+                                                        double& gv) {
   gx = gy = gz = gT = gv = 0.0;
   const double neg_inv_vv = -__dmul_rn(inv_v, inv_v);
   const double2* pick = M.pick + e * S;
@@ -101,8 +103,11 @@ __device__ __forceinline__ void srcloc_gradient_partial(const SrcLocShared& M, i
   }
   // A trajectory that has already diverged (non-finite coordinates) makes every term NaN;
   // nansum returns 0 for such a sum, and the bounds term then decides (+inf).
-  gx = nan_to_zero(gx); gy = nan_to_zero(gy); gz = nan_to_zero(gz); gT = nan_to_zero(gT);
-  gv = nan_to_zero(gv);
+  // (the 2-D reference sums with a plain sum, SourceLocation.py:133-136: NaN propagates there)
+  if (nansum) {
+    gx = nan_to_zero(gx); gy = nan_to_zero(gy); gz = nan_to_zero(gz); gT = nan_to_zero(gT);
+    gv = nan_to_zero(gv);
+  }
 }
 
 // Partial sum of squared standardised residuals of event e (SourceLocation.py:482-493).
@@ -133,7 +138,7 @@ __device__ __forceinline__ double group_sum(double v) {
 }
 
 // Per-thread view of one chain: 4 event parameters (+ the shared velocity).
-template <int TPC, int LPE>
+template <int TPC, int LPE, int NP = 4>
 struct SrcLocLane {
   int e, sub, c;
   bool has_event, lead, vlead, live;
@@ -151,52 +156,62 @@ struct SrcLocLane {
     vlead = t == 0;                // the lane that accounts for / writes the velocity
     if (!has_event) e = E - 1;
   }
+  // external coordinate of internal slot i (x, y, z, T); the 2-D variant has no y (-1)
+  // slot i carries a parameter (compile-time once the loops over i are unrolled)
+  __device__ __forceinline__ static constexpr bool active(int i) { return NP == 4 || i != 1; }
+  __device__ __forceinline__ int coord(int i) const {
+    return NP == 4 ? 4 * e + i : (i == 1 ? -1 : 3 * e + (i == 0 ? 0 : i - 1));
+  }
 };
 
 // Gradient of the full target at the lane's coordinates: prior terms + travel-time term.
 // g[0..3] for (x,y,z,T) of the lane's event, gvel for the velocity coordinate.
-template <int TPC, int LPE>
+template <int TPC, int LPE, int NP>
 __device__ __forceinline__ void srcloc_total_gradient(const DevTarget& T, const SrcLocDev& L,
                                                       const SrcLocShared& M,
-                                                      const SrcLocLane<TPC, LPE>& ln,
+                                                      const SrcLocLane<TPC, LPE, NP>& ln,
                                                       const ChainReduce<TPC>& red, const double* q,
                                                       double qv, unsigned oob, double* g, double& gvel) {
   const double inv_v = __ddiv_rn(1.0, L.infer_velocity ? qv : L.velocity);
   double gx, gy, gz, gT, gv;
   srcloc_gradient_partial<LPE>(M, L.stations, ln.e, ln.sub, q[0], q[1], q[2], q[3], inv_v,
-                               L.infer_velocity != 0, gx, gy, gz, gT, gv);
+                               L.infer_velocity != 0, NP == 4, gx, gy, gz, gT, gv);
   gx = group_sum<LPE>(gx); gy = group_sum<LPE>(gy); gz = group_sum<LPE>(gz); gT = group_sum<LPE>(gT);
-  const int j0 = 4 * ln.e;
-  g[0] = __dadd_rn(prior_gradient(T, j0 + 0, q[0], oob), gx);
-  g[1] = __dadd_rn(prior_gradient(T, j0 + 1, q[1], oob), gy);
-  g[2] = __dadd_rn(prior_gradient(T, j0 + 2, q[2], oob), gz);
-  g[3] = __dadd_rn(prior_gradient(T, j0 + 3, q[3], oob), gT);
+  const double lik[4] = {gx, gy, gz, gT};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = ln.coord(i);
+    g[i] = ln.active(i) ? __dadd_rn(prior_gradient(T, j, q[i], oob), lik[i]) : 0.0;
+  }
   gvel = 0.0;
   if (L.infer_velocity) {
     double a = ln.has_event ? gv : 0.0, b = 0.0, c2 = 0.0;
     red.sum3(a, b, c2);
-    gvel = __dadd_rn(prior_gradient(T, 4 * L.events, qv, oob), a);
+    gvel = __dadd_rn(prior_gradient(T, NP * L.events, qv, oob), a);
   }
 }
 
-template <int TPC, int LPE>
+template <int TPC, int LPE, int NP>
 __device__ __forceinline__ unsigned srcloc_violations(const DevTarget& T, const SrcLocDev& L,
-                                                      const SrcLocLane<TPC, LPE>& ln,
+                                                      const SrcLocLane<TPC, LPE, NP>& ln,
                                                       const ChainReduce<TPC>& red, const double* q,
                                                       double qv) {
   unsigned m = 0;
   if (T.n_checks) {
     if (ln.lead) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) m |= bound_violations(T, 4 * ln.e + i, q[i]);
+      for (int i = 0; i < 4; ++i) {
+        const int j = ln.coord(i);
+        if (ln.active(i)) m |= bound_violations(T, j, q[i]);
+      }
     }
-    if (L.infer_velocity && ln.vlead) m |= bound_violations(T, 4 * L.events, qv);
+    if (L.infer_velocity && ln.vlead) m |= bound_violations(T, NP * L.events, qv);
     m = red.any_bits(m);
   }
   return m;
 }
 
-template <int TPC, int LPE>
+template <int TPC, int LPE, int NP>
 __global__ void __launch_bounds__((TPC <= 32 ? SRCLOC_SMALL_BLOCK : TPC), (TPC <= 32 ? 8 : (TPC <= 256 ? 2 : 1)))
 hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
   extern __shared__ __align__(16) double dyn_smem[];
@@ -205,17 +220,21 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
   const SrcLocShared M = srcloc_stage(L, dyn_smem);
   const DevTarget& T = A.T;
   const int d = T.dims, E = L.events;
-  SrcLocLane<TPC, LPE> ln;
+  SrcLocLane<TPC, LPE, NP> ln;
   ln.init(A.chains, E);
   const int c = ln.c;
   const size_t row = (size_t)c * d, C = (size_t)A.chains;
-  const int j0 = 4 * ln.e, jv = 4 * E;
+  int cj[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cj[i] = ln.coord(i);
+  constexpr int kNP = NP;
+  const int jv = kNP * E;
   const bool inferv = L.infer_velocity != 0;
   const bool grad_checks = T.grad_check_mask != 0u;
 
   double qc[4], q[4], p[4], qcv = 0.0, qv = 0.0, pv = 0.0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) qc[i] = A.q[row + j0 + i];
+  for (int i = 0; i < 4; ++i) qc[i] = ln.active(i) ? A.q[row + cj[i]] : 0.0;
   if (inferv) qcv = A.q[row + jv];
   double x = A.x[c];
   int accepted = 0;
@@ -246,19 +265,37 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
     if (A.z_in) {
       const double* zr = A.z_in + kc * d;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) p[i] = zr[j0 + i];
+      for (int i = 0; i < 4; ++i) p[i] = ln.active(i) ? zr[cj[i]] : 0.0;
       if (inferv) pv = zr[jv];
     } else {
-      normal_pair(A.seed, cg, kg, (uint32_t)(2 * ln.e), p[0], p[1]);
-      normal_pair(A.seed, cg, kg, (uint32_t)(2 * ln.e + 1), p[2], p[3]);
-      if (inferv) { double unused; normal_pair(A.seed, cg, kg, (uint32_t)(2 * E), pv, unused); }
+      // normals are keyed by coordinate pair (coordinates 2m, 2m+1 come from pair m)
+      if constexpr (NP == 4) {
+        normal_pair(A.seed, cg, kg, (uint32_t)(2 * ln.e), p[0], p[1]);
+        normal_pair(A.seed, cg, kg, (uint32_t)(2 * ln.e + 1), p[2], p[3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          p[i] = 0.0;
+          if (ln.active(i)) {
+            double z0, z1;
+            normal_pair(A.seed, cg, kg, (uint32_t)(cj[i] >> 1), z0, z1);
+            p[i] = (cj[i] & 1) ? z1 : z0;
+          }
+        }
+      }
+      if (inferv) {
+        double z0, z1;
+        normal_pair(A.seed, cg, kg, (uint32_t)(jv >> 1), z0, z1);
+        pv = (jv & 1) ? z1 : z0;
+      }
     }
     double k0 = 0.0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       q[i] = qc[i];
-      if (T.sqrtm) p[i] = __dmul_rn(__ldg(T.sqrtm + j0 + i), p[i]);
-      if (ln.lead) k0 = __dadd_rn(k0, kinetic_term(T, j0 + i, p[i]));
+      if (!ln.active(i)) continue;
+      if (T.sqrtm) p[i] = __dmul_rn(__ldg(T.sqrtm + cj[i]), p[i]);
+      if (ln.lead) k0 = __dadd_rn(k0, kinetic_term(T, cj[i], p[i]));
     }
     if (inferv) {
       qv = qcv;
@@ -269,25 +306,28 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
     int gi = 0;
     auto mom = [&](double cb) {
       unsigned oob = 0;
-      if (grad_checks) oob = srcloc_violations<TPC, LPE>(T, L, ln, red, q, qv);
+      if (grad_checks) oob = srcloc_violations<TPC, LPE, NP>(T, L, ln, red, q, qv);
       double g[4], gvel;
-      srcloc_total_gradient<TPC, LPE>(T, L, M, ln, red, q, qv, oob, g, gvel);
+      srcloc_total_gradient<TPC, LPE, NP>(T, L, M, ln, red, q, qv, oob, g, gvel);
       if (A.trace_q && ln.live) {
         const size_t o = (((size_t)kb * A.S.grads_per_proposal + gi) * C + c) * d;
         if (ln.lead) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { A.trace_q[o + j0 + i] = q[i]; A.trace_g[o + j0 + i] = g[i]; }
+          for (int i = 0; i < 4; ++i)
+            if (ln.active(i)) { A.trace_q[o + cj[i]] = q[i]; A.trace_g[o + cj[i]] = g[i]; }
         }
         if (inferv && ln.vlead) { A.trace_q[o + jv] = qv; A.trace_g[o + jv] = gvel; }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) momentum_update(cb, g[i], p[i]);
+      for (int i = 0; i < 4; ++i)
+        if (ln.active(i)) momentum_update(cb, g[i], p[i]);
       if (inferv) momentum_update(cb, gvel, pv);
       ++gi;
     };
     auto pos = [&](double ca) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) position_update(T, j0 + i, ca, q[i], p[i]);
+      for (int i = 0; i < 4; ++i)
+        if (ln.active(i)) position_update(T, cj[i], ca, q[i], p[i]);
       if (inferv) position_update(T, jv, ca, qv, pv);
     };
     run_schedule(A.S, eps, mom, pos);
@@ -297,8 +337,9 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
     if (ln.lead) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        k1 = __dadd_rn(k1, kinetic_term(T, j0 + i, p[i]));
-        u1 = __dadd_rn(u1, prior_misfit(T, j0 + i, q[i]));
+        if (!ln.active(i)) continue;
+        k1 = __dadd_rn(k1, kinetic_term(T, cj[i], p[i]));
+        u1 = __dadd_rn(u1, prior_misfit(T, cj[i], q[i]));
       }
     }
     if (inferv && ln.vlead) {
@@ -311,7 +352,7 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
     red.sum3(k0, k1, u1);
     double z0 = 0.0, z1 = 0.0;
     red.sum3(lik, z0, z1);
-    const unsigned oob = srcloc_violations<TPC, LPE>(T, L, ln, red, q, qv);
+    const unsigned oob = srcloc_violations<TPC, LPE, NP>(T, L, ln, red, q, qv);
     // BayesRule order: prior misfit first, then the likelihood, then the bounds
     double x1 = __dadd_rn(__dadd_rn(u1, T.const_sum), __dmul_rn(0.5, lik));
     if (oob) x1 = __dadd_rn(x1, CUDART_INF);
@@ -324,7 +365,8 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
       if (A.out_q_prop) {
         if (ln.lead) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { A.out_q_prop[kc * d + j0 + i] = q[i]; A.out_p_prop[kc * d + j0 + i] = p[i]; }
+          for (int i = 0; i < 4; ++i)
+            if (ln.active(i)) { A.out_q_prop[kc * d + cj[i]] = q[i]; A.out_p_prop[kc * d + cj[i]] = p[i]; }
         }
         if (inferv && ln.vlead) { A.out_q_prop[kc * d + jv] = qv; A.out_p_prop[kc * d + jv] = pv; }
       }
@@ -345,7 +387,8 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
       const size_t srow = (store_row * C + c) * (size_t)(d + 1);
       if (ln.lead) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) A.out_samples[srow + j0 + i] = qc[i];
+        for (int i = 0; i < 4; ++i)
+          if (ln.active(i)) A.out_samples[srow + cj[i]] = qc[i];
       }
       if (ln.vlead) {
         if (inferv) A.out_samples[srow + jv] = qcv;
@@ -358,7 +401,8 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
   if (ln.live) {
     if (ln.lead) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) A.q[row + j0 + i] = qc[i];
+      for (int i = 0; i < 4; ++i)
+        if (ln.active(i)) A.q[row + cj[i]] = qc[i];
     }
     if (ln.vlead) {
       if (inferv) A.q[row + jv] = qcv;
@@ -370,7 +414,7 @@ hmc_fused_srcloc_kernel(const FusedArgs A, const SrcLocDev L) {
 }
 
 // mode 0: x[c] = misfit ; mode 1: g[c,:] = gradient
-template <int TPC, int LPE>
+template <int TPC, int LPE, int NP>
 __global__ void __launch_bounds__((TPC <= 32 ? SRCLOC_SMALL_BLOCK : TPC))
 srcloc_eval_kernel(const DevTarget T, const SrcLocDev L, int chains, int mode,
                    const double* __restrict__ qin, double* __restrict__ out) {
@@ -379,19 +423,24 @@ srcloc_eval_kernel(const DevTarget T, const SrcLocDev L, int chains, int mode,
   const ChainReduce<TPC> red{scratch};
   const SrcLocShared M = srcloc_stage(L, dyn_smem);
   const int d = T.dims, E = L.events;
-  SrcLocLane<TPC, LPE> ln;
+  SrcLocLane<TPC, LPE, NP> ln;
   ln.init(chains, E);
   const size_t row = (size_t)ln.c * d;
-  const int j0 = 4 * ln.e, jv = 4 * E;
+  int cj[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cj[i] = ln.coord(i);
+  constexpr int kNP = NP;
+  const int jv = kNP * E;
   double q[4], qv = 0.0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) q[i] = qin[row + j0 + i];
+  for (int i = 0; i < 4; ++i) q[i] = ln.active(i) ? qin[row + cj[i]] : 0.0;
   if (L.infer_velocity) qv = qin[row + jv];
-  const unsigned oob = srcloc_violations<TPC, LPE>(T, L, ln, red, q, qv);
+  const unsigned oob = srcloc_violations<TPC, LPE, NP>(T, L, ln, red, q, qv);
   if (mode == 0) {
     double u1 = 0.0, z0 = 0.0, z1 = 0.0;
     if (ln.lead)
-      for (int i = 0; i < 4; ++i) u1 = __dadd_rn(u1, prior_misfit(T, j0 + i, q[i]));
+      for (int i = 0; i < 4; ++i)
+        if (ln.active(i)) u1 = __dadd_rn(u1, prior_misfit(T, cj[i], q[i]));
     if (L.infer_velocity && ln.vlead) u1 = __dadd_rn(u1, prior_misfit(T, jv, qv));
     const double inv_vel = __ddiv_rn(1.0, L.infer_velocity ? qv : L.velocity);
     double lik = srcloc_misfit_partial<LPE>(M, L.stations, ln.e, ln.sub, q[0], q[1], q[2], q[3], inv_vel);
@@ -403,10 +452,11 @@ srcloc_eval_kernel(const DevTarget T, const SrcLocDev L, int chains, int mode,
     if (ln.live && ln.vlead) out[ln.c] = x1;
   } else {
     double g[4], gvel;
-    srcloc_total_gradient<TPC, LPE>(T, L, M, ln, red, q, qv, oob, g, gvel);
+    srcloc_total_gradient<TPC, LPE, NP>(T, L, M, ln, red, q, qv, oob, g, gvel);
     if (ln.live) {
       if (ln.lead)
-        for (int i = 0; i < 4; ++i) out[row + j0 + i] = g[i];
+        for (int i = 0; i < 4; ++i)
+          if (ln.active(i)) out[row + cj[i]] = g[i];
       if (L.infer_velocity && ln.vlead) out[row + jv] = gvel;
     }
   }

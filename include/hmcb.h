@@ -110,6 +110,13 @@ int hmcb_set_likelihood_srcloc3d(hmcb_engine *e, int64_t events, int64_t station
                                  const double *tobs, const double *std, int infer_velocity,
                                  double velocity);
 
+/* SourceLocation2D (SourceLocation.py:100-158): parameters (x, z, T) per event (+ velocity);
+ * stations rx / rz [S]; dims must be 3*E (+1).  Missing picks (NaN) are skipped in misfit and
+ * gradient alike (the reference's 2-D gradient uses a plain sum and would return NaN). */
+int hmcb_set_likelihood_srcloc2d(hmcb_engine *e, int64_t events, int64_t stations,
+                                 const double *rx, const double *rz, const double *tobs,
+                                 const double *std, int infer_velocity, double velocity);
+
 /* Validate the configuration, upload constants, choose the execution path and allocate
  * workspaces.  Must be called after the setters and before any evaluation. */
 int hmcb_finalize(hmcb_engine *e);

@@ -88,6 +88,11 @@ def misfit(node, m: np.ndarray) -> float:
             res = (G @ m - _col(node["d"])) / _col(node["sigma"])
             inner = own + (0.5 * np.linalg.norm(res) ** 2).item()
         return inner + wrapper  # LinearMatrix.py:114-116
+    if kind == "srcloc2d":
+        # SourceLocation.py:100-109
+        x, z, T, v = _split_events_2d(node, m)
+        dist = ((x - node["rx"][None, :]) ** 2.0 + (z - node["rz"][None, :]) ** 2.0) ** 0.5
+        return own + 0.5 * np.nansum(((node["tobs"] - (T + dist / v)) / node["std"]) ** 2)
     if kind == "srcloc3d":
         # SourceLocation.py:482-493
         x, y, z, T, v = _split_events(node, m)
@@ -131,6 +136,21 @@ def gradient(node, m: np.ndarray) -> np.ndarray:
             return _matrix(node, "GtG") @ m - _col(node["Gtd0"])
         G, Gt = _matrix(node, "G"), _matrix(node, "Gt")
         return Gt @ ((G @ m - _col(node["d"])) / _col(node["var"]))
+    if kind == "srcloc2d":
+        # SourceLocation.py:111-158 (plain sums: no missing picks in the pinned cases)
+        x, z, T, v = _split_events_2d(node, m)
+        dx = x - node["rx"][None, :]
+        dz = z - node["rz"][None, :]
+        d = (dx**2.0 + dz**2.0) ** 0.5
+        w = ((T + d / v) - node["tobs"]) / (node["std"] ** 2)
+        g = np.zeros_like(m)
+        stop = 3 * node["events"]
+        g[0:stop:3, 0] = np.sum(w * (dx / (v * d)), axis=1)
+        g[1:stop:3, 0] = np.sum(w * (dz / (v * d)), axis=1)
+        g[2:stop:3, 0] = np.sum(w * np.ones_like(dx), axis=1)
+        if node["infer_velocity"]:
+            g[-1, 0] = np.sum(w * (-d / (v * v)))
+        return g
     if kind == "srcloc3d":
         # SourceLocation.py:495-540
         x, y, z, T, v = _split_events(node, m)
@@ -159,6 +179,13 @@ def _split_events(node, m):
     x, y, z, T = (m[i:stop:4] for i in range(4))  # each (E,1); SourceLocation.py:697-713
     v = m[-1] if node["infer_velocity"] else node["velocity"]
     return x, y, z, T, v
+
+
+def _split_events_2d(node, m):
+    stop = 3 * node["events"]
+    x, z, T = (m[i:stop:3] for i in range(3))
+    v = m[-1] if node["infer_velocity"] else node["velocity"]
+    return x, z, T, v
 
 
 _MATRIX_CACHE = {}

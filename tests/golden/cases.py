@@ -40,6 +40,8 @@ SETTINGS = {
     "composite_top": _settings("lf", 6, 0.4, True, 6, 8),
     # bounded Normal on its own: reflection and out-of-bounds rejection
     "normal_bounded": _settings("lf", 5, 0.9, True, 6, 8),
+    # 2-D source location with inferred velocity, Uniform box in BayesRule, Diagonal mass
+    "srcloc2d_infer_v": _settings("lf", 6, 0.03, True, 5, 6),
     # dense (N x N) data covariance, premultiplied form (LinearMatrix.py:226-305)
     "dense_fullcov_premult": _settings("3s", 2, 0.35, True, 4, 4),
 }
@@ -66,6 +68,19 @@ def make_inputs(name: str) -> dict:
         inp.update(G=rng.normal(size=(90, dims)) / np.sqrt(90), d=rng.normal(size=(90, 1)),
                    var=rng.uniform(0.5, 1.5, size=(90, 1)),
                    mass=rng.uniform(0.5, 2.0, size=(dims, 1)))
+    elif name == "srcloc2d_infer_v":
+        E, S = 3, 6
+        dims = 3 * E + 1
+        sx = rng.uniform(-10, 30, size=(1, S))
+        sz = np.zeros((1, S))
+        ex, ez, eT = rng.uniform(0, 20, size=(E, 1)), rng.uniform(1, 10, size=(E, 1)), rng.uniform(0, 10, size=(E, 1))
+        tt = eT + ((ex - sx) ** 2 + (ez - sz) ** 2) ** 0.5 / 3.0
+        lo = np.vstack([np.tile(np.array([[-5.0], [0.0], [-2.0]]), (E, 1)), [[1.5]]])
+        hi = np.vstack([np.tile(np.array([[25.0], [12.0], [12.0]]), (E, 1)), [[5.0]]])
+        inp.update(sx=sx, sz=sz, tobs=tt + 0.1 * rng.normal(size=tt.shape),
+                   std=rng.uniform(0.08, 0.2, size=tt.shape), lo=lo, hi=hi,
+                   mass=rng.uniform(0.5, 2.0, size=(dims, 1)),
+                   truth=np.hstack([ex, ez, eT]).reshape(-1, 1))
     elif name == "dense_fullcov_premult":
         dims = 24
         N = 40
@@ -127,7 +142,7 @@ def make_inputs(name: str) -> dict:
     inp["dims"] = np.int64(dims)
     if name.startswith("srcloc"):
         base = inp["truth"][:, 0]
-        if name == "srcloc_infer_v":
+        if name in ("srcloc_infer_v", "srcloc2d_infer_v"):
             base = np.concatenate([base, [3.0]])
         q0 = base[None, :] + 0.3 * rng.normal(size=(C, dims))
         q0 = np.clip(q0, inp["lo"][:, 0] + 1e-3, inp["hi"][:, 0] - 1e-3)
@@ -162,6 +177,10 @@ def build(name: str, inp: dict, ns):
     elif name == "dense_premult_vecvar_3s":
         post = D.BayesRule([D.Normal(np.zeros((dims, 1)), 4.0),
                             D.LinearMatrix(cp("G"), cp("d"), cp("var"))])
+        mass = M.Diagonal(cp("mass"))
+    elif name == "srcloc2d_infer_v":
+        lik = D.SourceLocation2D(cp("sx"), cp("sz"), cp("tobs"), cp("std"), infer_velocity=True)
+        post = D.BayesRule([D.Uniform(cp("lo"), cp("hi")), lik])
         mass = M.Diagonal(cp("mass"))
     elif name == "dense_fullcov_premult":
         post = D.BayesRule([D.Normal(np.zeros((dims, 1)), 2.0),
