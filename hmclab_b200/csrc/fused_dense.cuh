@@ -25,6 +25,7 @@ constexpr int FD_THREADS = 256;       // 8 warps, warp w owns rows [16 w, 16 w +
 constexpr int FD_LDA = FD_M + 4;      // 132 doubles: conflict-free A fragments
 constexpr int FD_LDB = FD_BN + 4;     // 36 doubles: conflict-free B fragments
 constexpr int FD_RED = 5;             // k0, k1, prior misfit, likelihood misfit, bound flags
+// (+ 256 B static: the gradient's bound flags)
 constexpr size_t FD_SMEM_BYTES =
     sizeof(double) * ((size_t)FD_M * FD_LDA + (size_t)FD_M * FD_LDB + (size_t)FD_RED * 8 * FD_BN + 4 * FD_BN) +
     sizeof(int) * FD_BN;
@@ -47,6 +48,7 @@ hmc_fused_dense_kernel(const FusedDenseArgs D) {
   double* x_s = uacc_s + FD_BN;                  // current misfit
   double* x1_s = x_s + FD_BN;                    // proposed misfit (scratch)
   int* acc_s = reinterpret_cast<int*>(x1_s + FD_BN);
+  __shared__ unsigned gflags[2][FD_BN];          // per-chain bound violations seen by the gradient
 
   const FusedArgs& A = D.F;
   const DevTarget& T = A.T;
@@ -86,6 +88,13 @@ hmc_fused_dense_kernel(const FusedDenseArgs D) {
   }
   const bool has_mass = T.invm != nullptr;
   const bool has_refl = T.refl_lb != nullptr || T.refl_ub != nullptr;
+  const bool grad_checks = T.grad_check_mask != 0u;
+  unsigned cover[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    cover[i] = (grad_checks && row_ok[i]) ? ((unsigned)T.c_cover[r[i]] & T.grad_check_mask) : 0u;
+  if (tid < 2 * FD_BN) gflags[tid / FD_BN][tid % FD_BN] = 0u;
+  int gbuf = 0;
 
   double qc[2][4][2], q[2][4][2], p[2][4][2];
 #pragma unroll
@@ -241,9 +250,30 @@ hmc_fused_dense_kernel(const FusedDenseArgs D) {
     auto mom = [&](double b_mult) {
       __syncthreads();           // previous product has finished reading Bs
       store_positions(q);
+      if (grad_checks) {
+        // misfit_bounds of priors / containers adds +inf to the gradient of every coordinate of
+        // a violated check's range (base.py:361-374, 564-570): per-chain flags through shared memory
+        if (tid < FD_BN) gflags[gbuf ^ 1][tid] = 0u;   // the buffer of the next evaluation
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            unsigned m = 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              if (row_ok[i]) m |= bound_violations(T, r[i], q[i][j][h]);
+            if (m) atomicOr(&gflags[gbuf][col(j, h)], m);
+          }
+      }
       __syncthreads();
       double y[2][4][2];
       gemm(y);
+      unsigned oob[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) oob[j][h] = grad_checks ? gflags[gbuf][col(j, h)] : 0u;
+      gbuf ^= 1;
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -251,7 +281,8 @@ hmc_fused_dense_kernel(const FusedDenseArgs D) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const double lik = __dsub_rn(y[i][j][h], gtd[i]);
-            const double pg = kind[i] ? __dadd_rn(0.0, term_gradient(kind[i], ta[i], tb[i], q[i][j][h])) : 0.0;
+            double pg = kind[i] ? __dadd_rn(0.0, term_gradient(kind[i], ta[i], tb[i], q[i][j][h])) : 0.0;
+            if (oob[j][h] & cover[i]) pg = __dadd_rn(pg, CUDART_INF);
             const double g = __dadd_rn(pg, lik);
             if (A.trace_q && row_ok[i] && chain_ok(j, h)) {
               const size_t o = (((size_t)kb * A.S.grads_per_proposal + gi) * C + (c0 + col(j, h))) * d + r[i];

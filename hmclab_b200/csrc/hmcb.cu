@@ -813,7 +813,7 @@ int hmcb_finalize(hmcb_engine* e) {
     // small premultiplied dense models: the whole block of proposals runs in one kernel with
     // GtG resident in shared memory (the staged workspaces still serve hmcb_misfit/gradient)
     e->fused_dense = e->lik == LK_DENSE_PREMULT && e->dpad == 128 && T.n_terms <= 1 &&
-                     T.grad_check_mask == 0u && !std::getenv("HMCB_FORCE_STAGED");
+                     !std::getenv("HMCB_FORCE_STAGED");
     // the host copies of the big operands are no longer needed
     std::vector<double>().swap(e->h_A);
     std::vector<double>().swap(e->h_At);

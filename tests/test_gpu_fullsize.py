@@ -91,7 +91,8 @@ def test_config1_shape_vs_oracle():
     assert eng.path == "fused_dense"
 
 
-def test_fused_dense_kernel_equals_staged_pipeline():
+@pytest.mark.parametrize("prior", ["laplace", "uniform_box", "bounded_normal"])
+def test_fused_dense_kernel_equals_staged_pipeline(prior):
     """Small premultiplied dense models: the whole-proposal tensor-core kernel and the staged
     multi-launch pipeline are independent implementations; same device random streams, same
     chains (also with thinning, two blocks, a 4-stage integrator and a diagonal mass)."""
@@ -106,11 +107,17 @@ def test_fused_dense_kernel_equals_staged_pipeline():
     G = rng.normal(size=(data, dims)) / np.sqrt(data)
     dvec = G @ rng.normal(size=(dims, 1)) + 0.3 * rng.normal(size=(data, 1))
     var = rng.uniform(0.5, 1.5, size=(data, 1))
-    post = D.BayesRule([D.Laplace(np.zeros((dims, 1)), np.full((dims, 1), 2.0)),
-                        D.LinearMatrix(G, dvec, var)])
+    if prior == "laplace":
+        pr = D.Laplace(np.zeros((dims, 1)), np.full((dims, 1), 2.0))
+    elif prior == "uniform_box":      # reflection on the box + bound checks visible to the gradient
+        pr = D.Uniform(np.full((dims, 1), -1.5), np.full((dims, 1), 1.5))
+    else:
+        pr = D.Normal(np.zeros((dims, 1)), 1.0, lower_bounds=np.full((dims, 1), -2.0),
+                      upper_bounds=np.full((dims, 1), 2.5))
+    post = D.BayesRule([pr, D.LinearMatrix(G, dvec, var)])
     mass = M.Diagonal(rng.uniform(0.5, 2.0, size=(dims, 1)))
     plan, mplan = flatten(describe(post)), describe_mass(mass)
-    q0 = rng.normal(size=(C, dims))
+    q0 = np.clip(rng.normal(size=(C, dims)), -1.4, 1.4)
     results = {}
     for label, force in (("fused", None), ("staged", "1")):
         if force:
@@ -132,7 +139,7 @@ def test_fused_dense_kernel_equals_staged_pipeline():
             rows.append(buf.cpu().numpy())
         results[label] = (np.concatenate(rows), q.cpu().numpy(), x.cpu().numpy(), acc.cpu().numpy())
     f, s = results["fused"], results["staged"]
-    assert np.array_equal(f[3], s[3]) and 0.1 < f[3].mean() / 12 < 0.999
+    assert np.array_equal(f[3], s[3]) and 0.05 < f[3].mean() / 12 < 0.999
     assert rel_err(f[0], s[0]) < 1e-11 and rel_err(f[1], s[1]) < 1e-11 and rel_err(f[2], s[2]) < 1e-11
 
 
