@@ -388,6 +388,18 @@ def main():
                     "kernel": {"fused_dense": "hmc_fused_dense_kernel (one launch per step)"}.get(
                         eng.path, "dmma_gemm_kernel / csr_spmm_kernel (whole step time attributed)"),
                     "algorithmic_flops_per_grad_eval": flops, "peak_source": src}
+        if "nnz" in w.extra:
+            # SpMM path: also the HBM view of the same step, from the
+            # algorithmic bytes 16 (d + N) + 24 nnz / C per gradient evaluation and chain
+            n_data = w.extra.get("data", w.extra.get("rays", 0))
+            abytes = 16.0 * (w.dims + n_data) + 24.0 * w.extra["nnz"] / w.chains
+            gbs = abytes * value / world / 1e9
+            roofline["kernel"] = "csr_spmm_strip_kernel (two launches per gradient evaluation; whole step time attributed)"
+            roofline["hbm"] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                               "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_grad_eval": abytes}
+            roofline["note"] = ("fp64 FMA work (4 nnz flop per gradient evaluation) against the measured DGEMM "
+                                "peak; the kernel itself is bound by the shared-memory data pipe "
+                                "(one 8-byte gather per FMA), see DESIGN.md")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

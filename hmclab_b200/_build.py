@@ -33,7 +33,7 @@ NVCC_FLAGS = [
 # (source, object suffix, extra defines)
 UNITS = (
     [("hmcb.cu", "", []), ("launch_fused.cu", "", []), ("launch_srcloc.cu", "", []),
-     ("launch_staged.cu", "", []), ("launch_fused_dense.cu", "", [])]
+     ("launch_staged.cu", "", []), ("launch_spmm.cu", "", []), ("launch_fused_dense.cu", "", [])]
     + [("launch_fused_ppt.cu", f"_{p}", [f"-DHMCB_PPT={p}"]) for p in (1, 2, 4)]
     + [("launch_srcloc_lpe.cu", f"_{l}_{n}", [f"-DHMCB_LPE={l}", f"-DHMCB_NP={n}"])
        for l in (1, 2, 4) for n in (3, 4)]
@@ -60,6 +60,27 @@ def _source_digest() -> str:
     return h.hexdigest()
 
 
+def _unit_digest(src: str, defines) -> str:
+    """Hash of a translation unit: its source, the closure of its local #include files, flags."""
+    import re
+    seen, todo = set(), [os.path.join(CSRC, src)]
+    while todo:
+        path = os.path.normpath(todo.pop())
+        if path in seen or not os.path.isfile(path):
+            continue
+        seen.add(path)
+        with open(path) as f:
+            for inc in re.findall(r'^\s*#include\s+"([^"]+)"', f.read(), flags=re.M):
+                todo.append(os.path.join(os.path.dirname(path), inc))
+    h = hashlib.sha256()
+    for path in sorted(seen):
+        h.update(path.encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(list(NVCC_FLAGS) + list(defines)).encode())
+    return h.hexdigest()
+
+
 def is_current() -> bool:
     stamp = LIB_PATH + ".digest"
     if not (os.path.exists(LIB_PATH) and os.path.exists(stamp)):
@@ -79,6 +100,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     def compile_unit(unit):
         src, suffix, defines = unit
         obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + suffix + ".o")
+        digest, stamp = _unit_digest(src, defines), obj + ".digest"
+        if not force and os.path.exists(obj) and os.path.exists(stamp):
+            with open(stamp) as f:
+                if f.read().strip() == digest:
+                    return obj
         cmd = [nvcc, *NVCC_FLAGS, *defines, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -87,6 +113,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed for {src}{suffix}:\n{res.stdout}\n{res.stderr}")
         if verbose:
             sys.stderr.write(res.stderr)
+        with open(stamp, "w") as f:
+            f.write(digest)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 4)) as pool:

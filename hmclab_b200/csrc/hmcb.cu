@@ -105,6 +105,8 @@ struct hmcb_engine {
   double *dA_rowmajor = nullptr;  // [128 x 128] GtG for the fused small-dense kernel
   double *dA = nullptr, *dAt = nullptr, *dvec = nullptr, *dvar = nullptr, *dsigma = nullptr;
   CsrDev csr_dev{}, csr_t_dev{};
+  StripDev strip_dev{}, strip_t_dev{};  // shared-memory staged SpMM tables (spmm_strip.cuh)
+  bool use_strips = false;
   double *q_cur = nullptr, *q_w[2] = {nullptr, nullptr}, *p_w = nullptr, *R = nullptr;
   double *eps = nullptr, *uacc = nullptr, *k0part = nullptr, *k1part = nullptr, *upart = nullptr,
          *lpart = nullptr;
@@ -252,6 +254,123 @@ int upload_csr(hmcb_engine* e, const HostCsr& m, CsrDev* out) {
   return 0;
 }
 
+int env_int(const char* name, int fallback) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : fallback;
+}
+
+// Tables of the shared-memory staged SpMM (spmm_strip.cuh): per row chunk the columns are cut
+// greedily into strips of at most kb columns / emax nonzeros; per (chunk, strip) the nonzeros of
+// the chunk's rows inside the strip are stored row by row with their [begin, end) pairs.
+// Rows are sorted by column and duplicate entries summed first (scipy allows both).
+int upload_csr_strips(hmcb_engine* e, const HostCsr& m, const SpmmShape& shape, int kb, int emax,
+                      int stages, StripDev* out) {
+  const int S = 32 * shape.cpl, RB = shape.warps * shape.rw;
+  const int64_t rows = m.rows, cols = m.cols;
+  std::vector<int32_t> ip(rows + 1, 0), ix;
+  std::vector<double> dv;
+  ix.reserve(m.nnz); dv.reserve(m.nnz);
+  {
+    std::vector<std::pair<int32_t, double>> row;
+    for (int64_t i = 0; i < rows; ++i) {
+      row.clear();
+      for (int32_t k = m.indptr[i]; k < m.indptr[i + 1]; ++k) row.emplace_back(m.indices[k], m.data[k]);
+      std::stable_sort(row.begin(), row.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+      for (size_t k = 0; k < row.size(); ++k) {
+        if (k && row[k].first == row[k - 1].first) dv.back() += row[k].second;
+        else { ix.push_back(row[k].first); dv.push_back(row[k].second); }
+      }
+      ip[i + 1] = (int32_t)ix.size();
+    }
+  }
+  const int chunks = (int)((rows + RB - 1) / RB);
+  const int W = shape.warps, RW = shape.rw, hdr = (W + 3) / 4;   // header slots (4 ints each)
+  std::vector<SpmmStrip> strips;
+  std::vector<int32_t> strip_ptr(chunks + 1, 0);
+  std::vector<SpmmEntry> ent;
+  ent.reserve(ix.size() + ix.size() / 2);
+  const int budget = emax - hdr - W;   // slots left for nonzeros: header and one sentinel per warp
+  // strips per chunk: column c belongs to strip c % T (local index c / T); T grows until the
+  // fullest (chunk, strip) group fits in the slot budget
+  int64_t T = std::max<int64_t>(1, (cols + kb - 1) / kb);
+  std::vector<int32_t> cnt;
+  for (;;) {
+    cnt.assign((size_t)chunks * T, 0);
+    int32_t worst = 0;
+    for (int64_t i = 0; i < rows; ++i)
+      for (int32_t k = ip[i]; k < ip[i + 1]; ++k) worst = std::max(worst, ++cnt[(size_t)(i / RB) * T + ix[k] % T]);
+    if (worst <= budget) break;
+    if (T >= cols) return fail("internal: SpMM strip does not fit");
+    T = std::min<int64_t>(cols, T + T / 4 + 1);
+  }
+  std::vector<std::vector<SpmmEntry>> bucket(T);   // per strip, per warp streams built in one pass
+  std::vector<int32_t> wstart((size_t)T * W);
+  for (int b = 0; b < chunks; ++b) {
+    const int64_t r0 = (int64_t)b * RB, r1 = std::min<int64_t>(rows, r0 + RB);
+    for (auto& v : bucket) v.clear();
+    for (int w = 0; w < W; ++w) {
+      for (int64_t t = 0; t < T; ++t) wstart[t * W + w] = (int32_t)bucket[t].size();
+      for (int rr = 0; rr < RW; ++rr) {
+        const int64_t i = r0 + w * RW + rr;
+        if (i >= r1) break;
+        for (int32_t k = ip[i]; k < ip[i + 1]; ++k)
+          bucket[ix[k] % T].push_back(SpmmEntry{dv[k], (int)((ix[k] / T) * S * 8), rr});
+      }
+      for (int64_t t = 0; t < T; ++t) bucket[t].push_back(SpmmEntry{0.0, 0, RW});
+    }
+    for (int64_t t = 0; t < T; ++t) {
+      if ((int)bucket[t].size() == W) continue;   // only sentinels: nothing to do in this strip
+      SpmmStrip st{(int)t, (int)((cols - t + T - 1) / T), (int)ent.size(), hdr + (int)bucket[t].size()};
+      if (st.ent_cnt > emax) return fail("internal: strip nonzero count mismatch");
+      const size_t base = ent.size();
+      ent.resize(base + hdr, SpmmEntry{0.0, 0, 0});
+      int32_t* first = reinterpret_cast<int32_t*>(&ent[base]);
+      for (int w = 0; w < W; ++w) first[w] = hdr + wstart[t * W + w];
+      ent.insert(ent.end(), bucket[t].begin(), bucket[t].end());
+      strips.push_back(st);
+    }
+    strip_ptr[b + 1] = (int32_t)strips.size();
+  }
+  if ((cols + T - 1) / T > kb) return fail("internal: SpMM strip wider than its buffer");
+  const SpmmEntry* d_ent = nullptr; const SpmmStrip* d_strips = nullptr;
+  const int32_t* d_ptr = nullptr;
+  if (dev_upload(e, ent, &d_ent) || dev_upload(e, strips, &d_strips) || dev_upload(e, strip_ptr, &d_ptr)) return -1;
+  out->ent = d_ent; out->strips = d_strips; out->strip_ptr = d_ptr;
+  out->rows = (int)rows; out->chunks = chunks; out->cstride = (int)T;
+  out->warps = shape.warps; out->rw = shape.rw; out->cpl = shape.cpl;
+  out->kb = kb; out->emax = emax; out->stages = stages;
+  out->b_bytes = kb * S * 8;
+  out->stage_bytes = (out->b_bytes + emax * 16 + 127) / 128 * 128;
+  HMCB_CUDA(spmm_strip_init(*out));
+  return 0;
+}
+
+// Chooses the SpMM path for the CSR likelihoods: the shared-memory staged kernel in the mapping
+// and strip limits that measured best on the tomography workload (profiles/spmm_lab_r01.json).
+// profiles/tools/spmm_lab.py overrides them through the environment: HMCB_SPMM_SHAPE = 0..n-1 picks
+// a thread mapping of launch_spmm.cu (-1: the L2-gather kernel it replaced, kept as the lab's
+// baseline), HMCB_SPMM_KB / _EMAX / _STAGES the strip limits.
+int upload_csr_both(hmcb_engine* e, const HostCsr& m, CsrDev* gather, StripDev* strip) {
+  const SpmmShape* shapes = nullptr;
+  const int n_shapes = spmm_strip_shapes(&shapes);
+  const int which = env_int("HMCB_SPMM_SHAPE", 0);
+  e->use_strips = which >= 0;
+  if (!e->use_strips) return upload_csr(e, m, gather);
+  HMCB_CHECK(which < n_shapes, "HMCB_SPMM_SHAPE out of range");
+  const SpmmShape sh = shapes[which];
+  const int S = 32 * sh.cpl, RB = sh.warps * sh.rw;
+  // three stages of (60 KB of B rows + 10 KB of nonzeros): deeper pipelines and wider strips both
+  // measured slower
+  const int kb = env_int("HMCB_SPMM_KB", 61440 / (S * 8));
+  // a single column can hold RB nonzeros of the chunk: the slot limit must leave room for them
+  const int emax = std::max(RB + sh.warps + (sh.warps + 3) / 4, env_int("HMCB_SPMM_EMAX", 640));
+  const int stage_bytes = kb * S * 8 + emax * 16 + 128;
+  int stages = env_int("HMCB_SPMM_STAGES", std::min(3, (220 * 1024) / stage_bytes));
+  HMCB_CHECK(kb >= 1 && stages >= 2 && stages <= SPMM_MAX_STAGES && stages * stage_bytes <= 225 * 1024,
+             "SpMM strip configuration does not fit in shared memory");
+  return upload_csr_strips(e, m, sh, kb, emax, stages, strip);
+}
+
 StagedCommon staged_common(const hmcb_engine* e, const hmcb_block* b) {
   StagedCommon S{};
   S.T = e->T; S.C = (int)e->C; S.ld = e->ld; S.jtiles = e->jtiles;
@@ -296,15 +415,21 @@ int staged_gradient_pass(hmcb_engine* e, const double* q_in, UpdateEpi epi, cuda
     }
     case LK_CSR_DIRECT: {
       ResidualEpi r{(int)e->N, (int)e->C, e->ld, e->dvec, e->dvar, e->R};
-      HMCB_CUDA(launch_spmm_residual(e->csr_dev, q_in, e->ld, r, s));
       epi.sub = nullptr;
-      HMCB_CUDA(launch_spmm_update(e->csr_t_dev, e->R, e->ld, epi, s));
+      if (e->use_strips) {
+        HMCB_CUDA(launch_spmm_strip_residual(e->strip_dev, q_in, e->ld, r, s));
+        HMCB_CUDA(launch_spmm_strip_update(e->strip_t_dev, e->R, e->ld, epi, s));
+      } else {
+        HMCB_CUDA(launch_spmm_residual(e->csr_dev, q_in, e->ld, r, s));
+        HMCB_CUDA(launch_spmm_update(e->csr_t_dev, e->R, e->ld, epi, s));
+      }
       e->launches += 2;
       break;
     }
     case LK_CSR_PREMULT: {
       epi.sub = e->dvec;
-      HMCB_CUDA(launch_spmm_update(e->csr_dev, q_in, e->ld, epi, s));
+      if (e->use_strips) HMCB_CUDA(launch_spmm_strip_update(e->strip_dev, q_in, e->ld, epi, s));
+      else HMCB_CUDA(launch_spmm_update(e->csr_dev, q_in, e->ld, epi, s));
       e->launches += 1;
       break;
     }
@@ -329,11 +454,13 @@ int staged_misfit_pass(hmcb_engine* e, const double* q, cudaStream_t s) {
       break;
     case LK_CSR_DIRECT:
       m.rows = (int)e->N; m.vec = e->dvec; m.sigma = e->dsigma;
-      HMCB_CUDA(launch_spmm_misfit(e->csr_dev, q, e->ld, m, s));
+      if (e->use_strips) HMCB_CUDA(launch_spmm_strip_misfit(e->strip_dev, q, e->ld, m, s));
+      else HMCB_CUDA(launch_spmm_misfit(e->csr_dev, q, e->ld, m, s));
       break;
     case LK_CSR_PREMULT:
       m.rows = (int)e->d; m.vec = e->dvec;
-      HMCB_CUDA(launch_spmm_misfit(e->csr_dev, q, e->ld, m, s));
+      if (e->use_strips) HMCB_CUDA(launch_spmm_strip_misfit(e->strip_dev, q, e->ld, m, s));
+      else HMCB_CUDA(launch_spmm_misfit(e->csr_dev, q, e->ld, m, s));
       break;
     default: return fail("internal: bad likelihood kind on the staged path");
   }
@@ -792,14 +919,15 @@ int hmcb_finalize(hmcb_engine* e) {
         e->ltiles = e->npad / GEMM_BM;
         break;
       case LK_CSR_DIRECT:
-        if (upload_csr(e, e->csr, &e->csr_dev) || upload_csr(e, e->csr_t, &e->csr_t_dev)) return -1;
-        e->ltiles = e->csr_dev.chunks * SPMM_WARPS;
+        if (upload_csr_both(e, e->csr, &e->csr_dev, &e->strip_dev) ||
+            upload_csr_both(e, e->csr_t, &e->csr_t_dev, &e->strip_t_dev)) return -1;
+        e->ltiles = e->use_strips ? e->strip_dev.chunks * e->strip_dev.warps : e->csr_dev.chunks * SPMM_WARPS;
         break;
       case LK_CSR_PREMULT:
-        if (upload_csr(e, e->csr, &e->csr_dev)) return -1;
+        if (upload_csr_both(e, e->csr, &e->csr_dev, &e->strip_dev)) return -1;
         if (dev_upload(e, e->h_vec, &tmp)) return -1;
         e->dvec = const_cast<double*>(tmp);
-        e->ltiles = e->csr_dev.chunks * SPMM_WARPS;
+        e->ltiles = e->use_strips ? e->strip_dev.chunks * e->strip_dev.warps : e->csr_dev.chunks * SPMM_WARPS;
         break;
       default: return fail("internal: bad likelihood kind");
     }

@@ -5,6 +5,7 @@
 #include "fused.cuh"
 #include "srcloc.cuh"
 #include "staged.cuh"
+#include "spmm_types.cuh"
 
 namespace hmcb {
 
@@ -65,6 +66,17 @@ cudaError_t launch_spmm_residual(const CsrDev& M, const double* B, int ldb, cons
                                  cudaStream_t s);
 cudaError_t launch_spmm_misfit(const CsrDev& M, const double* B, int ldb, const MisfitEpi& epi,
                                cudaStream_t s);
+// ---- launch_spmm.cu: shared-memory staged SpMM (spmm_strip.cuh) -------------------------------
+// thread mappings (consumer warps, rows per warp, chains per lane) the library is built with
+struct SpmmShape { int warps, rw, cpl; };
+int spmm_strip_shapes(const SpmmShape** out);
+cudaError_t spmm_strip_init(const StripDev& M);  // opt-in shared memory size of the mapping
+cudaError_t launch_spmm_strip_update(const StripDev& M, const double* B, int ldb, const UpdateEpi& epi,
+                                     cudaStream_t s);
+cudaError_t launch_spmm_strip_residual(const StripDev& M, const double* B, int ldb, const ResidualEpi& epi,
+                                       cudaStream_t s);
+cudaError_t launch_spmm_strip_misfit(const StripDev& M, const double* B, int ldb, const MisfitEpi& epi,
+                                     cudaStream_t s);
 cudaError_t launch_st_begin(const StagedCommon& S, long long kglob, double a_mult, const double* q_cur,
                             double* q_w, double* p, const double* z_in, const double* u_step_in,
                             const double* u_acc_in, double* eps_out, double* uacc_out, double* k0part,

@@ -1,0 +1,154 @@
+// spmm_strip.cuh -- CSR SpMM over the chain batch with the gathered operand staged in shared
+// memory (replaces the SciPy csr_matvec / MKL mkl_cspblas_dcsrgemv calls of
+// LinearMatrix.py:389-426 and Helpers/InterfaceMKL.py:87-121 for a whole batch of chains).
+//
+//   Y[i][c] = sum_k val[k] * B[col[k]][c]        B: [cols x chains], chains contiguous
+//
+// The L2-gather kernel (csr_spmm_kernel, gemm.cuh) moves nnz x chains x 8 B from L2 into the SMs
+// and sits on the L2 fabric limit.  Here a block owns RB = WARPS x RW rows and one slab of
+// S = 32 x CPL chains and walks the columns strip by strip:
+//   * hmcb_finalize deals the columns round-robin into T strips of at most KB columns (column c
+//     belongs to strip c mod T: every row spreads its nonzeros evenly over the strips, whatever
+//     its geometry, so the warps of a block stay balanced) and stores, per (chunk, strip), the nonzeros of the chunk's rows that
+//     fall into the strip as one flat stream per consumer warp ({value, local column offset,
+//     row within the warp} as 16 bytes, closed by a sentinel);
+//   * a producer warp stages strip after strip: the B rows of the strip with 16-byte cp.async
+//     (SASS LDGSTS) arriving on the stage's mbarrier, the nonzero streams with one bulk
+//     copy (TMA engine, SASS UBLKCP) completing on the same barrier; consumer warps release a stage through an
+//     "empty" mbarrier, there is no block-wide barrier in the loop;
+//   * a consumer warp keeps the accumulators of its RW rows x CPL chains per lane in registers
+//     and walks its stream with the next nonzero always in flight; every load of the inner loop
+//     is a shared-memory load: one 16-byte broadcast for the nonzero, one conflict-free
+//     S x 8 B row segment for the gather (CPL = 2: one gather feeds two FMAs).
+// L2 -> SM traffic drops from nnz x chains x 8 B to (rows / RB) x cols x chains x 8 B.
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+#include "spmm_types.cuh"
+
+namespace hmcb {
+
+__device__ __forceinline__ void cp_async_16(unsigned smem_addr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem) : "memory");
+}
+// the executing thread's earlier cp.async operations arrive on the barrier once they have completed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(a) : "memory");
+}
+
+constexpr int SPMM_PRODUCERS = 4;   // producer warps: one warp cannot keep enough copies in flight
+
+template <class Epilogue, int WARPS, int RW, int CPL>
+__global__ void __launch_bounds__((WARPS + SPMM_PRODUCERS) * 32, 1)
+csr_spmm_strip_kernel(const StripDev M, const double* __restrict__ B, int ldb, Epilogue epi) {
+  constexpr int S = 32 * CPL, RB = WARPS * RW;
+  extern __shared__ __align__(128) unsigned char strip_smem[];
+  __shared__ uint64_t full_bar[SPMM_MAX_STAGES], empty_bar[SPMM_MAX_STAGES];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk = blockIdx.x, slab0 = blockIdx.y * S;
+  const int s_begin = __ldg(M.strip_ptr + chunk);
+  const int nst = __ldg(M.strip_ptr + chunk + 1) - s_begin;
+  const int nstages = M.stages;
+
+  if (tid == 0) {
+    for (int st = 0; st < nstages; ++st) {
+      mbar_init(&full_bar[st], 32 * SPMM_PRODUCERS + 1);   // cp.async arrivals of every producer lane + expect_tx
+      mbar_init(&empty_bar[st], WARPS);
+    }
+    fence_async_proxy();
+  }
+  __syncthreads();
+
+  if (warp >= WARPS) {   // ---- producer warps: B rows interleaved between them
+    const int pw = warp - WARPS;
+    constexpr int LPR = S * 8 / 16, RPI = 32 / LPR;   // lanes per B row, rows per warp instruction
+    const int sub = lane / LPR, part = lane % LPR;
+    const size_t rstride = (size_t)M.cstride * ldb * 8;   // bytes between consecutive B rows of a strip
+    int stage = 0;
+    unsigned phase = 1;  // parity of the previous use of the stage (first pass: nothing to wait for)
+    for (int t = 0; t < nst; ++t) {
+      if (t >= nstages) mbar_wait(&empty_bar[stage], phase);
+      const int4 raw = __ldg(reinterpret_cast<const int4*>(M.strips + s_begin + t));
+      const int col0 = raw.x, ncols = raw.y, ent_off = raw.z, ent_cnt = raw.w;
+      unsigned char* base = strip_smem + (size_t)stage * M.stage_bytes;
+      // B rows: 16-byte cp.async per lane (a bulk copy per 256-byte row costs ~60 cycles of the
+      // copy engine each and starves the consumers); the lane's copies arrive on the stage's
+      // barrier when they have landed.  The nonzero streams of all warps: one bulk copy.
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(base) + (unsigned)(sub * S * 8 + part * 16);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(B + (size_t)col0 * ldb + slab0) + part * 16;
+      for (int j = pw * RPI + sub; j < ncols; j += RPI * SPMM_PRODUCERS)
+        cp_async_16(dst + (unsigned)(j - sub) * (S * 8u), src + (size_t)j * rstride);
+      cp_async_arrive_noinc(&full_bar[stage]);
+      if (pw == 0 && lane == 0) {
+        mbar_expect_tx(&full_bar[stage], (unsigned)ent_cnt * 16u);
+        bulk_copy_g2s(base + M.b_bytes, M.ent + ent_off, (unsigned)ent_cnt * 16u, &full_bar[stage]);
+      }
+      if (++stage == nstages) { stage = 0; phase ^= 1u; }
+    }
+    return;
+  }
+
+  // ---- consumer warps: rows [row0, row0 + RW), chains slab0 + lane * CPL + {0 .. CPL-1}
+  double acc[RW][CPL];
+#pragma unroll
+  for (int r = 0; r < RW; ++r)
+#pragma unroll
+    for (int h = 0; h < CPL; ++h) acc[r][h] = 0.0;
+
+  {
+    int stage = 0;
+    unsigned phase = 0;
+    for (int t = 0; t < nst; ++t) {
+      mbar_wait(&full_bar[stage], phase);
+      const unsigned char* base = strip_smem + (size_t)stage * M.stage_bytes;
+      const unsigned char* Bs = base + lane * (CPL * 8);
+      const int4* Es = reinterpret_cast<const int4*>(base + M.b_bytes);
+      Es += reinterpret_cast<const int*>(Es)[warp];   // header: first slot of every warp
+      int4 e = *Es;
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+#pragma unroll 1
+        while (e.w == r) {
+          const double v = __hiloint2double(e.y, e.x);
+          if constexpr (CPL == 1) {
+            const double b = *reinterpret_cast<const double*>(Bs + e.z);
+            e = *++Es;
+            acc[r][0] = fma(v, b, acc[r][0]);
+          } else {
+            const double2 b = *reinterpret_cast<const double2*>(Bs + e.z);
+            e = *++Es;
+            acc[r][0] = fma(v, b.x, acc[r][0]);
+            acc[r][1] = fma(v, b.y, acc[r][1]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == nstages) { stage = 0; phase ^= 1u; }
+    }
+  }
+
+  // ---- epilogue: one functor copy per chain of the lane (MisfitEpi carries a running sum)
+  const int row0 = chunk * RB + warp * RW;
+  const int c0 = slab0 + lane * CPL;
+  Epilogue ep[CPL];
+#pragma unroll
+  for (int h = 0; h < CPL; ++h) {
+    ep[h] = epi;
+    ep[h].tile_begin(row0, slab0);
+  }
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const int i = row0 + r;
+    if (i < M.rows) {
+#pragma unroll
+      for (int h = 0; h < CPL; ++h) ep[h].row(i, c0 + h, acc[r][h]);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < CPL; ++h) ep[h].chunk_end(chunk * WARPS + warp, c0 + h);
+}
+
+}  // namespace hmcb
