@@ -1,0 +1,100 @@
+"""The shared-memory staged CSR SpMM (hmclab_b200/csrc/spmm_strip.cuh) on awkward matrices:
+empty rows, a full row, a full column, a chain count that is no multiple of the slab width,
+every thread mapping the library is built with, strip limits small enough to force the
+builder's fallback (more, narrower strips), and raw C-ABI input with unsorted rows and split
+duplicate entries.  Checked against the numpy oracle evaluated chain by chain
+(misfit/gradient contract of LinearMatrix.py:389-426)."""
+import copy
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import rel_err
+from hmclab_b200 import Distributions as D
+from hmclab_b200 import MassMatrices as M
+from hmclab_b200._lowering import describe, describe_mass, flatten
+from oracle import hmc_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+
+
+def _awkward(premult, seed=11):
+    rng = np.random.default_rng(seed)
+    N, d = (700, 333) if not premult else (150, 90)
+    G = sp.random(N, d, density=0.05, random_state=np.random.RandomState(seed), format="lil")
+    G[5, :] = 0.0                       # empty row
+    G[100:121, :] = 0.0                 # a run of empty rows
+    G[7, :] = rng.normal(size=d)        # full row
+    G[:, 11] = rng.normal(size=(N, 1))  # full column
+    G = sp.csr_matrix(G)
+    G.eliminate_zeros()
+    dvec = rng.normal(size=(N, 1))
+    var = rng.uniform(0.5, 1.5, size=(N, 1))
+    lik = D.LinearMatrix(G, dvec, var, premultiplication=premult)
+    prior = D.Normal(np.zeros((d, 1)), rng.uniform(0.5, 2.0, size=(d, 1)))
+    return D.BayesRule([prior, lik]), d
+
+
+def _check(plan, tree, mtree, d, chains=130, seed=3):
+    import torch
+
+    from hmclab_b200._engine import Engine
+
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=(chains, d))
+    eng = Engine(plan, mtree, chains, integrator="lf", amount_of_steps=3)
+    assert eng.path == "staged"
+    qd = torch.as_tensor(q).cuda().contiguous()
+    g = eng.gradient(qd).cpu().numpy()
+    x = eng.misfit(qd).cpu().numpy()
+    sel = [0, 1, 63, 64, 65, chains - 1]
+    g_ref = np.stack([oracle.gradient(tree, q[c][:, None])[:, 0] for c in sel])
+    x_ref = np.array([oracle.misfit(tree, q[c][:, None]) for c in sel])
+    assert rel_err(g[sel], g_ref) < TOL
+    assert rel_err(x[sel], x_ref) < TOL
+    eng.close()
+    return g, x
+
+
+@pytest.mark.parametrize("premult", [False, True])
+@pytest.mark.parametrize("env", [{}, {"HMCB_SPMM_SHAPE": "1"}, {"HMCB_SPMM_SHAPE": "2"},
+                                 {"HMCB_SPMM_SHAPE": "3"},
+                                 {"HMCB_SPMM_KB": "7", "HMCB_SPMM_EMAX": "1", "HMCB_SPMM_STAGES": "4"},
+                                 {"HMCB_SPMM_SHAPE": "-1"}])
+def test_strip_spmm_on_awkward_matrices(monkeypatch, premult, env):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    post, d = _awkward(premult)
+    tree, mtree = describe(post), describe_mass(M.Unit(d))
+    _check(flatten(tree), tree, mtree, d)
+
+
+def test_strip_spmm_accepts_unsorted_rows_and_duplicates():
+    """The C ABI takes any valid CSR: rows need not be sorted and an entry may be split in two."""
+    post, d = _awkward(False)
+    tree, mtree = describe(post), describe_mass(M.Unit(d))
+    plan = flatten(tree)
+    g0, x0 = _check(plan, tree, mtree, d)
+
+    def scramble(indptr, indices, data, rng):
+        ip, ix, dv = [0], [], []
+        for i in range(len(indptr) - 1):
+            cols, vals = list(indices[indptr[i]:indptr[i + 1]]), list(data[indptr[i]:indptr[i + 1]])
+            if cols:   # split the first entry of the row into two halves (exact in binary)
+                cols.append(cols[0]); vals.append(vals[0] / 2); vals[0] = vals[0] / 2
+            perm = rng.permutation(len(cols))
+            ix += [cols[p] for p in perm]; dv += [vals[p] for p in perm]
+            ip.append(len(ix))
+        return (np.asarray(ip, dtype=np.int32), np.asarray(ix, dtype=np.int32), np.asarray(dv, dtype=np.float64))
+
+    rng = np.random.default_rng(5)
+    plan2 = copy.copy(plan)
+    lik = dict(plan["likelihood"])
+    lik["indptr"], lik["indices"], lik["data"] = scramble(lik["indptr"], lik["indices"], lik["data"], rng)
+    lik["t_indptr"], lik["t_indices"], lik["t_data"] = scramble(lik["t_indptr"], lik["t_indices"], lik["t_data"], rng)
+    plan2["likelihood"] = lik
+    g1, x1 = _check(plan2, tree, mtree, d)
+    assert rel_err(g1, g0) < 1e-13 and rel_err(x1, x0) < 1e-13
