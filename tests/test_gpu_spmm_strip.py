@@ -79,12 +79,13 @@ def test_strip_spmm_accepts_unsorted_rows_and_duplicates():
     plan = flatten(tree)
     g0, x0 = _check(plan, tree, mtree, d)
 
-    def scramble(indptr, indices, data, rng):
+    def scramble(indptr, indices, data, rng, n_split=50):   # the ABI takes one nnz for G and G^T
         ip, ix, dv = [0], [], []
         for i in range(len(indptr) - 1):
             cols, vals = list(indices[indptr[i]:indptr[i + 1]]), list(data[indptr[i]:indptr[i + 1]])
-            if cols:   # split the first entry of the row into two halves (exact in binary)
+            if cols and n_split > 0:   # split the first entry of the row into two halves (exact in binary)
                 cols.append(cols[0]); vals.append(vals[0] / 2); vals[0] = vals[0] / 2
+                n_split -= 1
             perm = rng.permutation(len(cols))
             ix += [cols[p] for p in perm]; dv += [vals[p] for p in perm]
             ip.append(len(ix))
