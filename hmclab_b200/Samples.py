@@ -6,8 +6,9 @@ On-disk format is the reference's:
   proposal: model, then misfit; the reader transposes, Samples.py:160-161) next to a
   ``<file>.pkl`` pickle of the attribute dictionary (Samples.py:146-151, 163-171);
 * ``*.h5`` / no extension -- HDF5 dataset ``"samples"`` of shape ``(d+1, n)`` with the
-  attributes on the dataset (Samples.py:127-144, 305-322).  Needs ``h5py``; when it is not
-  installed the request fails loudly (nothing is silently redirected).
+  attributes on the dataset (Samples.py:127-144, 305-322).  Written and read with ``h5py`` when
+  it is installed, otherwise by the native writer/reader of ``hmclab_b200._hdf5`` (classic
+  HDF5 layout: version 0 superblock, contiguous dataset, fixed-length string attributes).
 
 Files written here open with the reference's ``hmclab.Samples`` and vice versa.  A batched
 run stores its chains one after the other (all rows of chain 0, then chain 1, ...), which
@@ -52,6 +53,7 @@ class Samples:
         self._attributes = {}
         self._memmap = None
         self._h5 = None
+        self._native = None   # hmclab_b200._hdf5.Writer when h5py is not installed
 
         if mode == "r":
             if overwrite is not None:
@@ -63,13 +65,19 @@ class Samples:
                 self._array = _numpy.load(filename, mmap_mode="r").T
                 with open(f"{filename}.pkl", "rb") as f:
                     self._attributes = _pickle.load(f)
-            else:
-                self._require_h5py()
+            elif _have_h5py():
                 import h5py
 
                 try:
                     self._h5 = h5py.File(filename, "r")
                     self._dataset = self._h5["samples"]
+                except Exception as e:
+                    raise ValueError(f"Was not able to open the samples file. Exception: {e}")
+            else:
+                from . import _hdf5
+
+                try:
+                    self._dataset, self._attributes = _hdf5.open_dataset(filename, "samples")
                 except Exception as e:
                     raise ValueError(f"Was not able to open the samples file. Exception: {e}")
             self.burn_in = 0 if burn_in is None else burn_in
@@ -96,8 +104,6 @@ class Samples:
                     shown += f"` or attributes file `{filename}.pkl"
                 raise FileExistsError(
                     f"Trying to write samples to an already existing file `{shown}`.")
-            if self.filetype == "HDF5":
-                self._require_h5py()
             self._rows_written = 0
             self.write_attribute("write_index", 0)
             self.write_attribute("last_written_sample", -1)
@@ -123,6 +129,11 @@ class Samples:
                 _os.remove(self.filename)
             self._memmap = _numpy.lib.format.open_memmap(
                 self.filename, mode="w+", dtype=_numpy.float64, shape=(total, self._width))
+        elif not _have_h5py():
+            from . import _hdf5
+
+            self._native = _hdf5.Writer(self.filename, (self._width, total), "samples", overwrite=self.overwrite)
+            self._dataset = self._native.data
         else:
             import h5py
 
@@ -154,11 +165,17 @@ class Samples:
     def _compact(self):
         """A run that stopped early leaves unwritten rows; drop them so that every stored
         row is a sample (the reference's files only ever hold written samples)."""
-        if self._memmap is None and self._h5 is None:
+        if self._memmap is None and self._h5 is None and self._native is None:
             return
         if self._rows_written == self._per_chain:
             return
         keep = self._rows_written
+        if self._native is not None:
+            self._native.resize_columns(keep, self._per_chain)
+            self._dataset = self._native.data
+            self._per_chain = keep
+            self._attributes["samples_per_chain"] = keep
+            return
         if self.filetype == "NPY":
             data = _numpy.array(
                 self._memmap.reshape(self._chains, self._per_chain, self._width)[:, :keep, :])
@@ -188,6 +205,9 @@ class Samples:
         if self.filetype == "NPY":
             with open(f"{self.filename}.pkl", "wb") as f:
                 _pickle.dump(self._attributes, f)
+        elif self._native is not None:
+            self._native.close(self._attributes)
+            self._native = None
         elif self._h5 is not None:
             for key, value in self._attributes.items():
                 self._dataset.attrs[key] = value

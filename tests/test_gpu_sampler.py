@@ -45,14 +45,17 @@ def test_same_seed_reproduces_the_reference_samples_file(tmp_path, name):
     assert isinstance(sampler.current_x, float)
 
 
-def test_file_attributes_and_reader(tmp_path):
+@pytest.mark.parametrize("ext", [".npy", ".h5"])
+def test_file_attributes_and_reader(tmp_path, ext):
+    """Both of the reference's formats: NumPy + pickle, and HDF5 (h5py when installed, else the
+    native writer of hmclab_b200._hdf5)."""
     from hmclab_b200 import Distributions as D
     from hmclab_b200.Samplers import HMC
     from hmclab_b200.Samples import Samples
 
     d, C = 6, 5
     post = D.Normal(np.zeros((d, 1)), 1.0)
-    fn = str(tmp_path / "multi.npy")
+    fn = str(tmp_path / f"multi{ext}")
     sampler = HMC(seed=3).sample(fn, post, stepsize=0.3, proposals=40, online_thinning=4,
                                  chains=C, disable_progressbar=True, block_proposals=12)
     with Samples(fn) as s:
@@ -68,7 +71,7 @@ def test_file_attributes_and_reader(tmp_path):
         assert s.read_attribute("mass_matrix") == "unit mass matrix"
         last = s.chain(C - 1)[:, -1]
         # stored misfit is chi of the stored model: 0.5 * |m|^2
-        assert rel_err(s.misfits, 0.5 * np.sum(s.samples ** 2, axis=0)) < 1e-13
+        assert rel_err(np.ravel(s.misfits), 0.5 * np.sum(s.samples ** 2, axis=0)) < 1e-13
     assert last.shape == (d + 1,) and sampler.current_model.shape == (d, C)
     assert sampler.current_x.shape == (C,)
     assert sampler.amount_of_writes == 10 and sampler.current_proposal == 39
@@ -168,13 +171,14 @@ def test_sampling_statistics_of_a_known_target(tmp_path):
     assert np.all(np.abs(x.var(axis=(0, 2)) / var[:, 0] - 1) < 0.1)
 
 
-def test_max_time_stops_early_and_leaves_a_valid_file(tmp_path):
+@pytest.mark.parametrize("ext", [".npy", ".h5"])
+def test_max_time_stops_early_and_leaves_a_valid_file(tmp_path, ext):
     from hmclab_b200 import workloads
     from hmclab_b200.Samplers import HMC
     from hmclab_b200.Samples import Samples
 
     w = workloads.normal_iid(dims=200, chains=256)
-    fn = str(tmp_path / "cut.npy")
+    fn = str(tmp_path / f"cut{ext}")
     t0 = time.time()
     sampler = HMC(seed=1).sample(fn, w.posterior, stepsize=0.05, proposals=2_000_000,
                                  online_thinning=1000, chains=256, initial_model=w.initial_models,

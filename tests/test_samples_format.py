@@ -81,31 +81,90 @@ def test_error_behaviour(tmp_path):
         Samples(path, burn_in=15)
 
 
-def test_hdf5_needs_h5py_and_says_so(tmp_path):
+def _libhdf5_file():
+    """A file written by libhdf5 itself: SciPy ships a MATLAB v7.3 (= HDF5 behind a 512-byte user
+    block) test file."""
+    import scipy.io
+
+    path = os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data",
+                        "testhdf5_7.4_GLNX86.mat")
+    if not os.path.isfile(path):
+        pytest.skip("SciPy's HDF5 test file is not installed")
+    return path
+
+
+def test_native_hdf5_reader_parses_a_file_written_by_libhdf5():
+    """Pins the reader (and with it the writer's view of the format, which the next test reads
+    back through the same reader) to real libhdf5 output: superblock, root symbol table, group
+    B-tree, local heap, version 1 object header, datatype / dataspace / attribute messages."""
+    from hmclab_b200 import _hdf5
+
+    arr, attrs = _hdf5.open_dataset(_libhdf5_file(), "testdouble")
+    assert arr.shape == (9, 1) and arr.dtype == np.dtype("<f8")
+    assert np.allclose(np.asarray(arr)[:, 0], np.linspace(0, 2 * np.pi, 9))
+    assert attrs == {"MATLAB_class": "double"}
+
+
+def test_native_hdf5_messages_are_byte_identical_to_libhdf5s():
+    """The float64 datatype, the rank-2 dataspace, a scalar string attribute and the default
+    fill-value message encode to exactly the bytes libhdf5 wrote into that file."""
+    from hmclab_b200 import _hdf5
+
+    f = _hdf5._File(_libhdf5_file())
+    msgs = dict((t, d) for t, d in f.messages(f.links(f.root_header)["testdouble"]))
+    assert _hdf5._dtype_message("<f8") == msgs[0x0003][:20]
+    assert _hdf5._dataspace_message((9, 1)) == msgs[0x0001]
+    assert _hdf5._message(0x0005, b"\x01\x02\x02\x01\0\0\0\0")[8:] == msgs[0x0005]
+    mine = _hdf5._attribute_message("MATLAB_class", b"double")[8:]
+    # libhdf5 stored a null-terminated ASCII string of 6 bytes; ours is null padded UTF-8 of 7:
+    # same layout, the two datatype flag/size bytes and the padding differ
+    theirs = msgs[0x000C]
+    assert mine[:24] == theirs[:24] and mine[32:40] == theirs[32:40] and mine[40:46] == theirs[40:46]
+
+
+def test_hdf5_samples_file_without_h5py(tmp_path):
+    """`.h5` (the reference's default format, Samples.py:127-144): dataset "samples" (d+1, n)
+    float64 with the attributes on the dataset, chains one after the other."""
+    from hmclab_b200 import _hdf5
     from hmclab_b200.Samples import _have_h5py
 
     if _have_h5py():
-        pytest.skip("h5py present")
-    with pytest.raises(ImportError, match="h5py"):
-        Samples(str(tmp_path / "run.h5"), mode="w")
-
-
-@pytest.mark.skipif(not os.path.isdir("/root/reference/hmclab"), reason="reference not mounted")
-def test_reference_reader_opens_our_files(tmp_path):
-    from _reference_shim import import_reference
-
-    hmclab = import_reference()
-    path = str(tmp_path / "ours.npy")
-    data = _write(path, chains=1, per_chain=6, dims=3)
-    for key, val in dict(sampler="Hamiltonian Monte Carlo", acceptance_rate=0.5, online_thinning=1,
-                         start_time="a", end_time="b", runtime="c", runtime_seconds=1.0).items():
-        with open(path + ".pkl", "rb") as f:
-            attrs = pickle.load(f)
-        attrs[key] = val
-        with open(path + ".pkl", "wb") as f:
-            pickle.dump(attrs, f)
-    ref = hmclab.Samples(path, burn_in=1)
-    assert ref.numpy.shape == (4, 5)
-    assert np.array_equal(np.asarray(ref.numpy), data[1:, 0, :].T)
-    assert ref.read_attribute("write_index") == 6
-    ref.close()
+        pytest.skip("h5py present: the h5py backend is used")
+    path = str(tmp_path / "run.h5")
+    s = Samples(path, mode="w")
+    s.allocate(3, 5, 4)
+    rng = np.random.default_rng(0)
+    data = rng.normal(size=(5, 3, 5))
+    s.write_block(data[:2])
+    s.write_block(data[2:])
+    s.write_attribute("proposals", 5)
+    s.write_attribute("acceptance_rate", 0.8125)
+    s.write_attribute("sampler", "HMC")
+    s.write_attribute("start_time", "2026-10-17 12:00:00.000001")
+    s.close()
+    with open(path, "rb") as f:
+        assert f.read(8) == _hdf5.SIGNATURE
+    with Samples(path) as r:
+        assert r.numpy.shape == (5, 15)
+        assert np.array_equal(r.chain(1), data[:, 1, :].T)
+        assert np.array_equal(r.misfits[:, 0], np.concatenate([data[:, c, -1] for c in range(3)]))
+        assert r.read_attribute("write_index") == 15 and r.read_attribute("last_written_sample") == 14
+        assert r.read_attribute("acceptance_rate") == 0.8125
+        assert r.read_attribute("sampler") == "HMC"
+        assert r.read_attribute("start_time") == "2026-10-17 12:00:00.000001"
+    with Samples(path, burn_in=4) as r:
+        assert r.numpy.shape == (5, 11)
+    with pytest.raises(FileExistsError):
+        Samples(path, mode="w")
+    assert combine_samples([path, path]).shape == (5, 30)
+    # a run that stopped early is compacted to the written samples
+    part = str(tmp_path / "part")          # no extension = HDF5, as in the reference
+    s = Samples(part, mode="w")
+    s.allocate(3, 5, 4)
+    s.write_block(data[:2])
+    s.close()
+    with Samples(part) as r:
+        assert r.numpy.shape == (5, 6) and r.read_attribute("samples_per_chain") == 2
+        assert np.array_equal(r.chain(2), data[:2, 2, :].T)
+    arr, attrs = _hdf5.open_dataset(part + ".h5")
+    assert os.path.getsize(part + ".h5") < _hdf5.DATA_OFFSET + 8 * 75 + 4096 and attrs["chains"] == 3
