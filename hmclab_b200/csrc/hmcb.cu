@@ -107,6 +107,7 @@ struct hmcb_engine {
   CsrDev csr_dev{}, csr_t_dev{};
   StripDev strip_dev{}, strip_t_dev{};  // shared-memory staged SpMM tables (spmm_strip.cuh)
   bool use_strips = false;
+  CUtensorMap tmap_q[2], tmap_R;        // B operands of the strip SpMM: the two position planes and R
   double *q_cur = nullptr, *q_w[2] = {nullptr, nullptr}, *p_w = nullptr, *R = nullptr;
   double *eps = nullptr, *uacc = nullptr, *k0part = nullptr, *k1part = nullptr, *upart = nullptr,
          *lpart = nullptr;
@@ -341,6 +342,7 @@ int upload_csr_strips(hmcb_engine* e, const HostCsr& m, const SpmmShape& shape, 
   out->kb = kb; out->emax = emax; out->stages = stages;
   out->b_bytes = kb * S * 8;
   out->stage_bytes = (out->b_bytes + emax * 16 + 127) / 128 * 128;
+  out->kb_box = (int)((cols + T - 1) / T);
   HMCB_CUDA(spmm_strip_init(*out));
   return 0;
 }
@@ -359,11 +361,11 @@ int upload_csr_both(hmcb_engine* e, const HostCsr& m, CsrDev* gather, StripDev* 
   HMCB_CHECK(which < n_shapes, "HMCB_SPMM_SHAPE out of range");
   const SpmmShape sh = shapes[which];
   const int S = 32 * sh.cpl, RB = sh.warps * sh.rw;
-  // three stages of (60 KB of B rows + 10 KB of nonzeros): deeper pipelines and wider strips both
-  // measured slower
-  const int kb = env_int("HMCB_SPMM_KB", 61440 / (S * 8));
+  // two stages of (96 KB of B rows + 14 KB of nonzero slots): the widest strips that fit measured
+  // best once the B rows arrive by tensor-map TMA (profiles/spmm_lab_r01.json)
+  const int kb = env_int("HMCB_SPMM_KB", 98304 / (S * 8));
   // a single column can hold RB nonzeros of the chunk: the slot limit must leave room for them
-  const int emax = std::max(RB + sh.warps + (sh.warps + 3) / 4, env_int("HMCB_SPMM_EMAX", 640));
+  const int emax = std::max(RB + sh.warps + (sh.warps + 3) / 4, env_int("HMCB_SPMM_EMAX", 896));
   const int stage_bytes = kb * S * 8 + emax * 16 + 128;
   int stages = env_int("HMCB_SPMM_STAGES", std::min(3, (220 * 1024) / stage_bytes));
   HMCB_CHECK(kb >= 1 && stages >= 2 && stages <= SPMM_MAX_STAGES && stages * stage_bytes <= 225 * 1024,
@@ -388,6 +390,11 @@ inline int staged_lik_mode(const hmcb_engine* e) {
     case LK_DENSE_DIRECT: case LK_CSR_DIRECT: return LIK_DIRECT;
     default: return LIK_NONE;
   }
+}
+
+// tensor map of a position plane handed to the strip SpMM (only the two ping-pong planes are)
+inline const CUtensorMap& q_map(const hmcb_engine* e, const double* q) {
+  return e->tmap_q[q == e->q_w[1] ? 1 : 0];
 }
 
 // total gradient at q_in fused with the update described by `epi` (q_in -> epi.q_out)
@@ -417,8 +424,8 @@ int staged_gradient_pass(hmcb_engine* e, const double* q_in, UpdateEpi epi, cuda
       ResidualEpi r{(int)e->N, (int)e->C, e->ld, e->dvec, e->dvar, e->R};
       epi.sub = nullptr;
       if (e->use_strips) {
-        HMCB_CUDA(launch_spmm_strip_residual(e->strip_dev, q_in, e->ld, r, s));
-        HMCB_CUDA(launch_spmm_strip_update(e->strip_t_dev, e->R, e->ld, epi, s));
+        HMCB_CUDA(launch_spmm_strip_residual(e->strip_dev, q_map(e, q_in), q_in, e->ld, r, s));
+        HMCB_CUDA(launch_spmm_strip_update(e->strip_t_dev, e->tmap_R, e->R, e->ld, epi, s));
       } else {
         HMCB_CUDA(launch_spmm_residual(e->csr_dev, q_in, e->ld, r, s));
         HMCB_CUDA(launch_spmm_update(e->csr_t_dev, e->R, e->ld, epi, s));
@@ -428,7 +435,7 @@ int staged_gradient_pass(hmcb_engine* e, const double* q_in, UpdateEpi epi, cuda
     }
     case LK_CSR_PREMULT: {
       epi.sub = e->dvec;
-      if (e->use_strips) HMCB_CUDA(launch_spmm_strip_update(e->strip_dev, q_in, e->ld, epi, s));
+      if (e->use_strips) HMCB_CUDA(launch_spmm_strip_update(e->strip_dev, q_map(e, q_in), q_in, e->ld, epi, s));
       else HMCB_CUDA(launch_spmm_update(e->csr_dev, q_in, e->ld, epi, s));
       e->launches += 1;
       break;
@@ -454,12 +461,12 @@ int staged_misfit_pass(hmcb_engine* e, const double* q, cudaStream_t s) {
       break;
     case LK_CSR_DIRECT:
       m.rows = (int)e->N; m.vec = e->dvec; m.sigma = e->dsigma;
-      if (e->use_strips) HMCB_CUDA(launch_spmm_strip_misfit(e->strip_dev, q, e->ld, m, s));
+      if (e->use_strips) HMCB_CUDA(launch_spmm_strip_misfit(e->strip_dev, q_map(e, q), q, e->ld, m, s));
       else HMCB_CUDA(launch_spmm_misfit(e->csr_dev, q, e->ld, m, s));
       break;
     case LK_CSR_PREMULT:
       m.rows = (int)e->d; m.vec = e->dvec;
-      if (e->use_strips) HMCB_CUDA(launch_spmm_strip_misfit(e->strip_dev, q, e->ld, m, s));
+      if (e->use_strips) HMCB_CUDA(launch_spmm_strip_misfit(e->strip_dev, q_map(e, q), q, e->ld, m, s));
       else HMCB_CUDA(launch_spmm_misfit(e->csr_dev, q, e->ld, m, s));
       break;
     default: return fail("internal: bad likelihood kind on the staged path");
@@ -892,9 +899,7 @@ int hmcb_finalize(hmcb_engine* e) {
     e->npad = e->N ? round_up(e->N, 128) : 0;
     e->jtiles = (d + ST_DT - 1) / ST_DT;
     const size_t plane = (size_t)e->dpad * e->ld;
-    if (dev_alloc(e, plane, &e->q_cur) || dev_alloc(e, plane, &e->q_w[0]) || dev_alloc(e, plane, &e->q_w[1]) ||
-        dev_alloc(e, plane, &e->p_w))
-      return -1;
+    if (dev_alloc(e, plane, &e->q_cur) || dev_alloc(e, plane, &e->p_w)) return -1;
     if (dev_alloc(e, (size_t)e->ld, &e->eps) || dev_alloc(e, (size_t)e->ld, &e->uacc) ||
         dev_alloc(e, (size_t)e->ld, &e->accbuf))
       return -1;
@@ -935,7 +940,19 @@ int hmcb_finalize(hmcb_engine* e) {
       const double *dv = nullptr, *vv = nullptr, *sv = nullptr;
       if (dev_upload(e, e->h_vec, &dv) || dev_upload(e, e->h_var, &vv) || dev_upload(e, e->h_sigma, &sv)) return -1;
       e->dvec = const_cast<double*>(dv); e->dvar = const_cast<double*>(vv); e->dsigma = const_cast<double*>(sv);
-      if (dev_alloc(e, (size_t)e->npad * e->ld, &e->R)) return -1;
+      // (the strip SpMM reads R through a tensor map that needs one strip stride of slack rows)
+      const size_t r_rows = (size_t)e->npad + (e->use_strips && e->lik == LK_CSR_DIRECT ? e->strip_t_dev.cstride : 0);
+      if (dev_alloc(e, r_rows * e->ld, &e->R)) return -1;
+      if (e->use_strips && e->lik == LK_CSR_DIRECT)
+        HMCB_CUDA(spmm_strip_tensor_map(e->strip_t_dev, e->R, e->ld, (long long)r_rows, &e->tmap_R));
+    }
+    {
+      const bool strips = e->use_strips && (e->lik == LK_CSR_DIRECT || e->lik == LK_CSR_PREMULT);
+      const size_t q_rows = (size_t)e->dpad + (strips ? e->strip_dev.cstride : 0);
+      for (int k = 0; k < 2; ++k) {
+        if (dev_alloc(e, q_rows * e->ld, &e->q_w[k])) return -1;
+        if (strips) HMCB_CUDA(spmm_strip_tensor_map(e->strip_dev, e->q_w[k], e->ld, (long long)q_rows, &e->tmap_q[k]));
+      }
     }
     if (e->ltiles && dev_alloc(e, (size_t)e->ltiles * e->ld, &e->lpart)) return -1;
     // small premultiplied dense models: the whole block of proposals runs in one kernel with

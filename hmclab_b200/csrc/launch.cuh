@@ -71,12 +71,15 @@ cudaError_t launch_spmm_misfit(const CsrDev& M, const double* B, int ldb, const 
 struct SpmmShape { int warps, rw, cpl; };
 int spmm_strip_shapes(const SpmmShape** out);
 cudaError_t spmm_strip_init(const StripDev& M);  // opt-in shared memory size of the mapping
-cudaError_t launch_spmm_strip_update(const StripDev& M, const double* B, int ldb, const UpdateEpi& epi,
-                                     cudaStream_t s);
-cudaError_t launch_spmm_strip_residual(const StripDev& M, const double* B, int ldb, const ResidualEpi& epi,
-                                       cudaStream_t s);
-cudaError_t launch_spmm_strip_misfit(const StripDev& M, const double* B, int ldb, const MisfitEpi& epi,
-                                     cudaStream_t s);
+// `bmap`: tensor map of the operand B for M (spmm_strip_tensor_map)
+cudaError_t spmm_strip_tensor_map(const StripDev& M, const double* B, int ldb, long long rows_allocated,
+                                  CUtensorMap* out);
+cudaError_t launch_spmm_strip_update(const StripDev& M, const CUtensorMap& bmap, const double* B, int ldb,
+                                     const UpdateEpi& epi, cudaStream_t s);
+cudaError_t launch_spmm_strip_residual(const StripDev& M, const CUtensorMap& bmap, const double* B, int ldb,
+                                       const ResidualEpi& epi, cudaStream_t s);
+cudaError_t launch_spmm_strip_misfit(const StripDev& M, const CUtensorMap& bmap, const double* B, int ldb,
+                                     const MisfitEpi& epi, cudaStream_t s);
 cudaError_t launch_st_begin(const StagedCommon& S, long long kglob, double a_mult, const double* q_cur,
                             double* q_w, double* p, const double* z_in, const double* u_step_in,
                             const double* u_acc_in, double* eps_out, double* uacc_out, double* k0part,

@@ -1,11 +1,13 @@
 // launch_spmm.cu -- launchers of the shared-memory staged CSR SpMM (spmm_strip.cuh).
+#include <cudaTypedefs.h>
+
 #include "launch.cuh"
 #include "spmm_strip.cuh"
 
 namespace hmcb {
 
 // (consumer warps, rows per warp, chains per lane); index 0 is the default mapping
-static const SpmmShape kShapes[] = {{20, 12, 2}, {16, 16, 2}, {28, 16, 1}, {16, 32, 1}};
+static const SpmmShape kShapes[] = {{20, 12, 2}, {19, 16, 2}, {23, 12, 2}, {15, 20, 2}, {15, 16, 2}, {27, 8, 2}, {31, 8, 2}};
 
 int spmm_strip_shapes(const SpmmShape** out) {
   *out = kShapes;
@@ -14,10 +16,13 @@ int spmm_strip_shapes(const SpmmShape** out) {
 
 #define HMCB_SPMM_DISPATCH(M, CALL)                                                    \
   do {                                                                                 \
-    if ((M).warps == 16 && (M).rw == 16 && (M).cpl == 2) { CALL(16, 16, 2); }          \
-    else if ((M).warps == 20 && (M).rw == 12 && (M).cpl == 2) { CALL(20, 12, 2); }     \
-    else if ((M).warps == 28 && (M).rw == 16 && (M).cpl == 1) { CALL(28, 16, 1); }     \
-    else if ((M).warps == 16 && (M).rw == 32 && (M).cpl == 1) { CALL(16, 32, 1); }     \
+    if ((M).warps == 20 && (M).rw == 12 && (M).cpl == 2) { CALL(20, 12, 2); }          \
+    else if ((M).warps == 19 && (M).rw == 16 && (M).cpl == 2) { CALL(19, 16, 2); }     \
+    else if ((M).warps == 23 && (M).rw == 12 && (M).cpl == 2) { CALL(23, 12, 2); }     \
+    else if ((M).warps == 15 && (M).rw == 20 && (M).cpl == 2) { CALL(15, 20, 2); }     \
+    else if ((M).warps == 15 && (M).rw == 16 && (M).cpl == 2) { CALL(15, 16, 2); }     \
+    else if ((M).warps == 27 && (M).rw == 8 && (M).cpl == 2) { CALL(27, 8, 2); }       \
+    else if ((M).warps == 31 && (M).rw == 8 && (M).cpl == 2) { CALL(31, 8, 2); }       \
     else return cudaErrorInvalidValue;                                                 \
   } while (0)
 
@@ -39,30 +44,59 @@ cudaError_t spmm_strip_init(const StripDev& M) {
   return init_one<MisfitEpi>(M);
 }
 
+// B [rows x ldb] (chains contiguous) as the 3-D tensor {ldb chains, T strips, ceil(rows / T) rows per
+// strip}: row c of B is (strip c % T, local row c / T).  The buffer must hold T rows of slack
+// behind `rows_allocated - T` (hmcb_finalize allocates them) so that every (strip, local row)
+// inside the tensor is backed by memory.
+cudaError_t spmm_strip_tensor_map(const StripDev& M, const double* B, int ldb, long long rows_allocated,
+                                  CUtensorMap* out) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return e;
+    if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  const unsigned long long T = (unsigned long long)M.cstride;
+  const unsigned long long J = (unsigned long long)(rows_allocated / (long long)T);
+  if (J < (unsigned long long)M.kb_box) return cudaErrorInvalidValue;
+  const cuuint64_t dims[3] = {(cuuint64_t)ldb, T, J};
+  const cuuint64_t strides[2] = {(cuuint64_t)ldb * 8ull, T * (cuuint64_t)ldb * 8ull};
+  const cuuint32_t box[3] = {(cuuint32_t)(32 * M.cpl), 1u, (cuuint32_t)M.kb_box};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(B), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <class Epi>
-static cudaError_t launch_strip(const StripDev& M, const double* B, int ldb, const Epi& epi, cudaStream_t s) {
+static cudaError_t launch_strip(const StripDev& M, const CUtensorMap& bmap, const double* B, int ldb,
+                                const Epi& epi, cudaStream_t s) {
   const int S = 32 * M.cpl;
   if (ldb % S) return cudaErrorInvalidValue;
   const dim3 grid(M.chunks, ldb / S);   // chunk index fastest: blocks in flight share a chain slab in L2
   const size_t smem = (size_t)M.stages * M.stage_bytes;
 #define HMCB_CALL(W, R, P) \
-  csr_spmm_strip_kernel<Epi, W, R, P><<<grid, (W + SPMM_PRODUCERS) * 32, smem, s>>>(M, B, ldb, epi)
+  csr_spmm_strip_kernel<Epi, W, R, P><<<grid, (W + SPMM_PRODUCERS) * 32, smem, s>>>(M, bmap, epi)
   HMCB_SPMM_DISPATCH(M, HMCB_CALL);
 #undef HMCB_CALL
   return cudaGetLastError();
 }
 
-cudaError_t launch_spmm_strip_update(const StripDev& M, const double* B, int ldb, const UpdateEpi& epi,
-                                     cudaStream_t s) {
-  return launch_strip(M, B, ldb, epi, s);
+cudaError_t launch_spmm_strip_update(const StripDev& M, const CUtensorMap& bmap, const double* B, int ldb,
+                                     const UpdateEpi& epi, cudaStream_t s) {
+  return launch_strip(M, bmap, B, ldb, epi, s);
 }
-cudaError_t launch_spmm_strip_residual(const StripDev& M, const double* B, int ldb, const ResidualEpi& epi,
-                                       cudaStream_t s) {
-  return launch_strip(M, B, ldb, epi, s);
+cudaError_t launch_spmm_strip_residual(const StripDev& M, const CUtensorMap& bmap, const double* B, int ldb,
+                                       const ResidualEpi& epi, cudaStream_t s) {
+  return launch_strip(M, bmap, B, ldb, epi, s);
 }
-cudaError_t launch_spmm_strip_misfit(const StripDev& M, const double* B, int ldb, const MisfitEpi& epi,
-                                     cudaStream_t s) {
-  return launch_strip(M, B, ldb, epi, s);
+cudaError_t launch_spmm_strip_misfit(const StripDev& M, const CUtensorMap& bmap, const double* B, int ldb,
+                                     const MisfitEpi& epi, cudaStream_t s) {
+  return launch_strip(M, bmap, B, ldb, epi, s);
 }
 
 }  // namespace hmcb

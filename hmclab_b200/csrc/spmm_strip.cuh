@@ -12,9 +12,10 @@
 //     its geometry, so the warps of a block stay balanced) and stores, per (chunk, strip), the nonzeros of the chunk's rows that
 //     fall into the strip as one flat stream per consumer warp ({value, local column offset,
 //     row within the warp} as 16 bytes, closed by a sentinel);
-//   * a producer warp stages strip after strip: the B rows of the strip with 16-byte cp.async
-//     (SASS LDGSTS) arriving on the stage's mbarrier, the nonzero streams with one bulk
-//     copy (TMA engine, SASS UBLKCP) completing on the same barrier; consumer warps release a stage through an
+//   * a producer warp stages strip after strip into a ring of stages: the B rows of the strip
+//     with ONE tensor-map TMA load (B viewed as the 3-D tensor {chains, T, rows / T}; SASS
+//     UTMALDG), the nonzero streams with one bulk copy (UBLKCP), both completing on the
+//     stage's mbarrier; consumer warps release a stage through an
 //     "empty" mbarrier, there is no block-wide barrier in the loop;
 //   * a consumer warp keeps the accumulators of its RW rows x CPL chains per lane in registers
 //     and walks its stream with the next nonzero always in flight; every load of the inner loop
@@ -28,20 +29,21 @@
 
 namespace hmcb {
 
-__device__ __forceinline__ void cp_async_16(unsigned smem_addr, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem) : "memory");
-}
-// the executing thread's earlier cp.async operations arrive on the barrier once they have completed
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(a) : "memory");
-}
+constexpr int SPMM_PRODUCERS = 1;   // one warp drives the TMA ring
 
-constexpr int SPMM_PRODUCERS = 4;   // producer warps: one warp cannot keep enough copies in flight
+// 3-D tiled TMA load (SASS UTMALDG) completing on an mbarrier: box {S chains, 1 strip, kb rows}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem);
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
+          "r"(d), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(b) : "memory");
+}
 
 template <class Epilogue, int WARPS, int RW, int CPL>
 __global__ void __launch_bounds__((WARPS + SPMM_PRODUCERS) * 32, 1)
-csr_spmm_strip_kernel(const StripDev M, const double* __restrict__ B, int ldb, Epilogue epi) {
+csr_spmm_strip_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap, Epilogue epi) {
   constexpr int S = 32 * CPL, RB = WARPS * RW;
   extern __shared__ __align__(128) unsigned char strip_smem[];
   __shared__ uint64_t full_bar[SPMM_MAX_STAGES], empty_bar[SPMM_MAX_STAGES];
@@ -54,37 +56,27 @@ csr_spmm_strip_kernel(const StripDev M, const double* __restrict__ B, int ldb, E
 
   if (tid == 0) {
     for (int st = 0; st < nstages; ++st) {
-      mbar_init(&full_bar[st], 32 * SPMM_PRODUCERS + 1);   // cp.async arrivals of every producer lane + expect_tx
+      mbar_init(&full_bar[st], 1);   // the producer's expect_tx arrival; the copies complete the bytes
       mbar_init(&empty_bar[st], WARPS);
     }
     fence_async_proxy();
   }
   __syncthreads();
 
-  if (warp >= WARPS) {   // ---- producer warps: B rows interleaved between them
-    const int pw = warp - WARPS;
-    constexpr int LPR = S * 8 / 16, RPI = 32 / LPR;   // lanes per B row, rows per warp instruction
-    const int sub = lane / LPR, part = lane % LPR;
-    const size_t rstride = (size_t)M.cstride * ldb * 8;   // bytes between consecutive B rows of a strip
+  if (warp >= WARPS) {   // ---- producer warp: one lane drives the ring
+    // B is seen as a 3-D tensor {chains, T strips, rows of a strip} (row c of B = strip c mod T,
+    // local row c / T): one tensor-map load lands the whole strip; rows past the end of B are
+    // zero filled by the engine.  The nonzero streams of the (chunk, strip) group: one bulk copy.
+    if (lane != 0) return;
     int stage = 0;
     unsigned phase = 1;  // parity of the previous use of the stage (first pass: nothing to wait for)
     for (int t = 0; t < nst; ++t) {
       if (t >= nstages) mbar_wait(&empty_bar[stage], phase);
       const int4 raw = __ldg(reinterpret_cast<const int4*>(M.strips + s_begin + t));
-      const int col0 = raw.x, ncols = raw.y, ent_off = raw.z, ent_cnt = raw.w;
       unsigned char* base = strip_smem + (size_t)stage * M.stage_bytes;
-      // B rows: 16-byte cp.async per lane (a bulk copy per 256-byte row costs ~60 cycles of the
-      // copy engine each and starves the consumers); the lane's copies arrive on the stage's
-      // barrier when they have landed.  The nonzero streams of all warps: one bulk copy.
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(base) + (unsigned)(sub * S * 8 + part * 16);
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(B + (size_t)col0 * ldb + slab0) + part * 16;
-      for (int j = pw * RPI + sub; j < ncols; j += RPI * SPMM_PRODUCERS)
-        cp_async_16(dst + (unsigned)(j - sub) * (S * 8u), src + (size_t)j * rstride);
-      cp_async_arrive_noinc(&full_bar[stage]);
-      if (pw == 0 && lane == 0) {
-        mbar_expect_tx(&full_bar[stage], (unsigned)ent_cnt * 16u);
-        bulk_copy_g2s(base + M.b_bytes, M.ent + ent_off, (unsigned)ent_cnt * 16u, &full_bar[stage]);
-      }
+      mbar_expect_tx(&full_bar[stage], (unsigned)M.kb_box * (S * 8u) + (unsigned)raw.w * 16u);
+      tma_load_3d(base, &bmap, slab0, raw.x, 0, &full_bar[stage]);
+      bulk_copy_g2s(base + M.b_bytes, M.ent + raw.z, (unsigned)raw.w * 16u, &full_bar[stage]);
       if (++stage == nstages) { stage = 0; phase ^= 1u; }
     }
     return;

@@ -1,6 +1,7 @@
 // spmm_types.cuh -- tables of the shared-memory staged CSR SpMM (kernel: spmm_strip.cuh; built by
 // upload_csr_strips in hmcb.cu).
 #pragma once
+#include <cuda.h>   // CUtensorMap
 
 namespace hmcb {
 
@@ -28,6 +29,7 @@ struct StripDev {
   int warps, rw, cpl;       // thread mapping the tables were built for
   int kb, emax, stages;     // strip limits (columns, 16-byte slots) and pipeline depth
   int b_bytes, stage_bytes;
+  int kb_box;               // rows of the TMA box = widest strip = ceil(cols / cstride) <= kb
 };
 
 constexpr int SPMM_MAX_STAGES = 4;
