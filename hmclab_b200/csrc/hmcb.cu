@@ -285,12 +285,19 @@ int upload_csr_strips(hmcb_engine* e, const HostCsr& m, const SpmmShape& shape, 
     }
   }
   const int chunks = (int)((rows + RB - 1) / RB);
-  const int W = shape.warps, RW = shape.rw, hdr = (W + 3) / 4;   // header slots (4 ints each)
+  const int W = shape.warps, RW = shape.rw;
+  // compact 8-byte nonzeros when every value survives a round trip through fp32 (the reference
+  // rounds G to numpy.single by default) and HMCB_SPMM_COMPACT does not forbid it
+  bool compact = env_int("HMCB_SPMM_COMPACT", 1) != 0 && (int64_t)kb * S * 8 < (1 << 24) && RW < 255;
+  for (size_t k = 0; compact && k < dv.size(); ++k) compact = (double)(float)dv[k] == dv[k];
+  const int esz = compact ? 8 : 16;                       // bytes per slot
+  const int hdr = ((W * 4 + 15) / 16) * 16 / esz;         // header slots: first slot of every warp
+  const int cap = emax * 16 / esz;                        // slots a stage can hold
+  const int budget = cap - hdr - W - 1;   // left for nonzeros: header, one sentinel per warp, padding
   std::vector<SpmmStrip> strips;
   std::vector<int32_t> strip_ptr(chunks + 1, 0);
-  std::vector<SpmmEntry> ent;
-  ent.reserve(ix.size() + ix.size() / 2);
-  const int budget = emax - hdr - W;   // slots left for nonzeros: header and one sentinel per warp
+  std::vector<unsigned char> ent;                         // packed groups, 16-byte aligned each
+  ent.reserve((ix.size() + ix.size() / 4) * esz);
   // strips per chunk: column c belongs to strip c % T (local index c / T); T grows until the
   // fullest (chunk, strip) group fits in the slot budget
   int64_t T = std::max<int64_t>(1, (cols + kb - 1) / kb);
@@ -321,22 +328,30 @@ int upload_csr_strips(hmcb_engine* e, const HostCsr& m, const SpmmShape& shape, 
     }
     for (int64_t t = 0; t < T; ++t) {
       if ((int)bucket[t].size() == W) continue;   // only sentinels: nothing to do in this strip
-      SpmmStrip st{(int)t, (int)((cols - t + T - 1) / T), (int)ent.size(), hdr + (int)bucket[t].size()};
-      if (st.ent_cnt > emax) return fail("internal: strip nonzero count mismatch");
       const size_t base = ent.size();
-      ent.resize(base + hdr, SpmmEntry{0.0, 0, 0});
+      const size_t bytes = (((size_t)hdr + bucket[t].size()) * esz + 15) / 16 * 16;
+      if (bytes > (size_t)emax * 16) return fail("internal: strip nonzero count mismatch");
+      ent.resize(base + bytes, 0);
       int32_t* first = reinterpret_cast<int32_t*>(&ent[base]);
       for (int w = 0; w < W; ++w) first[w] = hdr + wstart[t * W + w];
-      ent.insert(ent.end(), bucket[t].begin(), bucket[t].end());
-      strips.push_back(st);
+      unsigned char* dst = &ent[base + (size_t)hdr * esz];
+      if (compact) {
+        SpmmEntry32* o = reinterpret_cast<SpmmEntry32*>(dst);
+        for (size_t k = 0; k < bucket[t].size(); ++k)
+          o[k] = SpmmEntry32{(float)bucket[t][k].val, (unsigned)bucket[t][k].off | ((unsigned)bucket[t][k].row << 24)};
+      } else {
+        std::memcpy(dst, bucket[t].data(), bucket[t].size() * sizeof(SpmmEntry));
+      }
+      strips.push_back(SpmmStrip{(int)t, (int)((cols - t + T - 1) / T), (int)(base / 16), (int)(bytes / 16)});
     }
     strip_ptr[b + 1] = (int32_t)strips.size();
   }
   if ((cols + T - 1) / T > kb) return fail("internal: SpMM strip wider than its buffer");
-  const SpmmEntry* d_ent = nullptr; const SpmmStrip* d_strips = nullptr;
+  HMCB_CHECK(ent.size() / 16 < (size_t)1 << 31, "CSR matrix too large for the strip tables");
+  const unsigned char* d_ent = nullptr; const SpmmStrip* d_strips = nullptr;
   const int32_t* d_ptr = nullptr;
   if (dev_upload(e, ent, &d_ent) || dev_upload(e, strips, &d_strips) || dev_upload(e, strip_ptr, &d_ptr)) return -1;
-  out->ent = d_ent; out->strips = d_strips; out->strip_ptr = d_ptr;
+  out->ent = d_ent; out->compact = compact ? 1 : 0; out->strips = d_strips; out->strip_ptr = d_ptr;
   out->rows = (int)rows; out->chunks = chunks; out->cstride = (int)T;
   out->warps = shape.warps; out->rw = shape.rw; out->cpl = shape.cpl;
   out->kb = kb; out->emax = emax; out->stages = stages;
@@ -367,8 +382,9 @@ int upload_csr_both(hmcb_engine* e, const HostCsr& m, CsrDev* gather, StripDev* 
   // a single column can hold RB nonzeros of the chunk: the slot limit must leave room for them
   const int emax = std::max(RB + sh.warps + (sh.warps + 3) / 4, env_int("HMCB_SPMM_EMAX", 896));
   const int stage_bytes = kb * S * 8 + emax * 16 + 128;
-  int stages = env_int("HMCB_SPMM_STAGES", std::min(3, (220 * 1024) / stage_bytes));
-  HMCB_CHECK(kb >= 1 && stages >= 2 && stages <= SPMM_MAX_STAGES && stages * stage_bytes <= 225 * 1024,
+  // 227 KB of dynamic shared memory per block, minus the static barriers
+  int stages = env_int("HMCB_SPMM_STAGES", std::min(3, (226 * 1024) / stage_bytes));
+  HMCB_CHECK(kb >= 1 && stages >= 2 && stages <= SPMM_MAX_STAGES && stages * stage_bytes <= 226 * 1024,
              "SpMM strip configuration does not fit in shared memory");
   return upload_csr_strips(e, m, sh, kb, emax, stages, strip);
 }

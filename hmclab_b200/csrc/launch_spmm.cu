@@ -7,7 +7,7 @@
 namespace hmcb {
 
 // (consumer warps, rows per warp, chains per lane); index 0 is the default mapping
-static const SpmmShape kShapes[] = {{20, 12, 2}, {19, 16, 2}, {23, 12, 2}, {15, 20, 2}, {15, 16, 2}, {27, 8, 2}, {31, 8, 2}};
+static const SpmmShape kShapes[] = {{31, 8, 2}, {27, 8, 2}, {23, 12, 2}, {20, 12, 2}, {19, 16, 2}};
 
 int spmm_strip_shapes(const SpmmShape** out) {
   *out = kShapes;
@@ -19,8 +19,6 @@ int spmm_strip_shapes(const SpmmShape** out) {
     if ((M).warps == 20 && (M).rw == 12 && (M).cpl == 2) { CALL(20, 12, 2); }          \
     else if ((M).warps == 19 && (M).rw == 16 && (M).cpl == 2) { CALL(19, 16, 2); }     \
     else if ((M).warps == 23 && (M).rw == 12 && (M).cpl == 2) { CALL(23, 12, 2); }     \
-    else if ((M).warps == 15 && (M).rw == 20 && (M).cpl == 2) { CALL(15, 20, 2); }     \
-    else if ((M).warps == 15 && (M).rw == 16 && (M).cpl == 2) { CALL(15, 16, 2); }     \
     else if ((M).warps == 27 && (M).rw == 8 && (M).cpl == 2) { CALL(27, 8, 2); }       \
     else if ((M).warps == 31 && (M).rw == 8 && (M).cpl == 2) { CALL(31, 8, 2); }       \
     else return cudaErrorInvalidValue;                                                 \
@@ -30,8 +28,10 @@ template <class Epi>
 static cudaError_t init_one(const StripDev& M) {
   const int bytes = M.stages * M.stage_bytes;
 #define HMCB_CALL(W, R, P)                                                                       \
-  return cudaFuncSetAttribute(csr_spmm_strip_kernel<Epi, W, R, P>,                               \
-                              cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+  return M.compact ? cudaFuncSetAttribute(csr_spmm_strip_kernel<Epi, W, R, P, true>,             \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)    \
+                   : cudaFuncSetAttribute(csr_spmm_strip_kernel<Epi, W, R, P, false>,            \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
   HMCB_SPMM_DISPATCH(M, HMCB_CALL);
 #undef HMCB_CALL
   return cudaSuccess;
@@ -79,8 +79,11 @@ static cudaError_t launch_strip(const StripDev& M, const CUtensorMap& bmap, cons
   if (ldb % S) return cudaErrorInvalidValue;
   const dim3 grid(M.chunks, ldb / S);   // chunk index fastest: blocks in flight share a chain slab in L2
   const size_t smem = (size_t)M.stages * M.stage_bytes;
-#define HMCB_CALL(W, R, P) \
-  csr_spmm_strip_kernel<Epi, W, R, P><<<grid, (W + SPMM_PRODUCERS) * 32, smem, s>>>(M, bmap, epi)
+#define HMCB_CALL(W, R, P)                                                                              \
+  if (M.compact)                                                                                       \
+    csr_spmm_strip_kernel<Epi, W, R, P, true><<<grid, (W + SPMM_PRODUCERS) * 32, smem, s>>>(M, bmap, epi); \
+  else                                                                                                 \
+    csr_spmm_strip_kernel<Epi, W, R, P, false><<<grid, (W + SPMM_PRODUCERS) * 32, smem, s>>>(M, bmap, epi)
   HMCB_SPMM_DISPATCH(M, HMCB_CALL);
 #undef HMCB_CALL
   return cudaGetLastError();

@@ -41,7 +41,7 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, 
           "r"(d), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(b) : "memory");
 }
 
-template <class Epilogue, int WARPS, int RW, int CPL>
+template <class Epilogue, int WARPS, int RW, int CPL, bool COMPACT>
 __global__ void __launch_bounds__((WARPS + SPMM_PRODUCERS) * 32, 1)
 csr_spmm_strip_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap, Epilogue epi) {
   constexpr int S = 32 * CPL, RB = WARPS * RW;
@@ -76,7 +76,8 @@ csr_spmm_strip_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap
       unsigned char* base = strip_smem + (size_t)stage * M.stage_bytes;
       mbar_expect_tx(&full_bar[stage], (unsigned)M.kb_box * (S * 8u) + (unsigned)raw.w * 16u);
       tma_load_3d(base, &bmap, slab0, raw.x, 0, &full_bar[stage]);
-      bulk_copy_g2s(base + M.b_bytes, M.ent + raw.z, (unsigned)raw.w * 16u, &full_bar[stage]);
+      bulk_copy_g2s(base + M.b_bytes, reinterpret_cast<const int4*>(M.ent) + raw.z, (unsigned)raw.w * 16u,
+                    &full_bar[stage]);
       if (++stage == nstages) { stage = 0; phase ^= 1u; }
     }
     return;
@@ -96,23 +97,48 @@ csr_spmm_strip_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap
       mbar_wait(&full_bar[stage], phase);
       const unsigned char* base = strip_smem + (size_t)stage * M.stage_bytes;
       const unsigned char* Bs = base + lane * (CPL * 8);
-      const int4* Es = reinterpret_cast<const int4*>(base + M.b_bytes);
-      Es += reinterpret_cast<const int*>(Es)[warp];   // header: first slot of every warp
-      int4 e = *Es;
+      if constexpr (COMPACT) {
+        // 8-byte nonzeros {fp32 value, row << 24 | byte offset}: one LDS.64 broadcast each
+        const uint2* Es = reinterpret_cast<const uint2*>(base + M.b_bytes);
+        Es += reinterpret_cast<const int*>(Es)[warp];   // header: first slot of every warp
+        uint2 e = *Es;
 #pragma unroll
-      for (int r = 0; r < RW; ++r) {
+        for (int r = 0; r < RW; ++r) {
 #pragma unroll 1
-        while (e.w == r) {
-          const double v = __hiloint2double(e.y, e.x);
-          if constexpr (CPL == 1) {
-            const double b = *reinterpret_cast<const double*>(Bs + e.z);
-            e = *++Es;
-            acc[r][0] = fma(v, b, acc[r][0]);
-          } else {
-            const double2 b = *reinterpret_cast<const double2*>(Bs + e.z);
-            e = *++Es;
-            acc[r][0] = fma(v, b.x, acc[r][0]);
-            acc[r][1] = fma(v, b.y, acc[r][1]);
+          while ((e.y >> 24) == (unsigned)r) {
+            const double v = (double)__uint_as_float(e.x);
+            const unsigned off = e.y & 0xFFFFFFu;
+            if constexpr (CPL == 1) {
+              const double b = *reinterpret_cast<const double*>(Bs + off);
+              e = *++Es;
+              acc[r][0] = fma(v, b, acc[r][0]);
+            } else {
+              const double2 b = *reinterpret_cast<const double2*>(Bs + off);
+              e = *++Es;
+              acc[r][0] = fma(v, b.x, acc[r][0]);
+              acc[r][1] = fma(v, b.y, acc[r][1]);
+            }
+          }
+        }
+      } else {
+        const int4* Es = reinterpret_cast<const int4*>(base + M.b_bytes);
+        Es += reinterpret_cast<const int*>(Es)[warp];   // header: first slot of every warp
+        int4 e = *Es;
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+#pragma unroll 1
+          while (e.w == r) {
+            const double v = __hiloint2double(e.y, e.x);
+            if constexpr (CPL == 1) {
+              const double b = *reinterpret_cast<const double*>(Bs + e.z);
+              e = *++Es;
+              acc[r][0] = fma(v, b, acc[r][0]);
+            } else {
+              const double2 b = *reinterpret_cast<const double2*>(Bs + e.z);
+              e = *++Es;
+              acc[r][0] = fma(v, b.x, acc[r][0]);
+              acc[r][1] = fma(v, b.y, acc[r][1]);
+            }
           }
         }
       }

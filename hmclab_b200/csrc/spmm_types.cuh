@@ -15,13 +15,22 @@ struct SpmmEntry {
 };
 static_assert(sizeof(SpmmEntry) == 16, "SpmmEntry must be 16 bytes");
 
+// Compact form, used when every value of the matrix is exactly representable in fp32 (the
+// reference rounds G to numpy.single by default, LinearMatrix.py:323): 8 bytes per nonzero.
+struct SpmmEntry32 {
+  float val;
+  unsigned meta;   // bits 0-23: byte offset of the B row inside the staged strip, bits 24-31: row
+};
+static_assert(sizeof(SpmmEntry32) == 8, "SpmmEntry32 must be 8 bytes");
+
 struct SpmmStrip {
   int col0, ncols;      // B rows col0 + j * cstride, j < ncols
-  int ent_off, ent_cnt; // 16-byte slots of this (chunk, strip) group in the packed array
+  int ent_off, ent_cnt; // 16-byte units: offset and size of this (chunk, strip) group in the packed array
 };
 
 struct StripDev {
-  const SpmmEntry* ent;
+  const void* ent;          // SpmmEntry[] or SpmmEntry32[] (compact)
+  int compact;              // 1: 8-byte nonzeros
   const SpmmStrip* strips;
   const int* strip_ptr;     // [chunks + 1]
   int rows, chunks;

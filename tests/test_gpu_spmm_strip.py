@@ -1,7 +1,8 @@
 """The shared-memory staged CSR SpMM (hmclab_b200/csrc/spmm_strip.cuh) on awkward matrices:
 empty rows, a full row, a full column, a chain count that is no multiple of the slab width,
-every thread mapping the library is built with, strip limits small enough to force the
-builder's fallback (more, narrower strips), and raw C-ABI input with unsorted rows and split
+every thread mapping the library is built with, both nonzero encodings (8-byte when the values
+are exact in fp32, else 16-byte), strip limits small enough to force the builder's fallback
+(more, narrower strips), and raw C-ABI input with unsorted rows and split
 duplicate entries.  Checked against the numpy oracle evaluated chain by chain
 (misfit/gradient contract of LinearMatrix.py:389-426)."""
 import copy
@@ -61,7 +62,8 @@ def _check(plan, tree, mtree, d, chains=130, seed=3):
 
 @pytest.mark.parametrize("premult", [False, True])
 @pytest.mark.parametrize("env", [{}, {"HMCB_SPMM_SHAPE": "1"}, {"HMCB_SPMM_SHAPE": "2"},
-                                 {"HMCB_SPMM_SHAPE": "3"},
+                                 {"HMCB_SPMM_SHAPE": "3"}, {"HMCB_SPMM_SHAPE": "4"},
+                                 {"HMCB_SPMM_COMPACT": "0"},
                                  {"HMCB_SPMM_KB": "7", "HMCB_SPMM_EMAX": "1", "HMCB_SPMM_STAGES": "4"},
                                  {"HMCB_SPMM_SHAPE": "-1"}])
 def test_strip_spmm_on_awkward_matrices(monkeypatch, premult, env):
