@@ -41,6 +41,34 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, 
           "r"(d), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(b) : "memory");
 }
 
+// shared-memory loads through 32-bit shared-window addresses: with generic pointers the compiler
+// re-derives the window base (S2UR / ULEA / UMOV) inside every unrolled row of the inner loop
+__device__ __forceinline__ unsigned lds_u32(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u32x2(unsigned a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int4 lds_s32x4(unsigned a) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(unsigned a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+
 template <class Epilogue, int WARPS, int RW, int CPL, bool COMPACT>
 __global__ void __launch_bounds__((WARPS + SPMM_PRODUCERS) * 32, 1)
 csr_spmm_strip_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap, Epilogue epi) {
@@ -91,51 +119,52 @@ csr_spmm_strip_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap
     for (int h = 0; h < CPL; ++h) acc[r][h] = 0.0;
 
   {
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(strip_smem);
     int stage = 0;
     unsigned phase = 0;
     for (int t = 0; t < nst; ++t) {
       mbar_wait(&full_bar[stage], phase);
-      const unsigned char* base = strip_smem + (size_t)stage * M.stage_bytes;
-      const unsigned char* Bs = base + lane * (CPL * 8);
+      const unsigned base = smem0 + (unsigned)stage * (unsigned)M.stage_bytes;
+      const unsigned bs = base + lane * (CPL * 8);
+      unsigned es = base + (unsigned)M.b_bytes;
       if constexpr (COMPACT) {
         // 8-byte nonzeros {fp32 value, row << 24 | byte offset}: one LDS.64 broadcast each
-        const uint2* Es = reinterpret_cast<const uint2*>(base + M.b_bytes);
-        Es += reinterpret_cast<const int*>(Es)[warp];   // header: first slot of every warp
-        uint2 e = *Es;
+        es += 8u * lds_u32(es + 4u * warp);   // header: first slot of every warp
+        uint2 e = lds_u32x2(es);
 #pragma unroll
         for (int r = 0; r < RW; ++r) {
 #pragma unroll 1
-          while ((e.y >> 24) == (unsigned)r) {
+          // rows come in ascending order: "row == r" is one unsigned compare, and the row bits
+          // leave the address by a compile-time constant
+          while (e.y < ((unsigned)(r + 1) << 24)) {
             const double v = (double)__uint_as_float(e.x);
-            const unsigned off = e.y & 0xFFFFFFu;
+            const unsigned at = bs + e.y - ((unsigned)r << 24);
+            es += 8u;
+            e = lds_u32x2(es);
             if constexpr (CPL == 1) {
-              const double b = *reinterpret_cast<const double*>(Bs + off);
-              e = *++Es;
-              acc[r][0] = fma(v, b, acc[r][0]);
+              acc[r][0] = fma(v, lds_f64(at), acc[r][0]);
             } else {
-              const double2 b = *reinterpret_cast<const double2*>(Bs + off);
-              e = *++Es;
+              const double2 b = lds_f64x2(at);
               acc[r][0] = fma(v, b.x, acc[r][0]);
               acc[r][1] = fma(v, b.y, acc[r][1]);
             }
           }
         }
       } else {
-        const int4* Es = reinterpret_cast<const int4*>(base + M.b_bytes);
-        Es += reinterpret_cast<const int*>(Es)[warp];   // header: first slot of every warp
-        int4 e = *Es;
+        es += 16u * lds_u32(es + 4u * warp);
+        int4 e = lds_s32x4(es);
 #pragma unroll
         for (int r = 0; r < RW; ++r) {
 #pragma unroll 1
           while (e.w == r) {
             const double v = __hiloint2double(e.y, e.x);
+            const unsigned at = bs + (unsigned)e.z;
+            es += 16u;
+            e = lds_s32x4(es);
             if constexpr (CPL == 1) {
-              const double b = *reinterpret_cast<const double*>(Bs + e.z);
-              e = *++Es;
-              acc[r][0] = fma(v, b, acc[r][0]);
+              acc[r][0] = fma(v, lds_f64(at), acc[r][0]);
             } else {
-              const double2 b = *reinterpret_cast<const double2*>(Bs + e.z);
-              e = *++Es;
+              const double2 b = lds_f64x2(at);
               acc[r][0] = fma(v, b.x, acc[r][0]);
               acc[r][1] = fma(v, b.y, acc[r][1]);
             }
