@@ -101,3 +101,28 @@ def test_strip_spmm_accepts_unsorted_rows_and_duplicates():
     plan2["likelihood"] = lik
     g1, x1 = _check(plan2, tree, mtree, d)
     assert rel_err(g1, g0) < 1e-13 and rel_err(x1, x0) < 1e-13
+
+
+def test_strip_spmm_is_deterministic_and_equals_the_gather_kernel(monkeypatch):
+    """Many blocks per SM and several ring turns per block: repeated evaluations are bit-identical
+    (the mbarrier ring neither reads a stage early nor overwrites one late), and the independent
+    L2-gather kernel gives the same numbers up to summation order."""
+    import torch
+
+    from hmclab_b200 import workloads
+    from hmclab_b200._engine import Engine
+
+    w = workloads.tomography(nx=60, ny=50, rays=9000, chains=1500)
+    tree, mtree = describe(w.posterior), describe_mass(w.mass_matrix)
+    plan = flatten(tree)
+    q = torch.as_tensor(w.initial_models).cuda().contiguous()
+    eng = Engine(plan, mtree, w.chains, integrator="lf", amount_of_steps=2)
+    g0, x0 = eng.gradient(q).clone(), eng.misfit(q).clone()
+    for _ in range(3):
+        assert torch.equal(eng.gradient(q), g0) and torch.equal(eng.misfit(q), x0)
+    eng.close()
+    monkeypatch.setenv("HMCB_SPMM_SHAPE", "-1")
+    ref = Engine(plan, mtree, w.chains, integrator="lf", amount_of_steps=2)
+    assert rel_err(g0.cpu().numpy(), ref.gradient(q).cpu().numpy()) < 1e-12
+    assert rel_err(x0.cpu().numpy(), ref.misfit(q).cpu().numpy()) < 1e-12
+    ref.close()
