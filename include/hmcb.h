@@ -91,7 +91,10 @@ int hmcb_set_likelihood_dense_direct(hmcb_engine *e, int64_t N, const double *G,
                                      const double *sigma);
 /* LinearMatrix, sparse G, direct form (LinearMatrix.py:406-426; replaces the MKL
  * mkl_cspblas_dcsrgemv binding, InterfaceMKL.py:87-121): CSR of G [N x dims] and CSR of
- * G^T [dims x N], int32 indices, float64 values. */
+ * G^T [dims x N], int32 indices, float64 values.  Both hold nnz entries; rows need not be
+ * sorted by column and an entry may be split over several slots (they are summed).  Values that
+ * are all exact in float32 (the reference rounds G to numpy.single by default) are stored in a
+ * compact 8-byte form on the device; that changes no result. */
 int hmcb_set_likelihood_csr_direct(hmcb_engine *e, int64_t N, int64_t nnz,
                                    const int32_t *indptr, const int32_t *indices,
                                    const double *data, const int32_t *t_indptr,
