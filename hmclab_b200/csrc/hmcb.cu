@@ -260,12 +260,20 @@ int env_int(const char* name, int fallback) {
   return (v && *v) ? std::atoi(v) : fallback;
 }
 
-// Tables of the shared-memory staged SpMM (spmm_strip.cuh): per row chunk the columns are cut
-// greedily into strips of at most kb columns / emax nonzeros; per (chunk, strip) the nonzeros of
-// the chunk's rows inside the strip are stored row by row with their [begin, end) pairs.
-// Rows are sorted by column and duplicate entries summed first (scipy allows both).
-int upload_csr_strips(hmcb_engine* e, const HostCsr& m, const SpmmShape& shape, int kb, int emax,
-                      int stages, StripDev* out) {
+// Host form of the tables of the shared-memory staged SpMM (spmm_strip.cuh, spmm_types.cuh).
+struct StripHost {
+  std::vector<unsigned char> ent;      // packed (chunk, strip) groups, 16-byte aligned each
+  std::vector<SpmmStrip> strips;
+  std::vector<int32_t> strip_ptr;      // [chunks + 1]
+  int chunks = 0, cstride = 0, kb_box = 0, compact = 0;
+};
+
+// Per row chunk of RB rows the columns are dealt round-robin into T strips (column c -> strip
+// c % T, local row c / T); per (chunk, strip) group: a header with the first slot of every warp,
+// then per warp the nonzeros of its RW rows in row order and a sentinel.  Rows are sorted by
+// column and duplicate entries summed first (scipy allows both).
+int build_strip_tables(const HostCsr& m, const SpmmShape& shape, int kb, int emax, bool allow_compact,
+                       StripHost* host) {
   const int S = 32 * shape.cpl, RB = shape.warps * shape.rw;
   const int64_t rows = m.rows, cols = m.cols;
   std::vector<int32_t> ip(rows + 1, 0), ix;
@@ -288,15 +296,16 @@ int upload_csr_strips(hmcb_engine* e, const HostCsr& m, const SpmmShape& shape, 
   const int W = shape.warps, RW = shape.rw;
   // compact 8-byte nonzeros when every value survives a round trip through fp32 (the reference
   // rounds G to numpy.single by default) and HMCB_SPMM_COMPACT does not forbid it
-  bool compact = env_int("HMCB_SPMM_COMPACT", 1) != 0 && (int64_t)kb * S * 8 < (1 << 24) && RW < 255;
+  bool compact = allow_compact && (int64_t)kb * S * 8 < (1 << 24) && RW < 255;
   for (size_t k = 0; compact && k < dv.size(); ++k) compact = (double)(float)dv[k] == dv[k];
   const int esz = compact ? 8 : 16;                       // bytes per slot
   const int hdr = ((W * 4 + 15) / 16) * 16 / esz;         // header slots: first slot of every warp
   const int cap = emax * 16 / esz;                        // slots a stage can hold
   const int budget = cap - hdr - W - 1;   // left for nonzeros: header, one sentinel per warp, padding
-  std::vector<SpmmStrip> strips;
-  std::vector<int32_t> strip_ptr(chunks + 1, 0);
-  std::vector<unsigned char> ent;                         // packed groups, 16-byte aligned each
+  std::vector<SpmmStrip>& strips = host->strips;
+  std::vector<int32_t>& strip_ptr = host->strip_ptr;
+  std::vector<unsigned char>& ent = host->ent;
+  strips.clear(); ent.clear(); strip_ptr.assign(chunks + 1, 0);
   ent.reserve((ix.size() + ix.size() / 4) * esz);
   // strips per chunk: column c belongs to strip c % T (local index c / T); T grows until the
   // fullest (chunk, strip) group fits in the slot budget
@@ -348,16 +357,30 @@ int upload_csr_strips(hmcb_engine* e, const HostCsr& m, const SpmmShape& shape, 
   }
   if ((cols + T - 1) / T > kb) return fail("internal: SpMM strip wider than its buffer");
   HMCB_CHECK(ent.size() / 16 < (size_t)1 << 31, "CSR matrix too large for the strip tables");
+  host->chunks = chunks; host->cstride = (int)T; host->kb_box = (int)((cols + T - 1) / T);
+  host->compact = compact ? 1 : 0;
+  return 0;
+}
+
+int upload_csr_strips(hmcb_engine* e, const HostCsr& m, const SpmmShape& shape, int kb, int emax,
+                      int stages, StripDev* out) {
+  StripHost host;
+  if (build_strip_tables(m, shape, kb, emax, env_int("HMCB_SPMM_COMPACT", 1) != 0, &host)) return -1;
+  const int S = 32 * shape.cpl;
+  const int64_t rows = m.rows;
+  const int chunks = host.chunks;
+  const int64_t T = host.cstride;
   const unsigned char* d_ent = nullptr; const SpmmStrip* d_strips = nullptr;
   const int32_t* d_ptr = nullptr;
-  if (dev_upload(e, ent, &d_ent) || dev_upload(e, strips, &d_strips) || dev_upload(e, strip_ptr, &d_ptr)) return -1;
-  out->ent = d_ent; out->compact = compact ? 1 : 0; out->strips = d_strips; out->strip_ptr = d_ptr;
+  if (dev_upload(e, host.ent, &d_ent) || dev_upload(e, host.strips, &d_strips) ||
+      dev_upload(e, host.strip_ptr, &d_ptr)) return -1;
+  out->ent = d_ent; out->compact = host.compact; out->strips = d_strips; out->strip_ptr = d_ptr;
   out->rows = (int)rows; out->chunks = chunks; out->cstride = (int)T;
   out->warps = shape.warps; out->rw = shape.rw; out->cpl = shape.cpl;
   out->kb = kb; out->emax = emax; out->stages = stages;
   out->b_bytes = kb * S * 8;
   out->stage_bytes = (out->b_bytes + emax * 16 + 127) / 128 * 128;
-  out->kb_box = (int)((cols + T - 1) / T);
+  out->kb_box = host.kb_box;
   HMCB_CUDA(spmm_strip_init(*out));
   return 0;
 }
@@ -380,7 +403,7 @@ int upload_csr_both(hmcb_engine* e, const HostCsr& m, CsrDev* gather, StripDev* 
   // best once the B rows arrive by tensor-map TMA (profiles/spmm_lab_r01.json)
   const int kb = env_int("HMCB_SPMM_KB", 98304 / (S * 8));
   // a single column can hold RB nonzeros of the chunk: the slot limit must leave room for them
-  const int emax = std::max(RB + sh.warps + (sh.warps + 3) / 4, env_int("HMCB_SPMM_EMAX", 896));
+  const int emax = std::max(RB + sh.warps + (sh.warps + 3) / 4 + 1, env_int("HMCB_SPMM_EMAX", 896));
   const int stage_bytes = kb * S * 8 + emax * 16 + 128;
   // 227 KB of dynamic shared memory per block, minus the static barriers
   int stages = env_int("HMCB_SPMM_STAGES", std::min(3, (226 * 1024) / stage_bytes));
@@ -607,6 +630,67 @@ FusedArgs fused_args(const hmcb_engine* e, const hmcb_block* b) {
 extern "C" {
 
 int hmcb_abi_version(void) { return HMCB_ABI_VERSION; }
+
+// Host-side self check of the strip tables: builds them exactly as hmcb_finalize does and walks
+// them the way csr_spmm_strip_kernel does (strip by strip, warp stream by warp stream, up to the
+// sentinel), checking the format invariants on the way.  No GPU involved.
+int hmcb_debug_spmm_tables(int64_t rows, int64_t cols, int64_t nnz, const int32_t* indptr,
+                           const int32_t* indices, const double* data, int warps, int rw, int cpl, int kb,
+                           int emax, int allow_compact, int64_t chains, const double* B, double* Y,
+                           int64_t* info) {
+  HMCB_CHECK(indptr && B && Y && info && (nnz == 0 || (indices && data)), "hmcb_debug_spmm_tables: NULL argument");
+  HMCB_CHECK(rows > 0 && cols > 0 && nnz >= 0 && chains > 0 && warps > 0 && rw > 0 && (cpl == 1 || cpl == 2) &&
+                 kb > 0 && emax > 0, "hmcb_debug_spmm_tables: bad sizes");
+  HostCsr m;
+  m.rows = rows; m.cols = cols; m.nnz = nnz;
+  m.indptr.assign(indptr, indptr + rows + 1);
+  m.indices.assign(indices, indices + nnz);
+  m.data.assign(data, data + nnz);
+  if (check_csr(m, "matrix")) return -1;
+  const SpmmShape shape{warps, rw, cpl};
+  const int S = 32 * cpl, RB = warps * rw;
+  emax = std::max(emax, RB + warps + (warps + 3) / 4 + 1);   // the floor hmcb_finalize applies
+  StripHost host;
+  if (build_strip_tables(m, shape, kb, emax, allow_compact != 0, &host)) return -1;
+  const int esz = host.compact ? 8 : 16;
+  const int64_t T = host.cstride;
+  std::fill(Y, Y + rows * chains, 0.0);
+  HMCB_CHECK((int64_t)host.strip_ptr.size() == host.chunks + 1 && host.kb_box <= kb, "strip tables: bad sizes");
+  for (int b = 0; b < host.chunks; ++b) {
+    for (int32_t s = host.strip_ptr[b]; s < host.strip_ptr[b + 1]; ++s) {
+      const SpmmStrip& st = host.strips[s];
+      HMCB_CHECK(st.ent_cnt > 0 && st.ent_cnt <= emax && st.col0 >= 0 && st.col0 < T && st.ncols <= host.kb_box &&
+                     (size_t)(st.ent_off + st.ent_cnt) * 16 <= host.ent.size(), "strip tables: bad strip descriptor");
+      const unsigned char* group = host.ent.data() + (size_t)st.ent_off * 16;
+      const int32_t* first = reinterpret_cast<const int32_t*>(group);
+      const int slots = st.ent_cnt * 16 / esz;
+      for (int w = 0; w < warps; ++w) {
+        int slot = first[w], last_row = 0;
+        for (;;) {
+          HMCB_CHECK(slot >= 0 && slot < slots, "strip tables: stream runs out of its group");
+          double val; int64_t off; int row;
+          if (host.compact) {
+            const SpmmEntry32* en = reinterpret_cast<const SpmmEntry32*>(group) + slot;
+            val = (double)en->val; off = en->meta & 0xFFFFFFu; row = (int)(en->meta >> 24);
+          } else {
+            const SpmmEntry* en = reinterpret_cast<const SpmmEntry*>(group) + slot;
+            val = en->val; off = en->off; row = en->row;
+          }
+          ++slot;
+          if (row == rw) break;   // sentinel
+          HMCB_CHECK(row >= last_row && row < rw && off % (S * 8) == 0 && off / (S * 8) < st.ncols,
+                     "strip tables: bad nonzero");
+          last_row = row;
+          const int64_t i = (int64_t)b * RB + (int64_t)w * rw + row, j = st.col0 + off / (S * 8) * T;
+          HMCB_CHECK(i < rows && j < cols, "strip tables: nonzero outside the matrix");
+          for (int64_t c = 0; c < chains; ++c) Y[i * chains + c] += val * B[j * chains + c];
+        }
+      }
+    }
+  }
+  info[0] = T; info[1] = (int64_t)host.strips.size(); info[2] = host.compact; info[3] = (int64_t)host.ent.size();
+  return 0;
+}
 const char* hmcb_last_error(void) { return g_error.c_str(); }
 
 int hmcb_create(int device, int64_t chains, int64_t dims, hmcb_engine** out) {

@@ -43,6 +43,16 @@ enum { HMCB_PATH_FUSED_PRIORS = 0, HMCB_PATH_FUSED_SRCLOC = 1, HMCB_PATH_STAGED 
        HMCB_PATH_FUSED_DENSE = 3 /* staged workspaces + whole-proposal kernel for dims <= 128 */ };
 
 int hmcb_abi_version(void);
+
+/* Host-side self check (no GPU): builds the strip tables of the shared-memory staged CSR SpMM for
+ * the given thread mapping (warps x rw rows, cpl chains per lane) and strip limits exactly as
+ * hmcb_finalize does, verifies their format invariants and evaluates Y = A B through them the way
+ * the kernel walks them.  B [cols x chains], Y [rows x chains] row-major; info[0..3] = strips per
+ * chunk, number of (chunk, strip) groups, 1 if the compact 8-byte nonzeros are used, table bytes. */
+int hmcb_debug_spmm_tables(int64_t rows, int64_t cols, int64_t nnz, const int32_t *indptr,
+                           const int32_t *indices, const double *data, int warps, int rw, int cpl,
+                           int kb, int emax, int allow_compact, int64_t chains, const double *B,
+                           double *Y, int64_t *info);
 const char *hmcb_last_error(void);
 
 /* lifetime ------------------------------------------------------------------------- */
