@@ -154,6 +154,9 @@ class Samples:
         if self.filetype == "NPY":
             view = self._memmap.reshape(self._chains, self._per_chain, self._width)
             view[:, r0:r1, :] = block.transpose(1, 0, 2)
+        elif self._native is not None:   # memmap of the (d+1, chains * per_chain) dataset: one strided copy
+            view = self._dataset.reshape(self._width, self._chains, self._per_chain)
+            view[:, :, r0:r1] = block.transpose(2, 1, 0)
         else:
             for c in range(self._chains):
                 lo = c * self._per_chain
