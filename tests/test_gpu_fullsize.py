@@ -232,6 +232,30 @@ def test_full_size_trajectories_are_time_reversible(name):
     assert (p2 + p0).abs().max().item() < 1e-8 * p0.abs().max().item()
 
 
+def test_full_size_config4_strip_spmm_equals_l2_gather_kernel(monkeypatch):
+    """BASELINE config 4 at full size (10k cells, 50k rays, 8192 chains): the shared-memory staged
+    SpMM (TMA ring, strip tables, compact nonzeros) and the independent L2-gather kernel give the
+    same misfits and gradients up to summation order, and the staged one is bit-reproducible."""
+    import torch
+
+    from hmclab_b200._engine import Engine
+
+    w = workloads.tomography()
+    tree, mtree = describe(w.posterior), describe_mass(w.mass_matrix)
+    plan = flatten(tree)
+    q = torch.as_tensor(w.initial_models).cuda().contiguous()
+    eng = Engine(plan, mtree, w.chains, integrator=w.integrator, amount_of_steps=w.amount_of_steps)
+    g, x = eng.gradient(q), eng.misfit(q)
+    assert torch.equal(eng.gradient(q), g) and torch.equal(eng.misfit(q), x)
+    eng.close()
+    monkeypatch.setenv("HMCB_SPMM_SHAPE", "-1")
+    ref = Engine(plan, mtree, w.chains, integrator=w.integrator, amount_of_steps=w.amount_of_steps)
+    g_ref, x_ref = ref.gradient(q), ref.misfit(q)
+    assert float((g - g_ref).abs().max() / g_ref.abs().max()) < 1e-12
+    assert float(((x - x_ref).abs() / x_ref.abs()).max()) < 1e-12
+    ref.close()
+
+
 def test_single_chain_single_dimension():
     w = workloads.normal_iid(dims=1, chains=1)
     eng, ref = _compare_with_oracle(w, K=5, chains_checked=1)
