@@ -168,3 +168,55 @@ def test_hdf5_samples_file_without_h5py(tmp_path):
         assert np.array_equal(r.chain(2), data[:2, 2, :].T)
     arr, attrs = _hdf5.open_dataset(part + ".h5")
     assert os.path.getsize(part + ".h5") < _hdf5.DATA_OFFSET + 8 * 75 + 4096 and attrs["chains"] == 3
+
+
+def test_native_hdf5_attribute_kinds_and_edge_cases(tmp_path):
+    """Scalars of every kind the samplers store, arrays, non-ASCII text, long names, an empty
+    dataset, a file behind a user block, and refusal of things the reader does not cover."""
+    from hmclab_b200 import _hdf5
+
+    path = str(tmp_path / "attrs.h5")
+    w = _hdf5.Writer(path, (2, 3))
+    w.data[:] = [[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]]
+    attrs = {"i": 7, "neg": -3, "np_i": np.int32(9), "f": 0.125, "np_f": np.float32(1.5), "flag": True,
+             "text": "Hamiltonian Monte Carlo", "unicode": "étape ε=0.1", "empty": "", "none": None,
+             "vector": np.array([1.0, 2.0, 3.0]), "ints": np.arange(4), "names": np.array(["lf", "4s"]),
+             "a_rather_long_attribute_name_that_needs_padding_to_eight_bytes": 1}
+    w.close(attrs)
+    arr, got = _hdf5.open_dataset(path)
+    assert np.array_equal(arr, [[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]])
+    assert got["i"] == 7 and got["neg"] == -3 and got["np_i"] == 9 and got["flag"] == 1
+    assert got["f"] == 0.125 and got["np_f"] == 1.5
+    assert got["text"] == "Hamiltonian Monte Carlo" and got["unicode"] == "étape ε=0.1"
+    assert got["empty"] == "" and got["none"] == "None"
+    assert np.array_equal(got["vector"], [1.0, 2.0, 3.0]) and np.array_equal(got["ints"], np.arange(4))
+    assert list(got["names"]) == ["lf", "4s"]
+    assert got["a_rather_long_attribute_name_that_needs_padding_to_eight_bytes"] == 1
+    # every structure sits on an 8-byte boundary and the end-of-file address is the file size
+    with open(path, "rb") as f:
+        raw = f.read()
+    eof, root = np.frombuffer(raw[40:48], "<u8")[0], np.frombuffer(raw[64:72], "<u8")[0]
+    assert eof == len(raw) and root % 8 == 0 and raw[root] == 1
+    # empty dataset
+    empty = str(tmp_path / "empty.h5")
+    _hdf5.Writer(empty, (5, 0)).close({"write_index": 0})
+    arr, got = _hdf5.open_dataset(empty)
+    assert arr.shape == (5, 0) and got["write_index"] == 0
+    # the same file behind a 512-byte user block (as MATLAB writes them) is still found
+    shifted = str(tmp_path / "shifted.h5")
+    with open(shifted, "wb") as f:
+        f.write(b"\0" * 512)
+        sb = bytearray(raw)
+        sb[24:32] = np.array([512], "<u8").tobytes()       # base address
+        f.write(bytes(sb))
+    arr, got = _hdf5.open_dataset(shifted)
+    assert np.array_equal(arr, [[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]]) and got["i"] == 7
+    with pytest.raises(KeyError):
+        _hdf5.open_dataset(path, "missing")
+    notes = str(tmp_path / "notes.h5")
+    with open(notes, "wb") as f:
+        f.write(b"not an hdf5 file" * 10)
+    with pytest.raises(ValueError):
+        _hdf5.open_dataset(notes)
+    with pytest.raises(FileExistsError):
+        _hdf5.Writer(path, (1, 1))
