@@ -368,6 +368,17 @@ class HMC:
                 B = min(self.block_proposals, self.proposals - done)
                 if nblock == 0 and self._first_block:
                     B = min(int(self._first_block), B)
+                if self.max_time is not None:
+                    # the reference checks max_time after every proposal (Samplers.py:700-704);
+                    # here it is checked between device blocks, so blocks are sized from the
+                    # measured rate to overshoot by at most ~5 % of max_time
+                    if done == 0:
+                        B = min(B, 4 * thin)
+                    else:
+                        per_proposal = max((_time.time() - t_start) / done, 1e-9)
+                        left = max(self.max_time - (_time.time() - t_start), 0.0)
+                        fit = int(min(0.05 * self.max_time, left) / per_proposal)
+                        B = max(1, min(B, fit))
                 rows = eng.stored_rows(B, thin, done)
                 slot = nblock & 1
                 draws = {}

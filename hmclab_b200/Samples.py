@@ -82,7 +82,9 @@ class Samples:
                     raise ValueError(f"Was not able to open the samples file. Exception: {e}")
             self.burn_in = 0 if burn_in is None else burn_in
             self.last_sample = self.read_attribute("write_index")
-            if self.last_sample <= self.burn_in:
+            # a batched run stores chain after chain: burn-in is per chain, so it has to be
+            # shorter than ONE chain (a reference file holds one chain: same rule as there)
+            if self.last_sample // self._chain_count() <= self.burn_in:
                 self._closed = False
                 self.close()
                 raise ValueError(
@@ -216,11 +218,27 @@ class Samples:
                 self._dataset.attrs[key] = value
 
     # -- reading -------------------------------------------------------------------------
+    def _chain_count(self):
+        try:
+            return max(1, int(self.read_attribute("chains")))
+        except (KeyError, AttributeError):
+            return 1       # a file written by the reference: one chain
+
+    def _after_burn_in(self, data):
+        """Columns with the first ``burn_in`` samples of EVERY chain removed (a batched run
+        stores all rows of chain 0, then chain 1, ...; Samples.py:280-322 holds one chain)."""
+        chains = self._chain_count()
+        if chains == 1 or self.burn_in == 0:
+            return data[:, self.burn_in:]
+        per = data.shape[1] // chains
+        block = _numpy.asarray(data[:, : chains * per]).reshape(data.shape[0], chains, per)
+        return block[:, :, self.burn_in:].reshape(data.shape[0], chains * (per - self.burn_in))
+
     @property
     def numpy(self):
         if self.filetype == "HDF5":
-            return self._dataset[:, self.burn_in:]
-        return self._array[:, self.burn_in:]
+            return self._after_burn_in(self._dataset)
+        return self._after_burn_in(self._array)
 
     @property
     def samples(self):
@@ -229,7 +247,7 @@ class Samples:
     @property
     def misfits(self):
         if self.filetype == "HDF5":
-            return self._dataset[-1, self.burn_in:][:, None]
+            return self.numpy[-1, :][:, None]
         return self.numpy[-1, :]
 
     def __getitem__(self, key):
@@ -239,7 +257,7 @@ class Samples:
         """``(d+1, samples_per_chain)`` block of one chain of a batched run."""
         n = int(self.read_attribute("samples_per_chain"))
         data = self._dataset if self.filetype == "HDF5" else self._array
-        return data[:, index * n: (index + 1) * n]
+        return data[:, index * n + self.burn_in: (index + 1) * n]
 
     # -- lifetime ------------------------------------------------------------------------
     def close(self):

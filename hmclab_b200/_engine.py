@@ -85,6 +85,9 @@ SIGNATURES = {
     "hmcb_path": (C.c_int, [C.c_void_p]),
     "hmcb_grads_per_proposal": (C.c_int64, [C.c_void_p]),
     "hmcb_launch_count": (C.c_int64, [C.c_void_p]),
+    "hmcb_kernel_timing_begin": (C.c_int, [C.c_void_p]),
+    "hmcb_kernel_timing_end": (C.c_int, [C.c_void_p, _c_double_p, C.POINTER(C.c_int64)]),
+    "hmcb_debug_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _c_double_p, _c_double_p]),
     "hmcb_misfit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmcb_gradient": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmcb_reflect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -248,6 +251,15 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self.lib.hmcb_launch_count(self._handle))
+
+    def kernel_timing_begin(self):
+        self._ok(self.lib.hmcb_kernel_timing_begin(self._handle))
+
+    def kernel_timing_end(self):
+        """[(total_ms, passes)] for the gradient passes and the misfit passes since _begin."""
+        ms, n = (C.c_double * 2)(), (C.c_int64 * 2)()
+        self._ok(self.lib.hmcb_kernel_timing_end(self._handle, ms, n))
+        return [(float(ms[i]), int(n[i])) for i in range(2)]
 
     def set_integrator(self, integrator: str, amount_of_steps: int):
         if integrator not in INTEGRATORS:

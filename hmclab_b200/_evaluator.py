@@ -55,15 +55,28 @@ class _Evaluator:
         return self._run("scale_momentum", z)
 
 
+def _fingerprint(dist, depth=0):
+    """Cheap identity of everything `update_bounds`, `normalize`, `collapse_bounds` or
+    `add_distribution` can change on a distribution or any of its children (those methods
+    rebind the attributes, so object identities are enough; big operators are not hashed)."""
+    own = (id(dist), id(getattr(dist, "lower_bounds", None)), id(getattr(dist, "upper_bounds", None)),
+           repr(getattr(dist, "normalization_constant", None)))
+    children = getattr(dist, "separate_distributions", None) or ()
+    if depth > 16:
+        return own
+    return own + tuple(_fingerprint(c, depth + 1) for c in children)
+
+
 def evaluator_for(dist) -> _Evaluator:
     from hmclab_b200._lowering import describe, flatten
 
-    ev = dist.__dict__.get("_hmcb_evaluator")
-    if ev is None:
+    key = _fingerprint(dist)
+    cached = dist.__dict__.get("_hmcb_evaluator")
+    if cached is None or cached[0] != key:
         plan = flatten(describe(dist))
-        ev = _Evaluator(plan, {"kind": "unit", "dims": plan["dims"]})
-        dist.__dict__["_hmcb_evaluator"] = ev
-    return ev
+        cached = (key, _Evaluator(plan, {"kind": "unit", "dims": plan["dims"]}))
+        dist.__dict__["_hmcb_evaluator"] = cached
+    return cached[1]
 
 
 def mass_evaluator_for(mass) -> _Evaluator:

@@ -67,29 +67,42 @@ def _message(mtype: int, data: bytes, flags: int = 0) -> bytes:
     return struct.pack("<HHB3x", mtype, len(data), flags) + data
 
 
-def _attribute_message(name: str, value: Any) -> bytes:
+_MAX_MESSAGE = 0xFFF0       # a version 1 header message stores its size in 16 bits
+
+
+def _as_array(value: Any) -> np.ndarray:
+    """The array an attribute value is stored as (little-endian f8 / i8 / fixed-length string)."""
     if isinstance(value, (str, bytes)):
         raw = value.encode("utf-8") if isinstance(value, str) else value
-        arr = np.array(raw + b"\0", dtype=f"S{len(raw) + 1}")
-    elif isinstance(value, (bool, np.bool_)):
-        arr = np.array(int(value), dtype="<i8")
-    else:
-        arr = np.asarray(value)
-        if arr.dtype.kind == "f":
-            arr = arr.astype("<f8")
-        elif arr.dtype.kind in "iu":
-            arr = arr.astype("<i8")
-        elif arr.dtype.kind == "U":
-            enc = np.char.encode(arr, "utf-8")
-            arr = enc.astype(f"S{enc.dtype.itemsize + 1}")
-        elif arr.dtype.kind != "S":
-            raw = str(value).encode("utf-8")
-            arr = np.array(raw + b"\0", dtype=f"S{len(raw) + 1}")
+        return np.array(raw + b"\0", dtype=f"S{len(raw) + 1}")
+    if isinstance(value, (bool, np.bool_)):
+        return np.array(int(value), dtype="<i8")
+    arr = np.asarray(value)
+    if arr.dtype.kind == "f":
+        return arr.astype("<f8")
+    if arr.dtype.kind in "iu":
+        return arr.astype("<i8")
+    if arr.dtype.kind == "b":
+        return arr.astype("<i8")
+    if arr.dtype.kind == "U":
+        enc = np.char.encode(arr, "utf-8")
+        return enc.astype(f"S{enc.dtype.itemsize + 1}")
+    if arr.dtype.kind == "S":
+        return arr
+    raw = str(value).encode("utf-8")
+    return np.array(raw + b"\0", dtype=f"S{len(raw) + 1}")
+
+
+def _attribute_body(name: str, value: Any) -> bytes:
+    arr = _as_array(value)
     nm = name.encode("utf-8") + b"\0"
     dtm, dsm = _dtype_message(arr.dtype), _dataspace_message(arr.shape)
     body = struct.pack("<BBHHH", 1, 0, len(nm), len(dtm), len(dsm))
-    body += _pad8(nm) + _pad8(dtm) + _pad8(dsm) + arr.tobytes()
-    return _message(0x000C, body)
+    return body + _pad8(nm) + _pad8(dtm) + _pad8(dsm) + arr.tobytes()
+
+
+def _attribute_message(name: str, value: Any) -> bytes:
+    return _message(0x000C, _attribute_body(name, value))
 
 
 def _object_header(messages) -> bytes:
@@ -130,16 +143,37 @@ class Writer:
                               shape=self.shape) if self.shape[0] * self.shape[1] else np.zeros(self.shape)
 
     def commit(self, attributes: Dict[str, Any]):
-        """(Re)write the metadata behind the data block and point the superblock at it."""
+        """(Re)write the metadata behind the data block and point the superblock at it.
+
+        A version 1 object-header message carries a 16-bit size, so an attribute above 64 KB
+        cannot live in the dataset's header (libhdf5 has the same limit for compact attribute
+        storage).  Such attributes -- the per-proposal ``stepsizes`` / ``acceptance_rates`` of an
+        autotuned run -- are stored as root-level datasets ``<name>.<attribute>`` next to the
+        samples; :func:`open_dataset` folds them back into the attribute dictionary."""
         if isinstance(self.data, np.memmap):
             self.data.flush()
         meta0 = DATA_OFFSET + max(self._nbytes_allocated, 8)
         meta0 += -meta0 % 8
-        # local heap data segment: "" at 0 (the root's own name), the dataset name at 8, one free block
-        nm = _pad8(self.name.encode("utf-8") + b"\0")
-        heap_data_size = 8 + len(nm) + 16
-        free_off = 8 + len(nm)
-        heap_data = b"\0" * 8 + nm + struct.pack("<QQ", _HEAP_FREE_NULL, 16)
+        small, big = {}, {}
+        for k, v in attributes.items():
+            msg = _attribute_body(k, v)
+            if len(msg) + 8 > _MAX_MESSAGE:
+                big[f"{self.name}.{k}"] = _as_array(v)
+            else:
+                small[k] = msg
+        if len(big) > 2 * _GROUP_LEAF_K - 1:
+            raise ValueError("too many oversize attributes for one symbol-table node")
+        names = sorted([self.name] + list(big), key=lambda n: n.encode("utf-8"))
+        # local heap data segment: "" at 0 (the root's own name), the link names, one free block
+        heap_names, name_off, off = b"", {}, 8
+        for n in names:
+            enc = _pad8(n.encode("utf-8") + b"\0")
+            name_off[n] = off
+            heap_names += enc
+            off += len(enc)
+        heap_data_size = off + 16
+        free_off = off
+        heap_data = b"\0" * 8 + heap_names + struct.pack("<QQ", _HEAP_FREE_NULL, 16)
         btree_size = 24 + (2 * _GROUP_INTERNAL_K + 1) * 8 + 2 * _GROUP_INTERNAL_K * 8
         snod_size = 8 + 2 * _GROUP_LEAF_K * 40
         a_root = meta0
@@ -151,22 +185,42 @@ class Writer:
         root = _object_header([_message(0x0011, struct.pack("<QQ", a_btree, a_heap), flags=1),
                                _message(0x0000, b"")])
         heap = b"HEAP" + struct.pack("<B3xQQQ", 0, heap_data_size, free_off, a_heap_data)
-        btree = b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, UNDEF, UNDEF) + struct.pack("<QQQ", 0, a_snod, 8)
+
+        def header(shape, dt, data_addr, nbytes, attr_msgs=()):
+            msgs = [
+                _message(0x0001, _dataspace_message(shape)),
+                _message(0x0003, _dtype_message(dt), flags=1),
+                # fill value message exactly as libhdf5 writes its default (version 1, allocation
+                # time late, write time "if set", defined, size 0)
+                _message(0x0005, struct.pack("<BBBBI", 1, 2, 2, 1, 0)),
+                _message(0x0008, struct.pack("<BBQQ", 3, 1, data_addr, nbytes)),
+            ]
+            return _object_header(msgs + [_message(0x000C, m) for m in attr_msgs])
+
+        main = header(self.shape, np.dtype("<f8"), DATA_OFFSET, 8 * self.shape[0] * self.shape[1],
+                      small.values())
+        # oversize attributes: header + raw data, one after the other behind the main header
+        addr = {self.name: a_dset}
+        cursor = a_dset + len(main)
+        extras = b""
+        for n in names:
+            if n == self.name:
+                continue
+            arr = big[n]
+            raw = arr.tobytes()
+            probe = header(arr.shape, arr.dtype, 0, len(raw))
+            addr[n] = cursor
+            extras += header(arr.shape, arr.dtype, cursor + len(probe), len(raw)) + _pad8(raw)
+            cursor += len(probe) + len(_pad8(raw))
+        btree = b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, UNDEF, UNDEF)
+        btree += struct.pack("<QQQ", 0, a_snod, name_off[names[-1]])
         btree += b"\0" * (btree_size - len(btree))
-        snod = b"SNOD" + struct.pack("<BBH", 1, 0, 1) + struct.pack("<QQII16x", 8, a_dset, 0, 0)
+        snod = b"SNOD" + struct.pack("<BBH", 1, 0, len(names))
+        for n in names:                                     # entries sorted by link name
+            snod += struct.pack("<QQII16x", name_off[n], addr[n], 0, 0)
         snod += b"\0" * (snod_size - len(snod))
-        msgs = [
-            _message(0x0001, _dataspace_message(self.shape)),
-            _message(0x0003, _dtype_message(np.dtype("<f8")), flags=1),
-            # fill value message exactly as libhdf5 writes its default (version 1, allocation time
-            # late, write time "if set", defined, size 0)
-            _message(0x0005, struct.pack("<BBBBI", 1, 2, 2, 1, 0)),
-            _message(0x0008, struct.pack("<BBQQ", 3, 1, DATA_OFFSET, 8 * self.shape[0] * self.shape[1])),
-        ]
-        msgs += [_attribute_message(k, v) for k, v in attributes.items()]
-        dset = _object_header(msgs)
-        blob = root + heap + heap_data + btree + snod + dset
-        assert len(root) == a_heap - a_root and a_dset - meta0 == len(blob) - len(dset)
+        blob = root + heap + heap_data + btree + snod + main + extras
+        assert len(root) == a_heap - a_root and a_dset - meta0 == len(blob) - len(main) - len(extras)
         eof = meta0 + len(blob)
         sb = SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, _GROUP_LEAF_K, _GROUP_INTERNAL_K, 0)
         sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
@@ -352,12 +406,21 @@ def open_dataset(filename: str, name: str = "samples"):
     links = f.links(f.root_header)
     if name not in links:
         raise KeyError(f"{filename}: no dataset `{name}` (found {sorted(links)})")
-    dt, shape, where, attrs = f.dataset(links[name])
-    count = int(np.prod(shape)) if shape else 1
-    if where[0] == "compact":
-        arr = np.frombuffer(where[1][: count * dt.itemsize], dtype=dt).reshape(shape).copy()
-    elif count == 0 or where[1] == UNDEF:
-        arr = np.zeros(shape, dtype=dt)
-    else:
-        arr = np.memmap(filename, dtype=dt, mode="r", offset=where[1], shape=shape)
+    def load(link, mapped):
+        dt, shape, where, attrs = f.dataset(links[link])
+        count = int(np.prod(shape)) if shape else 1
+        if where[0] == "compact":
+            arr = np.frombuffer(where[1][: count * dt.itemsize], dtype=dt).reshape(shape).copy()
+        elif count == 0 or where[1] == UNDEF:
+            arr = np.zeros(shape, dtype=dt)
+        elif mapped:
+            arr = np.memmap(filename, dtype=dt, mode="r", offset=where[1], shape=shape)
+        else:
+            arr = np.fromfile(filename, dtype=dt, count=count, offset=where[1]).reshape(shape)
+        return arr, attrs
+
+    arr, attrs = load(name, True)
+    for link in links:          # oversize attributes stored as companion datasets (Writer.commit)
+        if link.startswith(name + "."):
+            attrs[link[len(name) + 1:]] = load(link, False)[0]
     return arr, attrs

@@ -12,8 +12,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
-#define HMCB_MAX_PRIORS 8
-#define HMCB_MAX_CHECKS 8
+// bound checks are tracked per chain as bits of one 32-bit word
+#define HMCB_MAX_CHECKS 32
 
 namespace hmcb {
 
@@ -37,7 +37,7 @@ struct DevTarget {
   const double* t_b;            // [n_terms x dims]
   const double* c_lb;           // [n_checks x dims]
   const double* c_ub;           // [n_checks x dims]
-  const unsigned char* c_cover; // [dims]
+  const unsigned* c_cover;      // [dims]
   const double* refl_lb;  // [dims] or null
   const double* refl_ub;  // [dims] or null
   const double* invm;     // [dims] 1/diagonal, null = unit mass

@@ -120,6 +120,10 @@ struct hmcb_engine {
   double *sh_q = nullptr, *sh_x = nullptr, *sh_buf[2] = {nullptr, nullptr};
   int32_t* sh_acc = nullptr;
   size_t sh_buf_doubles = 0;
+  // hmcb_kernel_timing_*: CUDA event pairs recorded around the launches of the dominant kernels
+  bool ktiming = false;
+  std::vector<cudaEvent_t> kev[2];   // class 0: gradient-pass / whole-block kernels, 1: misfit pass
+  size_t kev_used[2] = {0, 0};
 };
 
 namespace {
@@ -174,6 +178,29 @@ int dev_upload_tiled(hmcb_engine* e, const double* src, int64_t rows, int64_t co
   *out = p;
   return 0;
 }
+
+// Event pair around one launch of a dominant kernel (only while hmcb_kernel_timing_begin is active):
+// the events go on the launching stream, so they time the kernel and nothing else.
+struct KernelTimer {
+  hmcb_engine* e; cudaStream_t s; int cls; bool on = false;
+  static constexpr size_t kMaxPairs = 16384;
+  KernelTimer(hmcb_engine* e_, cudaStream_t s_, int cls_) : e(e_), s(s_), cls(cls_) {
+    if (!e->ktiming || e->kev_used[cls] + 2 > 2 * kMaxPairs) return;
+    if (mark()) on = true;
+  }
+  ~KernelTimer() { if (on) mark(); }
+  bool mark() {
+    std::vector<cudaEvent_t>& v = e->kev[cls];
+    size_t& used = e->kev_used[cls];
+    if (used == v.size()) {
+      cudaEvent_t ev;
+      if (cudaEventCreate(&ev) != cudaSuccess) return false;
+      v.push_back(ev);
+    }
+    cudaEventRecord(v[used++], s);
+    return true;
+  }
+};
 
 void free_device(hmcb_engine* e) {
   for (void* p : e->allocs) cudaFree(p);
@@ -439,6 +466,7 @@ inline const CUtensorMap& q_map(const hmcb_engine* e, const double* q) {
 // total gradient at q_in fused with the update described by `epi` (q_in -> epi.q_out)
 int staged_gradient_pass(hmcb_engine* e, const double* q_in, UpdateEpi epi, cudaStream_t s) {
   epi.q_in = q_in;
+  KernelTimer timer(e, s, 0);
   switch (e->lik) {
     case LK_NONE: {
       HMCB_CUDA(launch_st_update(staged_common(e, nullptr), epi, s));
@@ -488,6 +516,7 @@ int staged_gradient_pass(hmcb_engine* e, const double* q_in, UpdateEpi epi, cuda
 int staged_misfit_pass(hmcb_engine* e, const double* q, cudaStream_t s) {
   MisfitEpi m{};
   m.mode = staged_lik_mode(e); m.C = (int)e->C; m.ld = e->ld; m.q = q; m.part = e->lpart;
+  KernelTimer timer(e, s, 1);
   switch (e->lik) {
     case LK_NONE: return 0;
     case LK_DENSE_PREMULT:
@@ -722,6 +751,7 @@ int hmcb_destroy(hmcb_engine* e) {
   for (int i = 0; i < 2; ++i) {
     if (e->ev_produced[i]) cudaEventDestroy(e->ev_produced[i]);
     if (e->ev_drained[i]) cudaEventDestroy(e->ev_drained[i]);
+    for (cudaEvent_t ev : e->kev[i]) cudaEventDestroy(ev);
   }
   delete e;
   return 0;
@@ -773,7 +803,6 @@ int hmcb_add_prior(hmcb_engine* e, int kind, int64_t offset, int64_t len, const 
   HMCB_CHECK(!e->finalized, "target must be described before hmcb_finalize");
   HMCB_CHECK(kind == HMCB_PRIOR_NORMAL || kind == HMCB_PRIOR_LAPLACE, "hmcb_add_prior: unknown kind");
   HMCB_CHECK(offset >= 0 && len > 0 && offset + len <= e->d, "hmcb_add_prior: range outside [0, dims)");
-  HMCB_CHECK((int)e->priors.size() < HMCB_MAX_PRIORS, "hmcb_add_prior: too many prior terms (max 8)");
   HostPrior p;
   p.kind = kind; p.offset = offset; p.len = len; p.constant = constant;
   copy_vec(p.a, a, len); copy_vec(p.b, b, len);
@@ -787,7 +816,7 @@ int hmcb_add_bound_check(hmcb_engine* e, int64_t offset, int64_t len, const doub
   HMCB_CHECK(!e->finalized, "target must be described before hmcb_finalize");
   HMCB_CHECK(offset >= 0 && len > 0 && offset + len <= e->d, "hmcb_add_bound_check: range outside [0, dims)");
   if (!lb && !ub) return 0;
-  HMCB_CHECK((int)e->checks.size() < HMCB_MAX_CHECKS, "hmcb_add_bound_check: too many bound checks (max 8)");
+  HMCB_CHECK((int)e->checks.size() < HMCB_MAX_CHECKS, "hmcb_add_bound_check: too many bound checks (max 32 distinct bounded objects per posterior)");
   HostCheck c;
   c.offset = offset; c.len = len; c.has_lb = lb != nullptr; c.has_ub = ub != nullptr;
   c.in_gradient = in_gradient ? 1 : 0;
@@ -957,14 +986,14 @@ int hmcb_finalize(hmcb_engine* e) {
     const double inf = std::numeric_limits<double>::infinity();
     const size_t nc = (size_t)std::max(T.n_checks, 1);
     std::vector<double> clb(nc * d, -inf), cub(nc * d, inf);
-    std::vector<unsigned char> cover((size_t)d, 0);
+    std::vector<unsigned> cover((size_t)d, 0u);
     for (int k = 0; k < T.n_checks; ++k) {
       const HostCheck& Ck = e->checks[k];
       for (int64_t r = 0; r < Ck.len; ++r) {
         const size_t j = (size_t)(Ck.offset + r);
         if (Ck.has_lb) clb[(size_t)k * d + j] = Ck.lb[(size_t)r];
         if (Ck.has_ub) cub[(size_t)k * d + j] = Ck.ub[(size_t)r];
-        cover[j] |= (unsigned char)(1u << k);
+        cover[j] |= (1u << k);
       }
       if (Ck.in_gradient) T.grad_check_mask |= (1u << k);
     }
@@ -1074,6 +1103,33 @@ int hmcb_path(const hmcb_engine* e) {
 }
 int64_t hmcb_grads_per_proposal(const hmcb_engine* e) { return e ? e->S.grads_per_proposal : -1; }
 int64_t hmcb_launch_count(const hmcb_engine* e) { return e ? e->launches : -1; }
+
+int hmcb_kernel_timing_begin(hmcb_engine* e) {
+  HMCB_CHECK(e, "engine is NULL");
+  e->ktiming = true;
+  e->kev_used[0] = e->kev_used[1] = 0;
+  return 0;
+}
+
+int hmcb_kernel_timing_end(hmcb_engine* e, double* total_ms, int64_t* passes) {
+  HMCB_CHECK(e && total_ms && passes, "hmcb_kernel_timing_end: NULL argument");
+  HMCB_CUDA(cudaSetDevice(e->device));
+  e->ktiming = false;
+  for (int c = 0; c < 2; ++c) {
+    double sum = 0.0;
+    const size_t pairs = e->kev_used[c] / 2;
+    for (size_t k = 0; k < pairs; ++k) {
+      float ms = 0.f;
+      HMCB_CUDA(cudaEventSynchronize(e->kev[c][2 * k + 1]));
+      HMCB_CUDA(cudaEventElapsedTime(&ms, e->kev[c][2 * k], e->kev[c][2 * k + 1]));
+      sum += ms;
+    }
+    total_ms[c] = sum;
+    passes[c] = (int64_t)pairs;
+    e->kev_used[c] = 0;
+  }
+  return 0;
+}
 
 #define HMCB_READY(e)                                                      \
   HMCB_CHECK((e) != nullptr, "engine is NULL");                            \
@@ -1188,16 +1244,19 @@ int hmcb_run_block(hmcb_engine* e, const hmcb_block* b, void* stream) {
              "hmcb_run_block: out_q_prop and out_p_prop go together");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (e->path == HMCB_PATH_FUSED_PRIORS) {
+    KernelTimer timer(e, s, 0);
     HMCB_CUDA(launch_fused_priors(fused_args(e, b), s));
     e->launches += 1;
     return 0;
   }
   if (e->path == HMCB_PATH_FUSED_SRCLOC) {
+    KernelTimer timer(e, s, 0);
     HMCB_CUDA(launch_fused_srcloc(fused_args(e, b), e->L, s));
     e->launches += 1;
     return 0;
   }
   if (e->fused_dense) {
+    KernelTimer timer(e, s, 0);
     HMCB_CUDA(launch_fused_dense(fused_args(e, b), e->dA_rowmajor, e->dvec, e->dtd, s));
     e->launches += 1;
     return 0;

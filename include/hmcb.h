@@ -138,6 +138,19 @@ int hmcb_path(const hmcb_engine *e);
 int64_t hmcb_grads_per_proposal(const hmcb_engine *e);
 /* number of kernels launched by this engine since creation (bench bookkeeping) */
 int64_t hmcb_launch_count(const hmcb_engine *e);
+/* Device time of the dominant kernels (bench bookkeeping, measurement rule of the roofline record):
+ * between _begin and _end every gradient pass of the likelihood (the DMMA GEMM / strip SpMM
+ * launches of one gradient evaluation; for the whole-block fused kernels the one launch of
+ * hmcb_run_block) is bracketed by a CUDA event pair on the launching stream.  _end synchronises
+ * and returns total_ms[2] / passes[2]: class 0 = gradient passes (or fused blocks), class 1 = the
+ * likelihood-misfit passes of the accept/reject step. */
+int hmcb_kernel_timing_begin(hmcb_engine *e);
+int hmcb_kernel_timing_end(hmcb_engine *e, double *total_ms, int64_t *passes);
+/* fp64 roofline denominators measured on `device` (no engine needed): kind 0 = DFMA loop of the
+ * SIMT fp64 pipe, 1 = DMMA (mma.sync.m8n8k4.f64) loop of the fp64 tensor path, operands in
+ * registers; best of `launches` launches of `iters` iterations -> best_ms, flops_per_launch. */
+int hmcb_debug_fp64_peak(int device, int kind, int iters, int launches, double *best_ms,
+                         double *flops_per_launch);
 
 /* Distributions contract on a batch (DEVICE pointers) ---------------------------------
  * misfit(m) -> float, gradient(m) -> (d,1)  (base.py:71,141), one row per chain. */

@@ -1,8 +1,11 @@
 """Parity at larger sizes: (i) CUDA vs the CPU oracle on seeded inputs at sizes the oracle
-finishes in seconds, for every workload family of BASELINE.json; (ii) at BASELINE.json's
-full config-2 size through a size-independent property: the fused register-resident kernel
-and the independent staged (transposed, multi-launch) pipeline must produce the same chains
-from the same device random streams."""
+finishes in seconds, for every workload family of BASELINE.json; (ii) CUDA vs the CPU oracle at
+BASELINE.json's FULL sizes for configs 2-5 (every chain is advanced on the GPU, the oracle
+follows the first, the middle and the last chain: the full-size grids -- 25 856 SpMM blocks,
+202 row chunks, 128 chain slabs -- are where indexing bugs would hide); (iii) size-independent
+properties at full size: the fused register-resident kernel and the independent staged
+(transposed, multi-launch) pipeline produce the same chains from the same device random
+streams, trajectories are time reversible, the strip SpMM equals the L2-gather kernel."""
 import os
 
 import numpy as np
@@ -82,6 +85,18 @@ def test_config5_source_location_vs_oracle():
     w = workloads.source_location(events=16, stations=30, chains=600)
     eng, _ = _compare_with_oracle(w, K=3)
     assert eng.path == "fused_srcloc"
+
+
+@pytest.mark.parametrize("name,K", [("normal_iid", 2), ("dense_large", 1), ("dense_large_premult", 1),
+                                    ("tomography", 1), ("source_location", 2)])
+def test_full_size_config_vs_oracle(name, K):
+    """BASELINE.json configs[1..4] at their full sizes against the numpy restatement
+    (Samplers.py:1463-1492): trajectories within 1e-10, accept/reject bits identical."""
+    w = workloads.BUILDERS[name]()
+    assert w.chains >= 4096
+    eng, ref = _compare_with_oracle(w, K=K)
+    assert eng.path == {"normal_iid": "fused_priors", "source_location": "fused_srcloc"}.get(name, "staged")
+    assert np.isfinite(ref["H1"]).all()
 
 
 def test_config1_shape_vs_oracle():
@@ -187,7 +202,8 @@ def test_full_size_config2_fused_equals_staged_pipeline():
 @pytest.mark.parametrize("name", ["normal_iid", "dense_large", "dense_large_premult", "tomography",
                                   "source_location"])
 def test_full_size_trajectories_are_time_reversible(name):
-    """At BASELINE.json's full sizes (no oracle can follow there): integrating forward, flipping
+    """At BASELINE.json's full sizes, for EVERY chain (the oracle test above follows three):
+    integrating forward, flipping
     the momentum and integrating again must return every chain to its start -- a property of
     the symmetric lf/3s/4s schemes that any error in the gradient, the mass matrix, the
     stage coefficients or the chain indexing of a kernel would break."""
@@ -260,3 +276,32 @@ def test_single_chain_single_dimension():
     w = workloads.normal_iid(dims=1, chains=1)
     eng, ref = _compare_with_oracle(w, K=5, chains_checked=1)
     assert eng.path == "fused_priors"
+
+
+def test_composite_of_many_per_parameter_priors_vs_oracle():
+    """The reference's common pattern: one prior object per parameter (or small group) inside a
+    CompositeDistribution -- 12 priors, 10 of them bounded (more objects than the 8 the first
+    version of the engine accepted), top level, so the composite reflects on its children's bounds."""
+    from hmclab_b200 import Distributions as D
+    from hmclab_b200 import MassMatrices as M
+
+    rng = np.random.default_rng(12)
+    parts, dims = [], 0
+    for k in range(12):
+        n = 1 + k % 3
+        if k % 3 == 0:
+            parts.append(D.Normal(rng.normal(size=(n, 1)), rng.uniform(0.5, 2.0, size=(n, 1)),
+                                  lower_bounds=np.full((n, 1), -3.0), upper_bounds=np.full((n, 1), 3.0)))
+        elif k % 3 == 1:
+            parts.append(D.Laplace(rng.normal(size=(n, 1)), rng.uniform(0.5, 2.0, size=(n, 1)),
+                                   lower_bounds=None if k == 1 else np.full((n, 1), -4.0)))
+        else:
+            parts.append(D.Uniform(np.full((n, 1), -2.0), np.full((n, 1), 2.5)) if k != 2 else
+                         D.Normal(np.zeros((n, 1)), 1.0))
+        dims += n
+    post = D.CompositeDistribution(parts)
+    C = 64
+    w = workloads.Workload("composite12", post, M.Diagonal(rng.uniform(0.5, 2.0, size=(dims, 1))), C, "3s", 4,
+                           0.3, np.clip(rng.normal(size=(C, dims)), -1.5, 1.5), "12 per-parameter priors")
+    eng, ref = _compare_with_oracle(w, K=6, chains_checked=8)
+    assert eng.path == "fused_priors" and ref["accept"].mean() > 0

@@ -41,8 +41,12 @@ def test_roundtrip_layout_is_the_references(tmp_path):
         assert np.array_equal(s.misfits, raw.T[-1])
         assert np.array_equal(s.chain(1), data[:, 1, :].T)
         assert np.array_equal(s[:, 3], raw[3])
-    with Samples(path, burn_in=4) as s:
-        assert s.numpy.shape == (5, 11)
+    with Samples(path, burn_in=4) as s:       # burn-in is per chain: 3 chains x (5 - 4) rows stay
+        assert s.numpy.shape == (5, 3)
+        assert np.array_equal(s.numpy, data[4:, :, :].transpose(2, 1, 0).reshape(5, 3))
+        assert np.array_equal(s.chain(2), data[4:, 2, :].T)
+    with pytest.raises(ValueError, match="burn-in"):
+        Samples(path, burn_in=5)              # as long as one chain: nothing would be left
     assert combine_samples([path, path]).shape == (5, 30)
 
 
@@ -152,8 +156,10 @@ def test_hdf5_samples_file_without_h5py(tmp_path):
         assert r.read_attribute("acceptance_rate") == 0.8125
         assert r.read_attribute("sampler") == "HMC"
         assert r.read_attribute("start_time") == "2026-10-17 12:00:00.000001"
-    with Samples(path, burn_in=4) as r:
-        assert r.numpy.shape == (5, 11)
+    with Samples(path, burn_in=2) as r:      # per chain: 3 chains x (5 - 2) rows stay
+        assert r.numpy.shape == (5, 9)
+        assert np.array_equal(r.samples, data[2:, :, :-1].transpose(2, 1, 0).reshape(4, 9))
+        assert np.array_equal(r.misfits[:, 0], data[2:, :, -1].T.reshape(9))
     with pytest.raises(FileExistsError):
         Samples(path, mode="w")
     assert combine_samples([path, path]).shape == (5, 30)
@@ -168,6 +174,38 @@ def test_hdf5_samples_file_without_h5py(tmp_path):
         assert np.array_equal(r.chain(2), data[:2, 2, :].T)
     arr, attrs = _hdf5.open_dataset(part + ".h5")
     assert os.path.getsize(part + ".h5") < _hdf5.DATA_OFFSET + 8 * 75 + 4096 and attrs["chains"] == 3
+
+
+def test_native_hdf5_attributes_above_64_kb(tmp_path):
+    """An autotuned run stores per-proposal `stepsizes` / `acceptance_rates` (Samplers.py:1340-1341,
+    443-451 of the host mirror): above 64 KB they cannot be header messages; they become companion
+    datasets and come back as attributes, and the file stays readable."""
+    from hmclab_b200 import _hdf5
+    from hmclab_b200.Samples import _have_h5py
+
+    if _have_h5py():
+        pytest.skip("h5py present: the h5py backend is used")
+    path = str(tmp_path / "tuned.h5")
+    s = Samples(path, mode="w")
+    s.allocate(2, 3, 4)
+    s.write_block(np.arange(30, dtype=float).reshape(3, 2, 5))
+    steps = np.random.default_rng(1).uniform(size=(10000, 2))
+    rates = np.random.default_rng(2).uniform(size=(10000, 2))
+    s.write_attribute("stepsizes", steps)
+    s.write_attribute("acceptance_rates", rates)
+    s.write_attribute("final_stepsizes", np.ones(20000))
+    s.write_attribute("small", np.ones((7, 1)))
+    s.close()
+    with Samples(path) as r:
+        assert r.read_attribute("write_index") == 6
+        assert np.array_equal(r.read_attribute("stepsizes"), steps)
+        assert np.array_equal(r.read_attribute("acceptance_rates"), rates)
+        assert r.read_attribute("final_stepsizes").shape == (20000,)
+        assert r.read_attribute("small").shape == (7, 1)
+        assert r.numpy.shape == (5, 6)
+    f = _hdf5._File(path)
+    assert sorted(f.links(f.root_header)) == ["samples", "samples.acceptance_rates",
+                                              "samples.final_stepsizes", "samples.stepsizes"]
 
 
 def test_native_hdf5_attribute_kinds_and_edge_cases(tmp_path):
