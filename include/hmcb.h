@@ -148,7 +148,9 @@ int hmcb_kernel_timing_begin(hmcb_engine *e);
 int hmcb_kernel_timing_end(hmcb_engine *e, double *total_ms, int64_t *passes);
 /* fp64 roofline denominators measured on `device` (no engine needed): kind 0 = DFMA loop of the
  * SIMT fp64 pipe, 1 = DMMA (mma.sync.m8n8k4.f64) loop of the fp64 tensor path, operands in
- * registers; best of `launches` launches of `iters` iterations -> best_ms, flops_per_launch. */
+ * registers, 2 = fp32 -> fp64 conversions (F2F) next to one DADD each (flops_per_launch then
+ * counts conversions); best of `launches` launches of `iters` iterations -> best_ms,
+ * flops_per_launch. */
 int hmcb_debug_fp64_peak(int device, int kind, int iters, int launches, double *best_ms,
                          double *flops_per_launch);
 

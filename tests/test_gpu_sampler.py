@@ -78,7 +78,7 @@ def test_file_attributes_and_reader(tmp_path, ext):
     assert 0 < sampler.accepted_proposals <= 40 * C
     with pytest.raises(FileExistsError):
         HMC(seed=3).sample(fn, post, proposals=4, chains=C)
-    assert sampler.load_results(burn_in=2).shape == (d + 1, C * 10 - 2)
+    assert sampler.load_results(burn_in=2).shape == (d + 1, C * (10 - 2))   # burn-in is per chain
 
 
 def test_device_rng_is_reproducible_and_independent_of_sharding(tmp_path):
@@ -185,10 +185,13 @@ def test_max_time_stops_early_and_leaves_a_valid_file(tmp_path, ext):
                                  max_time=0.5, block_proposals=2000)
     assert time.time() - t0 < 30
     done = sampler.current_proposal + 1
-    assert 0 < done < 2_000_000 and done % 2000 == 0
+    # blocks are sized from the measured rate once max_time is set, so the run stops close to
+    # the limit (the reference checks after every proposal), wherever that falls inside a block
+    assert 0 < done < 2_000_000
+    assert sampler.end_time is not None and (sampler.end_time - sampler.start_time).total_seconds() < 0.5 * 1.5 + 1.0
     with Samples(fn) as s:
         per = s.read_attribute("samples_per_chain")
-        assert per == done // 1000 and s.numpy.shape == (201, 256 * per)
+        assert per == -(-done // 1000) and s.numpy.shape == (201, 256 * per)
         assert np.all(np.isfinite(s.numpy))
 
 
