@@ -52,6 +52,9 @@ SIGNATURES = {
     "hmcb_debug_spmm_tables": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _c_int32_p, _c_int32_p, _c_double_p,
                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                          _c_double_p, _c_double_p, C.POINTER(C.c_int64)]),
+    "hmcb_debug_spmm_block_tables": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _c_int32_p, _c_int32_p, _c_double_p,
+                                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                               _c_double_p, _c_double_p, C.POINTER(C.c_int64)]),
     "hmcb_last_error": (C.c_char_p, []),
     "hmcb_create": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
     "hmcb_destroy": (C.c_int, [C.c_void_p]),

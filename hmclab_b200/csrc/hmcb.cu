@@ -389,6 +389,253 @@ int build_strip_tables(const HostCsr& m, const SpmmShape& shape, int kb, int ema
   return 0;
 }
 
+// ---- row-blocked form ------------------------------------------------------------------------
+// Rows sorted by column with duplicates summed (scipy allows unsorted rows and split entries).
+void canonical_csr(const HostCsr& m, std::vector<int32_t>* ip, std::vector<int32_t>* ix, std::vector<double>* dv) {
+  ip->assign(m.rows + 1, 0); ix->clear(); dv->clear();
+  ix->reserve(m.nnz); dv->reserve(m.nnz);
+  std::vector<std::pair<int32_t, double>> row;
+  for (int64_t i = 0; i < m.rows; ++i) {
+    row.clear();
+    for (int32_t k = m.indptr[i]; k < m.indptr[i + 1]; ++k) row.emplace_back(m.indices[k], m.data[k]);
+    std::stable_sort(row.begin(), row.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    for (size_t k = 0; k < row.size(); ++k) {
+      if (k && row[k].first == row[k - 1].first) dv->back() += row[k].second;
+      else { ix->push_back(row[k].first); dv->push_back(row[k].second); }
+    }
+    (*ip)[i + 1] = (int32_t)ix->size();
+  }
+}
+
+// Groups of R rows with similar column sets, so that one gathered B row feeds several rows of a
+// group.  Greedy: the seed is the first unassigned row, its R-1 partners are the unassigned rows
+// that share the most columns with it (counted through the transpose).  order: [groups x R]
+// original row indices, -1 = padding.  Deterministic.
+void cluster_rows(int64_t rows, int64_t cols, const std::vector<int32_t>& ip, const std::vector<int32_t>& ix,
+                  int R, std::vector<int32_t>* order) {
+  std::vector<int32_t> tptr(cols + 1, 0), tidx(ix.size());
+  for (int32_t j : ix) ++tptr[j + 1];
+  for (int64_t j = 0; j < cols; ++j) tptr[j + 1] += tptr[j];
+  {
+    std::vector<int32_t> fill(tptr.begin(), tptr.end() - 1);
+    for (int64_t i = 0; i < rows; ++i)
+      for (int32_t k = ip[i]; k < ip[i + 1]; ++k) tidx[fill[ix[k]]++] = (int32_t)i;
+  }
+  std::vector<char> assigned(rows, 0);
+  std::vector<int32_t> cnt(rows, 0), touched, empty_rows;
+  order->clear();
+  order->reserve(rows + R);
+  for (int64_t seed = 0; seed < rows; ++seed) {
+    if (assigned[seed]) continue;
+    assigned[seed] = 1;
+    if (ip[seed] == ip[seed + 1]) { empty_rows.push_back((int32_t)seed); continue; }
+    touched.clear();
+    for (int32_t k = ip[seed]; k < ip[seed + 1]; ++k) {
+      const int32_t j = ix[k];
+      for (int32_t t = tptr[j]; t < tptr[j + 1]; ++t) {
+        const int32_t i = tidx[t];
+        if (!assigned[i] && cnt[i]++ == 0) touched.push_back(i);
+      }
+    }
+    const size_t want = std::min<size_t>(R - 1, touched.size());
+    std::partial_sort(touched.begin(), touched.begin() + want, touched.end(), [&](int32_t a, int32_t b) {
+      return cnt[a] != cnt[b] ? cnt[a] > cnt[b] : a < b;
+    });
+    order->push_back((int32_t)seed);
+    for (size_t k = 0; k < want; ++k) { assigned[touched[k]] = 1; order->push_back(touched[k]); }
+    for (size_t k = want; k + 1 < (size_t)R; ++k) order->push_back(-1);
+    for (int32_t i : touched) cnt[i] = 0;
+  }
+  for (size_t k = 0; k < empty_rows.size(); ++k) order->push_back(empty_rows[k]);
+  while (order->size() % R) order->push_back(-1);
+}
+
+struct BlockHost {
+  std::vector<unsigned char> ent;
+  std::vector<SpmmStrip> strips;
+  std::vector<int32_t> strip_ptr, perm;
+  int chunks = 0, cstride = 0, kb_box = 0;
+  int emax = 0;            // 16-byte units a stage reserves for the k-tiles
+  int box_rows = 0, row_boxes = 0, compact = 0;
+  int64_t blocks = 0, nnz = 0, ktiles = 0;
+};
+
+struct BlockShape { int warps, gw, nb; };
+
+// Staging geometry of a strip of `kb` B rows: row_boxes TMA boxes of box_rows rows (a box holds at
+// most 256 rows, and a multiple of 8 so that every box starts on a 1024-byte swizzle atom).
+void block_box_geometry(int64_t kb, int* box_rows, int* row_boxes) {
+  const int64_t nbr = (kb + 255) / 256;
+  *row_boxes = (int)nbr;
+  *box_rows = (int)(((kb + nbr - 1) / nbr + 7) / 8 * 8);
+}
+
+// Row-blocked tensor-core tables (spmm_types.cuh).  warps x gw groups of SPMM_BLOCK_R rows per
+// chunk; strips are dealt round-robin over the columns as in build_strip_tables.  A stage of `cap16`
+// 16-byte units holds the B rows of a strip and the k-tiles of one (chunk, strip) group: the number
+// of strips T is the smallest for which the widest strip and the fullest group fit together.
+int build_block_tables(const HostCsr& m, const BlockShape& shape, int cap16, bool allow_compact, BlockHost* host) {
+  constexpr int R = SPMM_BLOCK_R;
+  const int W = shape.warps, GW = shape.gw, NB = shape.nb, GPC = W * GW;
+  const int64_t cols = m.cols;
+  std::vector<int32_t> ip, ix;
+  std::vector<double> dv;
+  canonical_csr(m, &ip, &ix, &dv);
+  std::vector<int32_t>& order = host->perm;
+  cluster_rows(m.rows, cols, ip, ix, R, &order);
+  const int64_t groups = (int64_t)order.size() / R;
+  const int chunks = (int)((groups + GPC - 1) / GPC);
+  order.resize((size_t)chunks * GPC * R, -1);
+  bool compact = allow_compact;
+  for (size_t k = 0; compact && k < dv.size(); ++k) compact = (double)(float)dv[k] == dv[k];
+  host->compact = compact ? 1 : 0;
+  // column blocks of every group: distinct columns in ascending order, R values each
+  std::vector<int64_t> gptr(groups + 1, 0);
+  std::vector<int32_t> gcol;
+  std::vector<double> gval;
+  gcol.reserve(ix.size() / 2); gval.reserve(ix.size() / 2 * R);
+  {
+    int32_t cur[R];
+    for (int64_t g = 0; g < groups; ++g) {
+      for (int r = 0; r < R; ++r) { const int32_t i = order[g * R + r]; cur[r] = i < 0 ? -1 : ip[i]; }
+      for (;;) {
+        int32_t next = INT32_MAX;
+        for (int r = 0; r < R; ++r) {
+          const int32_t i = order[g * R + r];
+          if (i >= 0 && cur[r] < ip[i + 1]) next = std::min(next, ix[cur[r]]);
+        }
+        if (next == INT32_MAX) break;
+        gcol.push_back(next);
+        for (int r = 0; r < R; ++r) {
+          const int32_t i = order[g * R + r];
+          if (i >= 0 && cur[r] < ip[i + 1] && ix[cur[r]] == next) gval.push_back(dv[cur[r]++]);
+          else gval.push_back(0.0);
+        }
+      }
+      gptr[g + 1] = (int64_t)gcol.size();
+    }
+  }
+  host->blocks = (int64_t)gcol.size();
+  host->nnz = (int64_t)ix.size();
+  const int hdr16 = ((GPC + 1) * 4 + 15) / 16;
+  const int kt16 = 1 + (compact ? 128 : 256) / 16;      // offsets + A fragment of one k-tile
+  auto size16 = [&](int64_t n) { return (int64_t)hdr16 + n * kt16; };
+  // strips per chunk: T grows until the widest strip and the fullest (chunk, strip) group fit into a stage
+  int64_t T = std::max<int64_t>(1, (cols * NB * 8 + cap16 - 1) / cap16);
+  std::vector<int32_t> per_strip, kt;
+  int box_rows = 0, row_boxes = 0;
+  for (;;) {
+    int64_t worst = 0;
+    per_strip.assign((size_t)T, 0);
+    kt.assign((size_t)T, 0);
+    for (int b = 0; b < chunks; ++b) {
+      std::fill(kt.begin(), kt.end(), 0);
+      for (int64_t g = (int64_t)b * GPC; g < std::min<int64_t>(groups, (int64_t)(b + 1) * GPC); ++g) {
+        for (int64_t k = gptr[g]; k < gptr[g + 1]; ++k) ++per_strip[gcol[k] % T];
+        for (int64_t k = gptr[g]; k < gptr[g + 1]; ++k) {
+          int32_t& n = per_strip[gcol[k] % T];
+          if (n) { kt[gcol[k] % T] += (n + 3) / 4; n = 0; }
+        }
+      }
+      for (int64_t t = 0; t < T; ++t) worst = std::max<int64_t>(worst, kt[t]);
+    }
+    block_box_geometry((cols + T - 1) / T, &box_rows, &row_boxes);
+    const int64_t box16 = (int64_t)box_rows * row_boxes * NB * 8;
+    if (std::getenv("HMCB_DEBUG_TABLES"))
+      fprintf(stderr, "block tables: T=%lld worst=%lld k-tiles box16=%lld size16=%lld cap=%d\n", (long long)T,
+              (long long)worst, (long long)box16, (long long)size16(worst), cap16);
+    if (box16 + size16(worst) <= cap16 && worst < 1024 * 1024) { host->emax = (int)(cap16 - box16); break; }
+    if (T >= cols) return fail("internal: SpMM block strip does not fit");
+    T = std::min<int64_t>(cols, T + std::max<int64_t>(1, T / 16));
+  }
+  const int emax = host->emax;
+  const uint32_t region = (uint32_t)NB * box_rows * 128;      // bytes of one row box (all chain boxes)
+  std::vector<unsigned char>& ent = host->ent;
+  std::vector<SpmmStrip>& strips = host->strips;
+  std::vector<int32_t>& strip_ptr = host->strip_ptr;
+  ent.clear(); strips.clear(); strip_ptr.assign(chunks + 1, 0);
+  // per strip of the current chunk: k-tile offsets, A fragments (as doubles), per (warp, group) ranges
+  std::vector<std::vector<uint32_t>> boff(T);
+  std::vector<std::vector<double>> bval(T);
+  std::vector<uint32_t> first((size_t)T * GPC), count((size_t)T * GPC);
+  std::vector<std::vector<int64_t>> lists(T);     // entries of the current group per strip
+  std::vector<int64_t> q[2], tile;
+  int64_t ktiles = 0;
+  for (int b = 0; b < chunks; ++b) {
+    for (int64_t t = 0; t < T; ++t) { boff[t].clear(); bval[t].clear(); }
+    for (int s = 0; s < GPC; ++s) {
+      const int64_t g = (int64_t)b * GPC + s;
+      for (int64_t t = 0; t < T; ++t) { first[t * GPC + s] = (uint32_t)(boff[t].size() / 4); count[t * GPC + s] = 0; }
+      if (g >= groups) continue;
+      for (int64_t k = gptr[g]; k < gptr[g + 1]; ++k) lists[gcol[k] % T].push_back(k);
+      for (int64_t k0 = gptr[g]; k0 < gptr[g + 1]; ++k0) {
+        const int64_t t = gcol[k0] % T;
+        std::vector<int64_t>& L = lists[t];
+        if (L.empty()) continue;      // this strip of the group has been emitted already
+        // k-tiles of 4 columns: two staged rows with bit 2 clear + two with bit 2 set while both last
+        q[0].clear(); q[1].clear();
+        for (int64_t k : L) q[((gcol[k] / T) % box_rows >> 2) & 1].push_back(k);
+        size_t h0 = 0, h1 = 0;
+        auto emit = [&]() {
+          for (int c = 0; c < 4; ++c) {
+            if (c < (int)tile.size()) {
+              const int64_t r = gcol[tile[c]] / T, rl = r % box_rows;
+              boff[t].push_back((uint32_t)(r / box_rows) * region + (uint32_t)rl * 128u + (uint32_t)(rl & 7) * 16u);
+            } else {
+              boff[t].push_back(0u);
+            }
+          }
+          for (int l = 0; l < 32; ++l) {
+            const int c = l & 3, r = l >> 2;
+            bval[t].push_back(c < (int)tile.size() ? gval[tile[c] * R + r] : 0.0);
+          }
+          ++count[t * GPC + s];
+          tile.clear();
+        };
+        while (q[0].size() - h0 >= 2 && q[1].size() - h1 >= 2) {
+          tile = {q[0][h0], q[0][h0 + 1], q[1][h1], q[1][h1 + 1]};
+          h0 += 2; h1 += 2;
+          emit();
+        }
+        tile.clear();
+        // leftovers: keep the halves as balanced as they come
+        while (h0 < q[0].size() || h1 < q[1].size()) {
+          if (h0 < q[0].size() && (tile.size() % 2 == 0 || h1 >= q[1].size())) tile.push_back(q[0][h0++]);
+          else if (h1 < q[1].size()) tile.push_back(q[1][h1++]);
+          if (tile.size() == 4) emit();
+        }
+        if (!tile.empty()) emit();
+        L.clear();
+      }
+    }
+    for (int64_t t = 0; t < T; ++t) {
+      const int64_t n = (int64_t)boff[t].size() / 4;
+      if (n == 0) continue;
+      const size_t base = ent.size(), bytes = (size_t)size16(n) * 16;
+      if (bytes > (size_t)emax * 16) return fail("internal: block strip size mismatch");
+      ent.resize(base + bytes, 0);
+      uint32_t* hdr = reinterpret_cast<uint32_t*>(&ent[base]);
+      for (int s = 0; s < GPC; ++s) hdr[s] = (first[t * GPC + s] << 10) | count[t * GPC + s];
+      hdr[GPC] = (uint32_t)n;
+      std::memcpy(&ent[base + (size_t)hdr16 * 16], boff[t].data(), (size_t)n * 16);
+      unsigned char* a = &ent[base + (size_t)hdr16 * 16 + (size_t)n * 16];
+      if (compact) {
+        float* af = reinterpret_cast<float*>(a);
+        for (size_t k = 0; k < bval[t].size(); ++k) af[k] = (float)bval[t][k];
+      } else {
+        std::memcpy(a, bval[t].data(), bval[t].size() * sizeof(double));
+      }
+      strips.push_back(SpmmStrip{(int)t, (int)((cols - t + T - 1) / T), (int)(base / 16), (int)(bytes / 16)});
+      ktiles += n;
+    }
+    strip_ptr[b + 1] = (int32_t)strips.size();
+  }
+  HMCB_CHECK(ent.size() / 16 < (size_t)1 << 31, "CSR matrix too large for the block tables");
+  host->chunks = chunks; host->cstride = (int)T; host->kb_box = (int)((cols + T - 1) / T);
+  host->box_rows = box_rows; host->row_boxes = row_boxes; host->ktiles = ktiles;
+  return 0;
+}
+
 int upload_csr_strips(hmcb_engine* e, const HostCsr& m, const SpmmShape& shape, int kb, int emax,
                       int stages, StripDev* out) {
   StripHost host;
@@ -412,6 +659,25 @@ int upload_csr_strips(hmcb_engine* e, const HostCsr& m, const SpmmShape& shape, 
   return 0;
 }
 
+int upload_csr_blocks(hmcb_engine* e, const BlockHost& host, int rows, const BlockShape& shape, int stages,
+                      int cap16, StripDev* out) {
+  const unsigned char* d_ent = nullptr; const SpmmStrip* d_strips = nullptr;
+  const int32_t *d_ptr = nullptr, *d_perm = nullptr;
+  if (dev_upload(e, host.ent, &d_ent) || dev_upload(e, host.strips, &d_strips) ||
+      dev_upload(e, host.strip_ptr, &d_ptr) || dev_upload(e, host.perm, &d_perm)) return -1;
+  out->ent = d_ent; out->compact = host.compact; out->strips = d_strips; out->strip_ptr = d_ptr;
+  out->rows = rows; out->chunks = host.chunks; out->cstride = host.cstride;
+  out->warps = shape.warps; out->rw = SPMM_BLOCK_R * shape.gw; out->cpl = 0;
+  out->kb = host.kb_box; out->emax = host.emax; out->stages = stages;
+  out->b_bytes = host.box_rows * host.row_boxes * shape.nb * 128;
+  out->stage_bytes = cap16 * 16;
+  out->kb_box = host.kb_box;
+  out->blocked = 1; out->perm = d_perm;
+  out->gw = shape.gw; out->nb = shape.nb; out->box_rows = host.box_rows; out->row_boxes = host.row_boxes;
+  HMCB_CUDA(spmm_strip_init(*out));
+  return 0;
+}
+
 // Chooses the SpMM path for the CSR likelihoods: the shared-memory staged kernel in the mapping
 // and strip limits that measured best on the tomography workload (profiles/spmm_lab_r01.json).
 // profiles/tools/spmm_lab.py overrides them through the environment: HMCB_SPMM_SHAPE = 0..n-1 picks
@@ -424,6 +690,27 @@ int upload_csr_both(hmcb_engine* e, const HostCsr& m, CsrDev* gather, StripDev* 
   e->use_strips = which >= 0;
   if (!e->use_strips) return upload_csr(e, m, gather);
   HMCB_CHECK(which < n_shapes, "HMCB_SPMM_SHAPE out of range");
+  // Row-blocked form first (HMCB_SPMM_BLOCKED: -1 = when it pays, 0 = never, 1 = always): rows are
+  // regrouped into groups of 8 with similar column sets; it pays when a gathered B row then feeds
+  // enough rows of its group, i.e. when the 9 shared-memory wavefronts of a column block buy more
+  // than the 5 per nonzero of the plain strip kernel.
+  const int want_blocked = env_int("HMCB_SPMM_BLOCKED", -1);
+  if (want_blocked != 0) {
+    const BlockShape bs{env_int("HMCB_SPMM_BLOCK_WARPS", 31), env_int("HMCB_SPMM_BLOCK_GW", 4),
+                        env_int("HMCB_SPMM_BLOCK_NB", 1)};
+    HMCB_CHECK(spmm_block_shape_supported(bs.warps, bs.gw, bs.nb), "HMCB_SPMM_BLOCK_*: not a built mapping");
+    const int stages = env_int("HMCB_SPMM_STAGES", 2);
+    HMCB_CHECK(stages >= 2 && stages <= SPMM_MAX_STAGES, "HMCB_SPMM_STAGES out of range");
+    // a stage = the B rows of a strip + the k-tiles of one (chunk, strip) group; stages start on
+    // 1024-byte swizzle atoms
+    const int cap16 = ((225 * 1024) / stages) / 1024 * 64;
+    BlockHost host;
+    if (build_block_tables(m, bs, cap16, env_int("HMCB_SPMM_COMPACT", 1) != 0, &host)) return -1;
+    // it pays when a gathered B row feeds enough rows of its group: a k-tile (4 columns x 8 rows on the
+    // tensor pipe) has to carry more nonzeros than the plain kernel turns over in the same time
+    if (want_blocked > 0 || (host.ktiles > 0 && (double)host.nnz >= 6.0 * (double)host.ktiles))
+      return upload_csr_blocks(e, host, (int)m.rows, bs, stages, cap16, strip);
+  }
   const SpmmShape sh = shapes[which];
   const int S = 32 * sh.cpl, RB = sh.warps * sh.rw;
   // two stages of (96 KB of B rows + 14 KB of nonzero slots): the widest strips that fit measured
@@ -718,6 +1005,95 @@ int hmcb_debug_spmm_tables(int64_t rows, int64_t cols, int64_t nnz, const int32_
     }
   }
   info[0] = T; info[1] = (int64_t)host.strips.size(); info[2] = host.compact; info[3] = (int64_t)host.ent.size();
+  return 0;
+}
+// Same self check for the row-blocked tensor-core tables: clusters the rows, builds the tables as
+// hmcb_finalize does and walks them the way csr_spmm_block_kernel does (strip by strip, (warp, group)
+// by (warp, group), k-tile by k-tile, undoing the swizzled offsets).  No GPU involved.
+int hmcb_debug_spmm_block_tables(int64_t rows, int64_t cols, int64_t nnz, const int32_t* indptr,
+                                 const int32_t* indices, const double* data, int warps, int groups_per_warp,
+                                 int chain_boxes, int cap16, int allow_compact, int64_t chains, const double* B,
+                                 double* Y, int64_t* info) {
+  HMCB_CHECK(indptr && B && Y && info && (nnz == 0 || (indices && data)), "hmcb_debug_spmm_block_tables: NULL argument");
+  HMCB_CHECK(rows > 0 && cols > 0 && nnz >= 0 && chains > 0 && warps > 0 && groups_per_warp > 0 && chain_boxes > 0 &&
+                 cap16 > 0, "hmcb_debug_spmm_block_tables: bad sizes");
+  constexpr int R = SPMM_BLOCK_R;
+  HostCsr m;
+  m.rows = rows; m.cols = cols; m.nnz = nnz;
+  m.indptr.assign(indptr, indptr + rows + 1);
+  m.indices.assign(indices, indices + nnz);
+  m.data.assign(data, data + nnz);
+  if (check_csr(m, "matrix")) return -1;
+  const BlockShape shape{warps, groups_per_warp, chain_boxes};
+  const int GPC = warps * groups_per_warp;
+  BlockHost host;
+  if (build_block_tables(m, shape, cap16, allow_compact != 0, &host)) return -1;
+  const int64_t T = host.cstride;
+  const int hdr16 = ((GPC + 1) * 4 + 15) / 16;
+  const int asz = host.compact ? 128 : 256, kt16 = 1 + asz / 16;
+  const int64_t region = (int64_t)chain_boxes * host.box_rows * 128;
+  HMCB_CHECK(host.box_rows % 8 == 0 && host.box_rows <= 256 && host.box_rows * host.row_boxes >= host.kb_box &&
+                 (int64_t)host.box_rows * host.row_boxes * chain_boxes * 8 + host.emax <= cap16,
+             "block tables: stage overflows");
+  std::fill(Y, Y + rows * chains, 0.0);
+  HMCB_CHECK((int64_t)host.strip_ptr.size() == host.chunks + 1 &&
+                 (int64_t)host.perm.size() == (int64_t)host.chunks * GPC * R, "block tables: bad sizes");
+  {   // the permutation holds every row exactly once
+    std::vector<char> seen(rows, 0);
+    for (int32_t i : host.perm) {
+      if (i < 0) continue;
+      HMCB_CHECK(i < rows && !seen[i], "block tables: bad permutation");
+      seen[i] = 1;
+    }
+    for (int64_t i = 0; i < rows; ++i) HMCB_CHECK(seen[i], "block tables: a row is missing from the permutation");
+  }
+  int64_t ktiles = 0, balanced = 0;
+  for (int b = 0; b < host.chunks; ++b) {
+    for (int32_t s = host.strip_ptr[b]; s < host.strip_ptr[b + 1]; ++s) {
+      const SpmmStrip& st = host.strips[s];
+      HMCB_CHECK(st.ent_cnt > 0 && st.ent_cnt <= host.emax && st.col0 >= 0 && st.col0 < T && st.ncols <= host.kb_box &&
+                     (size_t)(st.ent_off + st.ent_cnt) * 16 <= host.ent.size(), "block tables: bad strip descriptor");
+      const unsigned char* group = host.ent.data() + (size_t)st.ent_off * 16;
+      const uint32_t* hdr = reinterpret_cast<const uint32_t*>(group);
+      const int64_t total = hdr[GPC];
+      HMCB_CHECK(total > 0 && (int64_t)hdr16 + total * kt16 == st.ent_cnt, "block tables: group size mismatch");
+      const uint32_t* off = reinterpret_cast<const uint32_t*>(group + (size_t)hdr16 * 16);
+      const unsigned char* afr = group + (size_t)hdr16 * 16 + (size_t)total * 16;
+      int64_t sum = 0;
+      for (int wg = 0; wg < GPC; ++wg) {
+        const int64_t first = hdr[wg] >> 10, n = hdr[wg] & 1023u;
+        HMCB_CHECK(first == sum && first + n <= total, "block tables: (warp, group) ranges are not consecutive");
+        sum += n;
+        for (int64_t k = first; k < first + n; ++k) {
+          int hi = 0, used = 0;
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t o = off[k * 4 + c];
+            const int64_t rb = o / region, rem = o % region, rl = rem / 128;
+            HMCB_CHECK(rb < host.row_boxes && rl < host.box_rows && rem % 128 == (rl & 7) * 16,
+                       "block tables: bad swizzled offset");
+            const int64_t j = st.col0 + (rb * host.box_rows + rl) * T;
+            bool any = false;
+            for (int r = 0; r < R; ++r) {
+              const double v = host.compact ? (double)reinterpret_cast<const float*>(afr + (size_t)k * asz)[r * 4 + c]
+                                            : reinterpret_cast<const double*>(afr + (size_t)k * asz)[r * 4 + c];
+              if (v == 0.0) continue;
+              any = true;
+              const int32_t i = host.perm[((size_t)b * GPC + wg) * R + r];
+              HMCB_CHECK(i >= 0 && j < cols, "block tables: value on a padding row or outside the matrix");
+              for (int64_t ch = 0; ch < chains; ++ch) Y[i * chains + ch] = std::fma(v, B[j * chains + ch], Y[i * chains + ch]);
+            }
+            if (any) { ++used; hi += (int)((rl >> 2) & 1); }
+          }
+          if (used == 4 && hi == 2) ++balanced;
+        }
+      }
+      HMCB_CHECK(sum == total, "block tables: k-tile count mismatch");
+      ktiles += total;
+    }
+  }
+  HMCB_CHECK(ktiles == host.ktiles, "block tables: total k-tile count mismatch");
+  info[0] = T; info[1] = (int64_t)host.strips.size(); info[2] = host.blocks; info[3] = (int64_t)host.ent.size();
+  info[4] = host.nnz; info[5] = host.ktiles; info[6] = balanced; info[7] = host.compact;
   return 0;
 }
 const char* hmcb_last_error(void) { return g_error.c_str(); }

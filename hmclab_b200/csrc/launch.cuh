@@ -70,6 +70,7 @@ cudaError_t launch_spmm_misfit(const CsrDev& M, const double* B, int ldb, const 
 // thread mappings (consumer warps, rows per warp, chains per lane) the library is built with
 struct SpmmShape { int warps, rw, cpl; };
 int spmm_strip_shapes(const SpmmShape** out);
+bool spmm_block_shape_supported(int warps, int gw, int nb);   // row-blocked kernel (csr_spmm_block_kernel)
 cudaError_t spmm_strip_init(const StripDev& M);  // opt-in shared memory size of the mapping
 // `bmap`: tensor map of the operand B for M (spmm_strip_tensor_map)
 cudaError_t spmm_strip_tensor_map(const StripDev& M, const double* B, int ldb, long long rows_allocated,

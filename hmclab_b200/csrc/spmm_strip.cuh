@@ -198,4 +198,172 @@ csr_spmm_strip_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap
   for (int h = 0; h < CPL; ++h) ep[h].chunk_end(chunk * WARPS + warp, c0 + h);
 }
 
+
+// ---- row-blocked tensor-core variant -----------------------------------------------------------
+// The kernel above gathers one 8-byte B element from shared memory per FMA: the shared-memory data
+// pipe (5 wavefronts per nonzero and 64 chains) and the issue slots (18 instructions per nonzero)
+// bind, the fp64 pipe idles at 17 %.  Broadcasting the matrix values costs a wavefront per 8 bytes
+// as well (a SIMT kernel with 8-row register blocking measured slower than the plain one), so the
+// operand reuse has to happen inside an instruction: the fp64 tensor core.
+//
+// hmcb_finalize regroups the rows into groups of 8 rows with similar column sets (cluster_rows in
+// hmcb.cu; rays that run side by side cross the same cells).  A group is one DMMA M-tile; a k-tile
+// is 4 columns of the group with its 8 x 4 A fragment stored in fragment order (zeros where a row
+// has no entry): one conflict-free per-lane load delivers 32 matrix values, one per-lane load the B
+// fragment (4 gathered rows x 8 chains), one mma.sync.m8n8k4.f64 does the 256 FMAs.
+//   * slab = 16 NB chains; B strips arrive as NB 128-byte-swizzled tensor-map TMA boxes
+//     {16 chains, 1 strip, box_rows rows} (per row box), so the 4 gathered rows of a k-tile -- chosen
+//     by the host with two of them in each half of the swizzle period -- cover every bank exactly
+//     twice;
+//   * a consumer warp owns GW groups (8 GW rows): 2 NB GW accumulator pairs per lane, and with the
+//     narrow slab a block covers WARPS x GW x 8 rows -- 4x the rows of the plain kernel, so 4x less
+//     L2 -> shared-memory staging of B per useful flop;
+//   * the grid interleaves the slabs of 128 chains per chunk so that a chunk's tables are re-read from L2.
+// Per k-tile and 16 chains: 2 table loads + 2 B loads + 2 DMMA + ~6 integer instructions; the tensor
+// pipe binds (4 cycles per DMMA and SM) at the matrix's 8 x 1 block fill.
+constexpr int SPMM_SLAB_CHAINS_MINOR = 128;   // chains covered by the interleaved slabs of one chunk
+
+__device__ __forceinline__ float lds_f32(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(a));
+  return v;
+}
+
+template <class Epilogue, int WARPS, int GW, int NB, bool COMPACT>
+__global__ void __launch_bounds__((WARPS + SPMM_PRODUCERS) * 32, 1)
+csr_spmm_block_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap, Epilogue epi) {
+  constexpr int S = 16 * NB, NT = 2 * NB, R = SPMM_BLOCK_R, GPC = WARPS * GW;
+  constexpr unsigned HDR = (unsigned)(((GPC + 1) * 4 + 15) / 16 * 16);   // header bytes
+  constexpr unsigned ASZ = COMPACT ? 128u : 256u;                         // bytes of an A fragment
+  extern __shared__ __align__(1024) unsigned char strip_smem[];
+  __shared__ uint64_t full_bar[SPMM_MAX_STAGES], empty_bar[SPMM_MAX_STAGES];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int SL = SPMM_SLAB_CHAINS_MINOR / S;   // slabs interleaved per chunk (ld is a multiple of 128)
+  const int chunk = blockIdx.x / SL;
+  const int slab0 = (blockIdx.y * SL + blockIdx.x % SL) * S;
+  const int s_begin = __ldg(M.strip_ptr + chunk);
+  const int nst = __ldg(M.strip_ptr + chunk + 1) - s_begin;
+  const int nstages = M.stages;
+  // the dynamic shared memory window is only guaranteed 16-byte aligned: round up to a swizzle atom
+  const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(strip_smem) + 1023u) & ~1023u;
+
+  if (tid == 0) {
+    for (int st = 0; st < nstages; ++st) {
+      mbar_init(&full_bar[st], 1);
+      mbar_init(&empty_bar[st], WARPS);
+    }
+    fence_async_proxy();
+  }
+  __syncthreads();
+
+  if (warp >= WARPS) {   // ---- producer warp: one lane drives the ring
+    if (lane != 0) return;
+    int stage = 0;
+    unsigned phase = 1;
+    const unsigned box_bytes = (unsigned)M.box_rows * 128u;
+    for (int t = 0; t < nst; ++t) {
+      if (t >= nstages) mbar_wait(&empty_bar[stage], phase);
+      const int4 raw = __ldg(reinterpret_cast<const int4*>(M.strips + s_begin + t));
+      const unsigned base = smem0 + (unsigned)stage * (unsigned)M.stage_bytes;
+      const unsigned bar = (unsigned)__cvta_generic_to_shared(&full_bar[stage]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
+                   "r"((unsigned)M.b_bytes + (unsigned)raw.w * 16u) : "memory");
+      for (int rb = 0; rb < M.row_boxes; ++rb)
+#pragma unroll
+        for (int cb = 0; cb < NB; ++cb)
+          asm volatile(
+              "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
+                  "r"(base + (unsigned)(rb * NB + cb) * box_bytes), "l"(&bmap), "r"(slab0 + 16 * cb), "r"(raw.x),
+                  "r"(rb * M.box_rows), "r"(bar) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+                       "r"(base + (unsigned)M.b_bytes), "l"(reinterpret_cast<const int4*>(M.ent) + raw.z),
+                   "r"((unsigned)raw.w * 16u), "r"(bar) : "memory");
+      if (++stage == nstages) { stage = 0; phase ^= 1u; }
+    }
+    return;
+  }
+
+  // ---- consumer warps: groups (chunk * WARPS + warp) * GW + g; lane holds C[row lane / 4][chains 2 (lane % 4) + {0, 1}]
+  double acc[GW][NT][2];
+#pragma unroll
+  for (int g = 0; g < GW; ++g)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[g][j][0] = acc[g][j][1] = 0.0;
+
+  {
+    // B fragment: lane holds B[k = lane % 4][chain n = lane / 4]; with the 128-byte swizzle the 16-byte
+    // granule index of chain n is XORed with (row & 7) -- the host stores row * 128 + (row & 7) * 16,
+    // the lane XORs its own granule and adds the half granule
+    const unsigned lconst = ((unsigned)(lane >> 3) << 4) | (((unsigned)(lane >> 2) & 1u) << 3);
+    const unsigned box_bytes = (unsigned)M.box_rows * 128u;
+    int stage = 0;
+    unsigned phase = 0;
+    for (int t = 0; t < nst; ++t) {
+      mbar_wait(&full_bar[stage], phase);
+      const unsigned base = smem0 + (unsigned)stage * (unsigned)M.stage_bytes;
+      const unsigned es = base + (unsigned)M.b_bytes;
+      const unsigned total = lds_u32(es + 4u * GPC);
+      const unsigned off0 = es + HDR + 4u * (lane & 3), a0 = es + HDR + 16u * total + (COMPACT ? 4u : 8u) * lane;
+#pragma unroll
+      for (int g = 0; g < GW; ++g) {
+        const unsigned mine = lds_u32(es + 4u * (warp * GW + g));
+        int n = (int)(mine & 1023u);
+        unsigned op = off0 + 16u * (mine >> 10), ap = a0 + ASZ * (mine >> 10);
+#pragma unroll 2
+        for (; n > 0; --n) {
+          const unsigned x = base + (lds_u32(op) ^ lconst);
+          double a;
+          if constexpr (COMPACT) a = (double)lds_f32(ap);
+          else a = lds_f64(ap);
+          op += 16u; ap += ASZ;
+#pragma unroll
+          for (int cb = 0; cb < NB; ++cb) {
+            const double b0 = lds_f64(x + cb * box_bytes), b1 = lds_f64((x ^ 64u) + cb * box_bytes);
+            dmma_8x8x4(acc[g][2 * cb][0], acc[g][2 * cb][1], a, b0);
+            dmma_8x8x4(acc[g][2 * cb + 1][0], acc[g][2 * cb + 1][1], a, b1);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == nstages) { stage = 0; phase ^= 1u; }
+    }
+  }
+
+  // ---- epilogue: block row -> original row through the permutation
+  const int brow0 = (chunk * WARPS + warp) * GW * R + (lane >> 2);
+  const int c0 = slab0 + 2 * (lane & 3);
+  if constexpr (Epilogue::kPerChainSum) {
+    // per-chain sums over the warp's rows: the rows of a chain sit in the 8 lanes with equal lane % 4
+    int rows[GW];
+#pragma unroll
+    for (int g = 0; g < GW; ++g) rows[g] = __ldg(M.perm + brow0 + g * R);
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double v = 0.0;
+#pragma unroll
+        for (int g = 0; g < GW; ++g)
+          if (rows[g] >= 0) v = __dadd_rn(v, epi.term(rows[g], c0 + 8 * j + h, acc[g][j][h]));
+        v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
+        v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 8));
+        v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 16));
+        if (lane < 4 && c0 + 8 * j + h < epi.ld) epi.part[(size_t)(chunk * WARPS + warp) * epi.ld + c0 + 8 * j + h] = v;
+      }
+  } else {
+#pragma unroll
+    for (int g = 0; g < GW; ++g) {
+      const int i = __ldg(M.perm + brow0 + g * R);
+      if (i < 0) continue;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        epi.row(i, c0 + 8 * j, acc[g][j][0]);
+        epi.row(i, c0 + 8 * j + 1, acc[g][j][1]);
+      }
+    }
+  }
+}
+
 }  // namespace hmcb

@@ -39,8 +39,30 @@ struct StripDev {
   int kb, emax, stages;     // strip limits (columns, 16-byte slots) and pipeline depth
   int b_bytes, stage_bytes;
   int kb_box;               // rows of the TMA box = widest strip = ceil(cols / cstride) <= kb
+  // row-blocked tensor-core form (csr_spmm_block_kernel): rows are regrouped into groups of
+  // SPMM_BLOCK_R = 8 rows with similar column sets (one DMMA M-tile), `gw` groups per consumer warp;
+  // `ent` then holds k-tiles of 4 columns with their 8 x 4 A fragments
+  int blocked;              // 1: the tables below are in the row-blocked format
+  const int* perm;          // [chunks x warps x gw x SPMM_BLOCK_R] original row of every block row, -1 = padding
+  int gw;                   // row groups per consumer warp
+  int nb;                   // 16-chain TMA boxes per slab (slab = 16 nb chains = 2 nb DMMA N-tiles)
+  int box_rows, row_boxes;  // a strip is staged as row_boxes x nb boxes of box_rows rows x 128 bytes
 };
 
 constexpr int SPMM_MAX_STAGES = 4;
+
+// Row-blocked tables.  A (chunk, strip) group is, in 16-byte units:
+//   header  : (warps x gw + 1) u32 -- per (warp, group) (first k-tile << 10 | number of k-tiles), then
+//             the group's total number of k-tiles n; padded to 16 bytes
+//   offsets : n x 4 u32 -- for the 4 columns of every k-tile the byte offset of its B row inside the
+//             staged strip with the 128-byte TMA swizzle of the row already applied
+//             (row_box * nb * box_rows * 128 + r * 128 + (r & 7) * 16, r = row inside the box)
+//   A       : n x 32 values in DMMA fragment order (lane l holds A[row l / 4][column l % 4] of the
+//             8 x 4 tile; 0.0 where the matrix has no entry), fp32 when every value of the matrix is
+//             exact in fp32 (`compact`), else fp64
+// The 4 columns of a k-tile are chosen so that two of their staged rows have bit 2 of the row index
+// clear and two have it set whenever possible: with the 128-byte swizzle the B fragment load of the
+// warp (4 rows x 8 chains x 8 bytes) then covers every bank exactly twice -- no conflict.
+constexpr int SPMM_BLOCK_R = 8;
 
 }  // namespace hmcb

@@ -24,6 +24,7 @@ enum { LIK_NONE = 0, LIK_PREMULT = 1, LIK_DIRECT = 2 };
 
 // Likelihood gradient Y -> total gradient -> p -= b*eps*g ; q += a*eps*dK/dp ; reflect.
 struct UpdateEpi {
+  static constexpr bool kPerChainSum = false;
   DevTarget T;
   int C, ld;
   const double* sub;       // [d] subtracted from Y (Gtd0 for the premultiplied form) or null
@@ -133,6 +134,7 @@ struct UpdateEpi {
 
 // R[i][c] = (Y - d_i) / var_i     (LinearMatrix.py:207-208, 425-426)
 struct ResidualEpi {
+  static constexpr bool kPerChainSum = false;
   int N, C, ld;
   const double* dvec;
   const double* var;
@@ -166,6 +168,7 @@ struct ResidualEpi {
 //   premultiplied: q_j * (Y_j - 2*Gtd0_j)            (LinearMatrix.py:185-191)
 //   direct       : ((Y_i - d_i) / sigma_i)^2         (LinearMatrix.py:192-202)
 struct MisfitEpi {
+  static constexpr bool kPerChainSum = true;   // the row-blocked SpMM reduces term() over rows itself
   int mode;  // LIK_PREMULT or LIK_DIRECT
   int rows, C, ld;
   const double* vec;    // Gtd0 [d] or d [N]

@@ -65,6 +65,7 @@ def main():
         gerr = float((g - ref[0]).abs().max() / ref[0].abs().max())
         xerr = float(((x - ref[1]).abs() / ref[1].abs()).max())
         times = []
+        eng.kernel_timing_begin()
         for _ in range(args.reps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -72,8 +73,9 @@ def main():
             b.record()
             torch.cuda.synchronize()
             times.append(a.elapsed_time(b))
+        (pass_ms, passes), _ = eng.kernel_timing_end()
         res = dict(cfg=cfg, setup_s=round(setup, 2), grad_ms=min(times), grad_ms_all=times, g_relerr=gerr,
-                   x_relerr=xerr)
+                   x_relerr=xerr, spmm_pair_ms=pass_ms / max(passes, 1))
         print(json.dumps(res), flush=True)
         results.append(res)
         eng.close()

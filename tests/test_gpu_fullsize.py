@@ -264,12 +264,15 @@ def test_full_size_config4_strip_spmm_equals_l2_gather_kernel(monkeypatch):
     g, x = eng.gradient(q), eng.misfit(q)
     assert torch.equal(eng.gradient(q), g) and torch.equal(eng.misfit(q), x)
     eng.close()
-    monkeypatch.setenv("HMCB_SPMM_SHAPE", "-1")
-    ref = Engine(plan, mtree, w.chains, integrator=w.integrator, amount_of_steps=w.amount_of_steps)
-    g_ref, x_ref = ref.gradient(q), ref.misfit(q)
-    assert float((g - g_ref).abs().max() / g_ref.abs().max()) < 1e-12
-    assert float(((x - x_ref).abs() / x_ref.abs()).max()) < 1e-12
-    ref.close()
+    # default = the row-blocked kernel (rays cluster); then the plain strip kernel, then L2 gathers
+    for env in ({"HMCB_SPMM_BLOCKED": "0"}, {"HMCB_SPMM_SHAPE": "-1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ref = Engine(plan, mtree, w.chains, integrator=w.integrator, amount_of_steps=w.amount_of_steps)
+        g_ref, x_ref = ref.gradient(q), ref.misfit(q)
+        assert float((g - g_ref).abs().max() / g_ref.abs().max()) < 1e-12
+        assert float(((x - x_ref).abs() / x_ref.abs()).max()) < 1e-12
+        ref.close()
 
 
 def test_single_chain_single_dimension():

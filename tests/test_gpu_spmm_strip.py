@@ -65,7 +65,16 @@ def _check(plan, tree, mtree, d, chains=130, seed=3):
                                  {"HMCB_SPMM_SHAPE": "3"}, {"HMCB_SPMM_SHAPE": "4"},
                                  {"HMCB_SPMM_COMPACT": "0"},
                                  {"HMCB_SPMM_KB": "7", "HMCB_SPMM_EMAX": "1", "HMCB_SPMM_STAGES": "4"},
-                                 {"HMCB_SPMM_SHAPE": "-1"}])
+                                 {"HMCB_SPMM_SHAPE": "-1"},
+                                 # the row-blocked kernel, forced (these matrices have no row clusters)
+                                 {"HMCB_SPMM_BLOCKED": "1"},
+                                 {"HMCB_SPMM_BLOCKED": "1", "HMCB_SPMM_COMPACT": "0"},
+                                 {"HMCB_SPMM_BLOCKED": "1", "HMCB_SPMM_BLOCK_GW": "2", "HMCB_SPMM_BLOCK_NB": "2",
+                                  "HMCB_SPMM_STAGES": "3"},
+                                 {"HMCB_SPMM_BLOCKED": "1", "HMCB_SPMM_BLOCK_WARPS": "15", "HMCB_SPMM_BLOCK_GW": "8",
+                                  "HMCB_SPMM_STAGES": "4"},
+                                 {"HMCB_SPMM_BLOCKED": "1", "HMCB_SPMM_BLOCK_WARPS": "3", "HMCB_SPMM_BLOCK_GW": "2",
+                                  "HMCB_SPMM_STAGES": "4"}])
 def test_strip_spmm_on_awkward_matrices(monkeypatch, premult, env):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -121,8 +130,12 @@ def test_strip_spmm_is_deterministic_and_equals_the_gather_kernel(monkeypatch):
     for _ in range(3):
         assert torch.equal(eng.gradient(q), g0) and torch.equal(eng.misfit(q), x0)
     eng.close()
-    monkeypatch.setenv("HMCB_SPMM_SHAPE", "-1")
-    ref = Engine(plan, mtree, w.chains, integrator="lf", amount_of_steps=2)
-    assert rel_err(g0.cpu().numpy(), ref.gradient(q).cpu().numpy()) < 1e-12
-    assert rel_err(x0.cpu().numpy(), ref.misfit(q).cpu().numpy()) < 1e-12
-    ref.close()
+    # straight rays cluster: the default path is the row-blocked kernel; the plain strip kernel and
+    # the independent L2-gather kernel give the same numbers up to summation order
+    for env in ({"HMCB_SPMM_BLOCKED": "0"}, {"HMCB_SPMM_SHAPE": "-1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ref = Engine(plan, mtree, w.chains, integrator="lf", amount_of_steps=2)
+        assert rel_err(g0.cpu().numpy(), ref.gradient(q).cpu().numpy()) < 1e-12
+        assert rel_err(x0.cpu().numpy(), ref.misfit(q).cpu().numpy()) < 1e-12
+        ref.close()

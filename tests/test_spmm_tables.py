@@ -114,3 +114,85 @@ def test_bad_csr_is_refused(lib):
     assert lib.hmcb_debug_spmm_tables(2, 2, 2, ip(indptr), ip(indices), dp(data), 4, 3, 1, 8, 64, 1, 1,
                                       dp(B), dp(Y), info) != 0
     assert len(lib.hmcb_last_error()) > 0
+
+
+# ---- row-blocked tensor-core tables (csr_spmm_block_kernel) ---------------------------------
+
+def _block_tables(lib, A, B, warps, gw=2, nb=1, cap16=7168, allow_compact=True):
+    A = sp.csr_matrix(A)
+    rows, cols = A.shape
+    chains = B.shape[1]
+    indptr = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(A.indices, dtype=np.int32)
+    data = np.ascontiguousarray(A.data, dtype=np.float64)
+    Bc = np.ascontiguousarray(B, dtype=np.float64)
+    Y = np.empty((rows, chains))
+    info = (C.c_int64 * 8)()
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))   # noqa: E731
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+    status = lib.hmcb_debug_spmm_block_tables(rows, cols, data.size, ip(indptr), ip(indices), dp(data), warps, gw, nb,
+                                              cap16, int(allow_compact), chains, dp(Bc), dp(Y), info)
+    assert status == 0, lib.hmcb_last_error().decode()
+    return Y, dict(T=info[0], groups=info[1], blocks=info[2], nbytes=info[3], nnz=info[4], ktiles=info[5],
+                   balanced=info[6], compact=info[7])
+
+
+@pytest.mark.parametrize("shape", [(31, 4, 1), (31, 2, 2), (15, 8, 1), (3, 2, 1)])
+@pytest.mark.parametrize("f32", [True, False])
+def test_block_tables_reproduce_the_product(lib, shape, f32):
+    A = _awkward(700, 333, 2, f32)
+    B = np.random.default_rng(1).normal(size=(333, 5))
+    Y, info = _block_tables(lib, A, B, *shape)
+    assert info["nnz"] == A.nnz and 0 < info["blocks"] <= A.nnz and info["compact"] == int(f32)
+    assert info["ktiles"] * 4 >= info["blocks"]
+    np.testing.assert_allclose(Y, A @ B, rtol=0, atol=1e-12 * np.abs(A @ B).max())
+    Bt = np.random.default_rng(2).normal(size=(700, 3))
+    Yt, info_t = _block_tables(lib, A.T, Bt, *shape, cap16=1024)     # small stages: many strips
+    assert info_t["T"] > 1
+    np.testing.assert_allclose(Yt, A.T @ Bt, rtol=0, atol=1e-11)
+    _, info_f = _block_tables(lib, A, B, *shape, allow_compact=False)
+    assert info_f["compact"] == 0 and info_f["nbytes"] > info["nbytes"] * (1.5 if f32 else 0.99)
+
+
+def test_block_tables_unsorted_rows_duplicates_and_empty_matrix_parts(lib):
+    rng = np.random.default_rng(9)
+    rows, cols = 90, 41
+    dense = np.where(rng.uniform(size=(rows, cols)) < 0.2, rng.normal(size=(rows, cols)), 0.0)
+    dense[10:30] = 0.0                                   # a run of empty rows
+    A = sp.csr_matrix(dense)
+    # split every entry into two slots and shuffle each row (scipy accepts both)
+    indptr, indices, data = [0], [], []
+    for i in range(rows):
+        cols_i = A.indices[A.indptr[i]:A.indptr[i + 1]]
+        vals_i = A.data[A.indptr[i]:A.indptr[i + 1]]
+        ci = np.concatenate([cols_i, cols_i]); vi = np.concatenate([0.25 * vals_i, 0.75 * vals_i])
+        perm = rng.permutation(ci.size)
+        indices += list(ci[perm]); data += list(vi[perm]); indptr.append(len(indices))
+    messy = sp.csr_matrix((np.array(data), np.array(indices), np.array(indptr)), shape=(rows, cols))
+    B = rng.normal(size=(cols, 4))
+    Y, info = _block_tables(lib, messy, B, 3, cap16=256)
+    assert info["nnz"] == A.nnz
+    np.testing.assert_allclose(Y, dense @ B, rtol=0, atol=1e-13)
+    assert np.all(Y[10:30] == 0.0)
+
+
+def test_row_clustering_finds_the_reuse_of_straight_rays(lib):
+    """Rays of a tomography operator that run side by side cross the same cells: after clustering
+    one gathered row of the operand feeds several rows of a group (the reason the blocked kernel
+    exists); a matrix without such structure gives almost none and keeps the plain strip kernel.
+    Most k-tiles pair their columns so that the swizzled B fragment load is free of conflicts."""
+    from hmclab_b200.workloads import straight_ray_matrix
+
+    G = straight_ray_matrix(40, 40, 6000, seed=3)
+    B = np.random.default_rng(0).normal(size=(1600, 2))
+    Y, info = _block_tables(lib, G, B, 31, 4, 1)
+    np.testing.assert_allclose(Y, G @ B, rtol=0, atol=1e-11)
+    assert info["nnz"] / info["blocks"] > 2.5
+    assert info["balanced"] > 0.5 * info["ktiles"]
+    Bt = np.random.default_rng(1).normal(size=(6000, 2))
+    Yt, info_t = _block_tables(lib, G.T, Bt, 31, 4, 1)
+    np.testing.assert_allclose(Yt, G.T @ Bt, rtol=0, atol=1e-10)
+    assert info_t["nnz"] / info_t["blocks"] > 2.0
+    R = sp.random(600, 500, density=0.01, random_state=np.random.RandomState(1), format="csr")
+    _, info_r = _block_tables(lib, R, np.ones((500, 1)), 31, 4, 1)
+    assert info_r["nnz"] / info_r["blocks"] < 1.5
