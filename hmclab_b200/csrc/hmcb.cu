@@ -485,18 +485,40 @@ int build_block_tables(const HostCsr& m, const BlockShape& shape, int cap16, boo
   cluster_rows(m.rows, cols, ip, ix, R, &order);
   const int64_t groups = (int64_t)order.size() / R;
   const int chunks = (int)((groups + GPC - 1) / GPC);
-  order.resize((size_t)chunks * GPC * R, -1);
+  {
+    // Balance the warps of a block: a stage of the ring is released when its slowest warp is done, so
+    // the warps of a chunk should carry the same work.  Groups are sorted by their number of nonzeros
+    // (heavy chunks first: they also run first), and inside a chunk dealt to the warps in serpentine
+    // order, so every warp gets one group of each weight class.
+    std::vector<int64_t> weight(groups, 0);
+    for (int64_t g = 0; g < groups; ++g)
+      for (int r = 0; r < R; ++r) {
+        const int32_t i = order[g * R + r];
+        if (i >= 0) weight[g] += ip[i + 1] - ip[i];
+      }
+    std::vector<int32_t> rank(groups);
+    for (int64_t g = 0; g < groups; ++g) rank[g] = (int32_t)g;
+    std::stable_sort(rank.begin(), rank.end(), [&](int32_t a, int32_t b) { return weight[a] > weight[b]; });
+    std::vector<int32_t> dealt((size_t)chunks * GPC * R, -1);
+    for (int64_t i = 0; i < groups; ++i) {
+      const int64_t b = i / GPC, k = i % GPC, g = k / W, w = (g & 1) ? W - 1 - k % W : k % W;
+      std::copy(order.begin() + (size_t)rank[i] * R, order.begin() + (size_t)(rank[i] + 1) * R,
+                dealt.begin() + (size_t)((b * W + w) * GW + g) * R);
+    }
+    order.swap(dealt);
+  }
   bool compact = allow_compact;
   for (size_t k = 0; compact && k < dv.size(); ++k) compact = (double)(float)dv[k] == dv[k];
   host->compact = compact ? 1 : 0;
-  // column blocks of every group: distinct columns in ascending order, R values each
-  std::vector<int64_t> gptr(groups + 1, 0);
+  // column blocks of every group slot (chunk, warp, group): distinct columns in ascending order, R values each
+  const int64_t slots = (int64_t)chunks * GPC;
+  std::vector<int64_t> gptr(slots + 1, 0);
   std::vector<int32_t> gcol;
   std::vector<double> gval;
   gcol.reserve(ix.size() / 2); gval.reserve(ix.size() / 2 * R);
   {
     int32_t cur[R];
-    for (int64_t g = 0; g < groups; ++g) {
+    for (int64_t g = 0; g < slots; ++g) {
       for (int r = 0; r < R; ++r) { const int32_t i = order[g * R + r]; cur[r] = i < 0 ? -1 : ip[i]; }
       for (;;) {
         int32_t next = INT32_MAX;
@@ -518,113 +540,144 @@ int build_block_tables(const HostCsr& m, const BlockShape& shape, int cap16, boo
   host->blocks = (int64_t)gcol.size();
   host->nnz = (int64_t)ix.size();
   const int hdr16 = ((GPC + 1) * 4 + 15) / 16;
-  const int kt16 = 1 + (compact ? 128 : 256) / 16;      // offsets + A fragment of one k-tile
-  auto size16 = [&](int64_t n) { return (int64_t)hdr16 + n * kt16; };
+  // a k-tile record: per column {B row offset / 16 | row mask << 13 | values before it << 21, values
+  // of the k-tile}, then the nonzero values column by column -- fp32 when the matrix allows, else fp64
+  const int rec_hdr = 32, vsz = compact ? 4 : 8;
+  std::vector<int32_t> ennz(gcol.size(), 0);          // nonzeros of every column block
+  for (size_t k = 0; k < gcol.size(); ++k)
+    for (int r = 0; r < R; ++r) ennz[k] += gval[k * R + r] != 0.0;
+  auto size16 = [&](int64_t tiles, int64_t values) {
+    return (int64_t)hdr16 + (tiles * (rec_hdr + (compact ? 4 : 0)) + values * vsz + 15) / 16;   // records are 8-byte aligned
+  };
   // strips per chunk: T grows until the widest strip and the fullest (chunk, strip) group fit into a stage
   int64_t T = std::max<int64_t>(1, (cols * NB * 8 + cap16 - 1) / cap16);
-  std::vector<int32_t> per_strip, kt;
+  std::vector<int32_t> per_strip, kt, nz;
   int box_rows = 0, row_boxes = 0;
   for (;;) {
     int64_t worst = 0;
     per_strip.assign((size_t)T, 0);
     kt.assign((size_t)T, 0);
+    nz.assign((size_t)T, 0);
     for (int b = 0; b < chunks; ++b) {
       std::fill(kt.begin(), kt.end(), 0);
-      for (int64_t g = (int64_t)b * GPC; g < std::min<int64_t>(groups, (int64_t)(b + 1) * GPC); ++g) {
-        for (int64_t k = gptr[g]; k < gptr[g + 1]; ++k) ++per_strip[gcol[k] % T];
+      std::fill(nz.begin(), nz.end(), 0);
+      for (int64_t g = (int64_t)b * GPC; g < (int64_t)(b + 1) * GPC; ++g) {
+        for (int64_t k = gptr[g]; k < gptr[g + 1]; ++k) { ++per_strip[gcol[k] % T]; nz[gcol[k] % T] += ennz[k]; }
         for (int64_t k = gptr[g]; k < gptr[g + 1]; ++k) {
           int32_t& n = per_strip[gcol[k] % T];
           if (n) { kt[gcol[k] % T] += (n + 3) / 4; n = 0; }
         }
       }
-      for (int64_t t = 0; t < T; ++t) worst = std::max<int64_t>(worst, kt[t]);
+      for (int64_t t = 0; t < T; ++t) worst = std::max<int64_t>(worst, size16(kt[t], nz[t]));
     }
     block_box_geometry((cols + T - 1) / T, &box_rows, &row_boxes);
     const int64_t box16 = (int64_t)box_rows * row_boxes * NB * 8;
+    if ((int64_t)box_rows * row_boxes * 128 * NB >= (1 << 17)) return fail("internal: SpMM block stage too large for 13-bit offsets");
     if (std::getenv("HMCB_DEBUG_TABLES"))
-      fprintf(stderr, "block tables: T=%lld worst=%lld k-tiles box16=%lld size16=%lld cap=%d\n", (long long)T,
-              (long long)worst, (long long)box16, (long long)size16(worst), cap16);
-    if (box16 + size16(worst) <= cap16 && worst < 1024 * 1024) { host->emax = (int)(cap16 - box16); break; }
+      fprintf(stderr, "block tables: T=%lld box16=%lld worst size16=%lld cap=%d\n", (long long)T, (long long)box16,
+              (long long)worst, cap16);
+    if (box16 + worst <= cap16 && worst * 4 < (1 << 22)) { host->emax = (int)(cap16 - box16); break; }
     if (T >= cols) return fail("internal: SpMM block strip does not fit");
     T = std::min<int64_t>(cols, T + std::max<int64_t>(1, T / 16));
   }
   const int emax = host->emax;
-  const uint32_t region = (uint32_t)NB * box_rows * 128;      // bytes of one row box (all chain boxes)
+  const uint32_t region = (uint32_t)NB * box_rows * 128u;      // bytes of one row box (NB chain boxes of 128-byte rows)
   std::vector<unsigned char>& ent = host->ent;
   std::vector<SpmmStrip>& strips = host->strips;
   std::vector<int32_t>& strip_ptr = host->strip_ptr;
   ent.clear(); strips.clear(); strip_ptr.assign(chunks + 1, 0);
-  // per strip of the current chunk: k-tile offsets, A fragments (as doubles), per (warp, group) ranges
-  std::vector<std::vector<uint32_t>> boff(T);
-  std::vector<std::vector<double>> bval(T);
+  // per strip of the current chunk: the record stream, per (warp, group) its first word and k-tile count
+  std::vector<std::vector<unsigned char>> rec(T);
   std::vector<uint32_t> first((size_t)T * GPC), count((size_t)T * GPC);
   std::vector<std::vector<int64_t>> lists(T);     // entries of the current group per strip
-  std::vector<int64_t> q[2], tile;
+  std::vector<int64_t> q[4], tile;
   int64_t ktiles = 0;
   for (int b = 0; b < chunks; ++b) {
-    for (int64_t t = 0; t < T; ++t) { boff[t].clear(); bval[t].clear(); }
+    for (int64_t t = 0; t < T; ++t) rec[t].clear();
     for (int s = 0; s < GPC; ++s) {
       const int64_t g = (int64_t)b * GPC + s;
-      for (int64_t t = 0; t < T; ++t) { first[t * GPC + s] = (uint32_t)(boff[t].size() / 4); count[t * GPC + s] = 0; }
-      if (g >= groups) continue;
+      for (int64_t t = 0; t < T; ++t) { first[t * GPC + s] = (uint32_t)(rec[t].size() / 4); count[t * GPC + s] = 0; }
       for (int64_t k = gptr[g]; k < gptr[g + 1]; ++k) lists[gcol[k] % T].push_back(k);
       for (int64_t k0 = gptr[g]; k0 < gptr[g + 1]; ++k0) {
         const int64_t t = gcol[k0] % T;
         std::vector<int64_t>& L = lists[t];
         if (L.empty()) continue;      // this strip of the group has been emitted already
-        // k-tiles of 4 columns: two staged rows with bit 2 clear + two with bit 2 set while both last
-        q[0].clear(); q[1].clear();
-        for (int64_t k : L) q[((gcol[k] / T) % box_rows >> 2) & 1].push_back(k);
-        size_t h0 = 0, h1 = 0;
+        // k-tiles of 4 columns in column order
         auto emit = [&]() {
-          for (int c = 0; c < 4; ++c) {
-            if (c < (int)tile.size()) {
-              const int64_t r = gcol[tile[c]] / T, rl = r % box_rows;
-              boff[t].push_back((uint32_t)(r / box_rows) * region + (uint32_t)rl * 128u + (uint32_t)(rl & 7) * 16u);
-            } else {
-              boff[t].push_back(0u);
+          std::vector<unsigned char>& out = rec[t];
+          uint32_t words[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          uint32_t before = 0;
+          for (int c = 0; c < (int)tile.size(); ++c) {
+            const int64_t r = gcol[tile[c]] / T, rl = r % box_rows;
+            const uint32_t off = (uint32_t)(r / box_rows) * region + (uint32_t)rl * 128u + (uint32_t)(rl & 7) * 16u;
+            uint32_t colmask = 0;
+            for (int rr = 0; rr < R; ++rr) colmask |= (gval[tile[c] * R + rr] != 0.0 ? 1u : 0u) << rr;
+            words[2 * c] = (off >> 4) | (colmask << 13) | (before << 21);
+            before += (uint32_t)__builtin_popcount(colmask);
+          }
+          for (int c = (int)tile.size(); c < 4; ++c) words[2 * c] = before << 21;
+          for (int c = 0; c < 4; ++c) words[2 * c + 1] = before;
+          const unsigned char* wb = reinterpret_cast<const unsigned char*>(words);
+          out.insert(out.end(), wb, wb + rec_hdr);
+          for (int c = 0; c < (int)tile.size(); ++c)
+            for (int rr = 0; rr < R; ++rr) {
+              const double v = gval[tile[c] * R + rr];
+              if (v == 0.0) continue;
+              if (compact) {
+                const float f = (float)v;
+                const unsigned char* fb = reinterpret_cast<const unsigned char*>(&f);
+                out.insert(out.end(), fb, fb + 4);
+              } else {
+                const unsigned char* vb = reinterpret_cast<const unsigned char*>(&v);
+                out.insert(out.end(), vb, vb + 8);
+              }
             }
-          }
-          for (int l = 0; l < 32; ++l) {
-            const int c = l & 3, r = l >> 2;
-            bval[t].push_back(c < (int)tile.size() ? gval[tile[c] * R + r] : 0.0);
-          }
+          while (out.size() % 8) out.push_back(0);     // the next record starts 8-byte aligned
           ++count[t * GPC + s];
           tile.clear();
         };
-        while (q[0].size() - h0 >= 2 && q[1].size() - h1 >= 2) {
-          tile = {q[0][h0], q[0][h0 + 1], q[1][h1], q[1][h1 + 1]};
-          h0 += 2; h1 += 2;
+        // The lanes of a quarter warp read the same 32-byte column of the 4 gathered rows; with the
+        // 128-byte swizzle row r lands in bank group (r >> 1) & 3 of that quarter: a k-tile whose 4 rows
+        // fall into 4 different classes loads its B fragment without a bank conflict.  One column of
+        // each class while all four last, then the fullest classes first.
+        for (auto& v : q) v.clear();
+        for (int64_t k : L) q[((gcol[k] / T) % box_rows >> 1) & 3].push_back(k);
+        size_t head[4] = {0, 0, 0, 0};
+        tile.clear();
+        for (;;) {
+          int order4[4] = {0, 1, 2, 3};
+          std::sort(order4, order4 + 4, [&](int a, int b) {
+            const size_t ra = q[a].size() - head[a], rb = q[b].size() - head[b];
+            return ra != rb ? ra > rb : a < b;
+          });
+          if (q[order4[0]].size() == head[order4[0]]) break;      // nothing left
+          for (int c = 0; c < 4 && tile.size() < 4; ++c)
+            if (head[order4[c]] < q[order4[c]].size()) tile.push_back(q[order4[c]][head[order4[c]]++]);
+          // fewer than 4 classes left: go round the classes again (2-way conflicts before 3-way ones)
+          for (bool took = true; took && tile.size() < 4;) {
+            took = false;
+            for (int c = 0; c < 4 && tile.size() < 4; ++c)
+              if (head[order4[c]] < q[order4[c]].size()) { tile.push_back(q[order4[c]][head[order4[c]]++]); took = true; }
+          }
           emit();
         }
-        tile.clear();
-        // leftovers: keep the halves as balanced as they come
-        while (h0 < q[0].size() || h1 < q[1].size()) {
-          if (h0 < q[0].size() && (tile.size() % 2 == 0 || h1 >= q[1].size())) tile.push_back(q[0][h0++]);
-          else if (h1 < q[1].size()) tile.push_back(q[1][h1++]);
-          if (tile.size() == 4) emit();
-        }
-        if (!tile.empty()) emit();
         L.clear();
       }
     }
     for (int64_t t = 0; t < T; ++t) {
-      const int64_t n = (int64_t)boff[t].size() / 4;
-      if (n == 0) continue;
-      const size_t base = ent.size(), bytes = (size_t)size16(n) * 16;
+      if (rec[t].empty()) continue;
+      int64_t n = 0;
+      for (int s = 0; s < GPC; ++s) n += count[t * GPC + s];
+      const size_t base = ent.size(), bytes = ((size_t)hdr16 * 16 + rec[t].size() + 15) / 16 * 16;
       if (bytes > (size_t)emax * 16) return fail("internal: block strip size mismatch");
       ent.resize(base + bytes, 0);
       uint32_t* hdr = reinterpret_cast<uint32_t*>(&ent[base]);
-      for (int s = 0; s < GPC; ++s) hdr[s] = (first[t * GPC + s] << 10) | count[t * GPC + s];
-      hdr[GPC] = (uint32_t)n;
-      std::memcpy(&ent[base + (size_t)hdr16 * 16], boff[t].data(), (size_t)n * 16);
-      unsigned char* a = &ent[base + (size_t)hdr16 * 16 + (size_t)n * 16];
-      if (compact) {
-        float* af = reinterpret_cast<float*>(a);
-        for (size_t k = 0; k < bval[t].size(); ++k) af[k] = (float)bval[t][k];
-      } else {
-        std::memcpy(a, bval[t].data(), bval[t].size() * sizeof(double));
+      for (int s = 0; s < GPC; ++s) {
+        if (count[t * GPC + s] >= 1024u || first[t * GPC + s] >= (1u << 22)) return fail("internal: block strip header overflow");
+        hdr[s] = (first[t * GPC + s] << 10) | count[t * GPC + s];
       }
+      hdr[GPC] = (uint32_t)n;
+      std::memcpy(&ent[base + (size_t)hdr16 * 16], rec[t].data(), rec[t].size());
       strips.push_back(SpmmStrip{(int)t, (int)((cols - t + T - 1) / T), (int)(base / 16), (int)(bytes / 16)});
       ktiles += n;
     }
@@ -1030,7 +1083,7 @@ int hmcb_debug_spmm_block_tables(int64_t rows, int64_t cols, int64_t nnz, const 
   if (build_block_tables(m, shape, cap16, allow_compact != 0, &host)) return -1;
   const int64_t T = host.cstride;
   const int hdr16 = ((GPC + 1) * 4 + 15) / 16;
-  const int asz = host.compact ? 128 : 256, kt16 = 1 + asz / 16;
+  const int rec_hdr = 32, vsz = host.compact ? 4 : 8;
   const int64_t region = (int64_t)chain_boxes * host.box_rows * 128;
   HMCB_CHECK(host.box_rows % 8 == 0 && host.box_rows <= 256 && host.box_rows * host.row_boxes >= host.kb_box &&
                  (int64_t)host.box_rows * host.row_boxes * chain_boxes * 8 + host.emax <= cap16,
@@ -1047,7 +1100,7 @@ int hmcb_debug_spmm_block_tables(int64_t rows, int64_t cols, int64_t nnz, const 
     }
     for (int64_t i = 0; i < rows; ++i) HMCB_CHECK(seen[i], "block tables: a row is missing from the permutation");
   }
-  int64_t ktiles = 0, balanced = 0;
+  int64_t ktiles = 0, full_tiles = 0;
   for (int b = 0; b < host.chunks; ++b) {
     for (int32_t s = host.strip_ptr[b]; s < host.strip_ptr[b + 1]; ++s) {
       const SpmmStrip& st = host.strips[s];
@@ -1056,41 +1109,54 @@ int hmcb_debug_spmm_block_tables(int64_t rows, int64_t cols, int64_t nnz, const 
       const unsigned char* group = host.ent.data() + (size_t)st.ent_off * 16;
       const uint32_t* hdr = reinterpret_cast<const uint32_t*>(group);
       const int64_t total = hdr[GPC];
-      HMCB_CHECK(total > 0 && (int64_t)hdr16 + total * kt16 == st.ent_cnt, "block tables: group size mismatch");
-      const uint32_t* off = reinterpret_cast<const uint32_t*>(group + (size_t)hdr16 * 16);
-      const unsigned char* afr = group + (size_t)hdr16 * 16 + (size_t)total * 16;
-      int64_t sum = 0;
+      const unsigned char* stream = group + (size_t)hdr16 * 16;
+      const int64_t stream_bytes = (int64_t)(st.ent_cnt - hdr16) * 16;
+      int64_t sum = 0, pos = 0;
       for (int wg = 0; wg < GPC; ++wg) {
         const int64_t first = hdr[wg] >> 10, n = hdr[wg] & 1023u;
-        HMCB_CHECK(first == sum && first + n <= total, "block tables: (warp, group) ranges are not consecutive");
+        HMCB_CHECK(first * 4 == pos, "block tables: (warp, group) streams are not consecutive");
         sum += n;
-        for (int64_t k = first; k < first + n; ++k) {
-          int hi = 0, used = 0;
+        for (int64_t k = 0; k < n; ++k) {
+          HMCB_CHECK(pos + rec_hdr <= stream_bytes, "block tables: record runs out of its group");
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(stream + pos);
+          const uint32_t values = w[1];
+          const unsigned char* vals = stream + pos + rec_hdr;
+          HMCB_CHECK(pos + rec_hdr + (int64_t)values * vsz <= stream_bytes, "block tables: values run out of their group");
+          uint32_t before = 0, classes = 0;
+          int used = 0;
           for (int c = 0; c < 4; ++c) {
-            const uint32_t o = off[k * 4 + c];
+            const uint32_t word = w[2 * c];
+            const int64_t o = (int64_t)(word & 0x1FFFu) << 4;
+            const uint32_t colmask = (word >> 13) & 0xFFu;
+            HMCB_CHECK(w[2 * c + 1] == values && (word >> 21) == before, "block tables: bad record header");
+            if (!colmask) continue;
+            ++used;
             const int64_t rb = o / region, rem = o % region, rl = rem / 128;
             HMCB_CHECK(rb < host.row_boxes && rl < host.box_rows && rem % 128 == (rl & 7) * 16,
-                       "block tables: bad swizzled offset");
+                       "block tables: bad swizzled B row offset");
+            classes |= 1u << ((rl >> 1) & 3);
             const int64_t j = st.col0 + (rb * host.box_rows + rl) * T;
-            bool any = false;
+            HMCB_CHECK(j < cols, "block tables: column outside the matrix");
             for (int r = 0; r < R; ++r) {
-              const double v = host.compact ? (double)reinterpret_cast<const float*>(afr + (size_t)k * asz)[r * 4 + c]
-                                            : reinterpret_cast<const double*>(afr + (size_t)k * asz)[r * 4 + c];
-              if (v == 0.0) continue;
-              any = true;
+              if (!(colmask >> r & 1u)) continue;
+              const double v = host.compact ? (double)reinterpret_cast<const float*>(vals)[before]
+                                            : reinterpret_cast<const double*>(vals)[before];
+              ++before;
               const int32_t i = host.perm[((size_t)b * GPC + wg) * R + r];
-              HMCB_CHECK(i >= 0 && j < cols, "block tables: value on a padding row or outside the matrix");
+              HMCB_CHECK(v != 0.0 && i >= 0, "block tables: value on a padding row");
               for (int64_t ch = 0; ch < chains; ++ch) Y[i * chains + ch] = std::fma(v, B[j * chains + ch], Y[i * chains + ch]);
             }
-            if (any) { ++used; hi += (int)((rl >> 2) & 1); }
           }
-          if (used == 4 && hi == 2) ++balanced;
+          HMCB_CHECK(before == values && used > 0, "block tables: value count mismatch");
+          if (used == 4 && classes == 15u) ++full_tiles;    // 4 columns in 4 bank classes: conflict free
+          pos += rec_hdr + ((int64_t)values * vsz + 7) / 8 * 8;
         }
       }
-      HMCB_CHECK(sum == total, "block tables: k-tile count mismatch");
+      HMCB_CHECK(sum == total && total > 0, "block tables: k-tile count mismatch");
       ktiles += total;
     }
   }
+  const int64_t balanced = full_tiles;
   HMCB_CHECK(ktiles == host.ktiles, "block tables: total k-tile count mismatch");
   info[0] = T; info[1] = (int64_t)host.strips.size(); info[2] = host.blocks; info[3] = (int64_t)host.ent.size();
   info[4] = host.nnz; info[5] = host.ktiles; info[6] = balanced; info[7] = host.compact;

@@ -30,6 +30,8 @@ int spmm_strip_shapes(const SpmmShape** out) {
     if ((M).warps == 31 && (M).gw == 4 && (M).nb == 1) { CALL(31, 4, 1); }             \
     else if ((M).warps == 31 && (M).gw == 2 && (M).nb == 1) { CALL(31, 2, 1); }        \
     else if ((M).warps == 31 && (M).gw == 2 && (M).nb == 2) { CALL(31, 2, 2); }        \
+    else if ((M).warps == 23 && (M).gw == 4 && (M).nb == 2) { CALL(23, 4, 2); }        \
+    else if ((M).warps == 19 && (M).gw == 4 && (M).nb == 2) { CALL(19, 4, 2); }        \
     else if ((M).warps == 15 && (M).gw == 4 && (M).nb == 2) { CALL(15, 4, 2); }        \
     else if ((M).warps == 15 && (M).gw == 8 && (M).nb == 1) { CALL(15, 8, 1); }        \
     else if ((M).warps == 3 && (M).gw == 2 && (M).nb == 1) { CALL(3, 2, 1); }          \
@@ -39,6 +41,7 @@ int spmm_strip_shapes(const SpmmShape** out) {
 bool spmm_block_shape_supported(int warps, int gw, int nb) {
   return (warps == 31 && gw == 4 && nb == 1) || (warps == 31 && gw == 2 && nb == 1) ||
          (warps == 31 && gw == 2 && nb == 2) || (warps == 15 && gw == 4 && nb == 2) ||
+         (warps == 23 && gw == 4 && nb == 2) || (warps == 19 && gw == 4 && nb == 2) ||
          (warps == 15 && gw == 8 && nb == 1) || (warps == 3 && gw == 2 && nb == 1);
 }
 

@@ -208,19 +208,18 @@ csr_spmm_strip_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap
 //
 // hmcb_finalize regroups the rows into groups of 8 rows with similar column sets (cluster_rows in
 // hmcb.cu; rays that run side by side cross the same cells).  A group is one DMMA M-tile; a k-tile
-// is 4 columns of the group with its 8 x 4 A fragment stored in fragment order (zeros where a row
-// has no entry): one conflict-free per-lane load delivers 32 matrix values, one per-lane load the B
-// fragment (4 gathered rows x 8 chains), one mma.sync.m8n8k4.f64 does the 256 FMAs.
-//   * slab = 16 NB chains; B strips arrive as NB 128-byte-swizzled tensor-map TMA boxes
-//     {16 chains, 1 strip, box_rows rows} (per row box), so the 4 gathered rows of a k-tile -- chosen
-//     by the host with two of them in each half of the swizzle period -- cover every bank exactly
-//     twice;
+// is 4 columns of the group with the nonzeros of its 8 x 4 A fragment: one per-lane load delivers
+// the lane's matrix value, one 16-byte per-lane load the B fragments of two N-tiles (4 gathered
+// rows x 16 chains), two mma.sync.m8n8k4.f64 do 512 FMAs.
+//   * slab = 16 NB chains, staged as 128-byte-swizzled tensor-map TMA boxes {16 chains, 1 strip,
+//     box_rows rows}; a box feeds two N-tiles, the even and the odd chains: lane (k, n) reads chains
+//     2n, 2n + 1 of row k with one 16-byte load.  A quarter warp (k = 0..3, two n) reads the same
+//     32-byte column of 4 rows; the swizzle moves row r to bank group (r >> 1) & 3 of that quarter, and
+//     the host picks the 4 columns of a k-tile from 4 different classes whenever it can: no conflict;
 //   * a consumer warp owns GW groups (8 GW rows): 2 NB GW accumulator pairs per lane, and with the
 //     narrow slab a block covers WARPS x GW x 8 rows -- 4x the rows of the plain kernel, so 4x less
 //     L2 -> shared-memory staging of B per useful flop;
 //   * the grid interleaves the slabs of 128 chains per chunk so that a chunk's tables are re-read from L2.
-// Per k-tile and 16 chains: 2 table loads + 2 B loads + 2 DMMA + ~6 integer instructions; the tensor
-// pipe binds (4 cycles per DMMA and SM) at the matrix's 8 x 1 block fill.
 constexpr int SPMM_SLAB_CHAINS_MINOR = 128;   // chains covered by the interleaved slabs of one chunk
 
 __device__ __forceinline__ float lds_f32(unsigned a) {
@@ -234,7 +233,7 @@ __global__ void __launch_bounds__((WARPS + SPMM_PRODUCERS) * 32, 1)
 csr_spmm_block_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap, Epilogue epi) {
   constexpr int S = 16 * NB, NT = 2 * NB, R = SPMM_BLOCK_R, GPC = WARPS * GW;
   constexpr unsigned HDR = (unsigned)(((GPC + 1) * 4 + 15) / 16 * 16);   // header bytes
-  constexpr unsigned ASZ = COMPACT ? 128u : 256u;                         // bytes of an A fragment
+  constexpr unsigned REC = 32u, VSZ = COMPACT ? 4u : 8u;                  // record header / value bytes
   extern __shared__ __align__(1024) unsigned char strip_smem[];
   __shared__ uint64_t full_bar[SPMM_MAX_STAGES], empty_bar[SPMM_MAX_STAGES];
 
@@ -245,7 +244,6 @@ csr_spmm_block_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap
   const int s_begin = __ldg(M.strip_ptr + chunk);
   const int nst = __ldg(M.strip_ptr + chunk + 1) - s_begin;
   const int nstages = M.stages;
-  // the dynamic shared memory window is only guaranteed 16-byte aligned: round up to a swizzle atom
   const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(strip_smem) + 1023u) & ~1023u;
 
   if (tid == 0) {
@@ -284,7 +282,8 @@ csr_spmm_block_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap
     return;
   }
 
-  // ---- consumer warps: groups (chunk * WARPS + warp) * GW + g; lane holds C[row lane / 4][chains 2 (lane % 4) + {0, 1}]
+  // ---- consumer warps: groups (chunk * WARPS + warp) * GW + g.  Lane holds rows lane / 4 of its groups
+  // and, per 16-chain box, chains 4 (lane % 4) + {0, 2} (even N-tile) and + {1, 3} (odd N-tile)
   double acc[GW][NT][2];
 #pragma unroll
   for (int g = 0; g < GW; ++g)
@@ -292,10 +291,8 @@ csr_spmm_block_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap
     for (int j = 0; j < NT; ++j) acc[g][j][0] = acc[g][j][1] = 0.0;
 
   {
-    // B fragment: lane holds B[k = lane % 4][chain n = lane / 4]; with the 128-byte swizzle the 16-byte
-    // granule index of chain n is XORed with (row & 7) -- the host stores row * 128 + (row & 7) * 16,
-    // the lane XORs its own granule and adds the half granule
-    const unsigned lconst = ((unsigned)(lane >> 3) << 4) | (((unsigned)(lane >> 2) & 1u) << 3);
+    const unsigned rowbit = 1u << (lane >> 2), below = rowbit - 1u;
+    const unsigned lconst = (unsigned)(lane >> 2) << 4;   // the lane's 16-byte granule (chains 2n, 2n + 1)
     const unsigned box_bytes = (unsigned)M.box_rows * 128u;
     int stage = 0;
     unsigned phase = 0;
@@ -303,25 +300,29 @@ csr_spmm_block_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap
       mbar_wait(&full_bar[stage], phase);
       const unsigned base = smem0 + (unsigned)stage * (unsigned)M.stage_bytes;
       const unsigned es = base + (unsigned)M.b_bytes;
-      const unsigned total = lds_u32(es + 4u * GPC);
-      const unsigned off0 = es + HDR + 4u * (lane & 3), a0 = es + HDR + 16u * total + (COMPACT ? 4u : 8u) * lane;
 #pragma unroll
       for (int g = 0; g < GW; ++g) {
         const unsigned mine = lds_u32(es + 4u * (warp * GW + g));
         int n = (int)(mine & 1023u);
-        unsigned op = off0 + 16u * (mine >> 10), ap = a0 + ASZ * (mine >> 10);
+        unsigned rp = es + HDR + 4u * (mine >> 10) + 8u * (lane & 3);   // the lane's column word of the record
 #pragma unroll 2
         for (; n > 0; --n) {
-          const unsigned x = base + (lds_u32(op) ^ lconst);
-          double a;
-          if constexpr (COMPACT) a = (double)lds_f32(ap);
-          else a = lds_f64(ap);
-          op += 16u; ap += ASZ;
+          const uint2 h = lds_u32x2(rp);
+          const unsigned colmask = h.x >> 13;      // bits 0-7: rows with a value in the lane's column
+          const unsigned vp = rp - 8u * (lane & 3) + REC + VSZ * ((h.x >> 21) + (unsigned)__popc(colmask & below));
+          double a = 0.0;
+          if (colmask & rowbit) {
+            if constexpr (COMPACT) a = (double)lds_f32(vp);
+            else a = lds_f64(vp);
+          }
+          // the host stores row * 128 + (row & 7) * 16: XOR with the lane's granule = its swizzled address
+          const unsigned x = base + (((h.x & 0x1FFFu) << 4) ^ lconst);
+          rp += REC + ((VSZ * h.y + 7u) & ~7u);   // records are 8-byte aligned
 #pragma unroll
           for (int cb = 0; cb < NB; ++cb) {
-            const double b0 = lds_f64(x + cb * box_bytes), b1 = lds_f64((x ^ 64u) + cb * box_bytes);
-            dmma_8x8x4(acc[g][2 * cb][0], acc[g][2 * cb][1], a, b0);
-            dmma_8x8x4(acc[g][2 * cb + 1][0], acc[g][2 * cb + 1][1], a, b1);
+            const double2 b = lds_f64x2(x + cb * box_bytes);
+            dmma_8x8x4(acc[g][2 * cb][0], acc[g][2 * cb][1], a, b.x);
+            dmma_8x8x4(acc[g][2 * cb + 1][0], acc[g][2 * cb + 1][1], a, b.y);
           }
         }
       }
@@ -331,9 +332,10 @@ csr_spmm_block_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap
     }
   }
 
-  // ---- epilogue: block row -> original row through the permutation
+  // ---- epilogue: block row -> original row through the permutation; accumulator (N-tile j, h) of box
+  // cb = j / 2 is chain 16 cb + 4 (lane % 4) + 2 h + j % 2
   const int brow0 = (chunk * WARPS + warp) * GW * R + (lane >> 2);
-  const int c0 = slab0 + 2 * (lane & 3);
+  const int c0 = slab0 + 4 * (lane & 3);
   if constexpr (Epilogue::kPerChainSum) {
     // per-chain sums over the warp's rows: the rows of a chain sit in the 8 lanes with equal lane % 4
     int rows[GW];
@@ -343,14 +345,15 @@ csr_spmm_block_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap
     for (int j = 0; j < NT; ++j)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
+        const int c = c0 + 16 * (j >> 1) + 2 * h + (j & 1);
         double v = 0.0;
 #pragma unroll
         for (int g = 0; g < GW; ++g)
-          if (rows[g] >= 0) v = __dadd_rn(v, epi.term(rows[g], c0 + 8 * j + h, acc[g][j][h]));
+          if (rows[g] >= 0) v = __dadd_rn(v, epi.term(rows[g], c, acc[g][j][h]));
         v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
         v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 8));
         v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 16));
-        if (lane < 4 && c0 + 8 * j + h < epi.ld) epi.part[(size_t)(chunk * WARPS + warp) * epi.ld + c0 + 8 * j + h] = v;
+        if (lane < 4 && c < epi.ld) epi.part[(size_t)(chunk * WARPS + warp) * epi.ld + c] = v;
       }
   } else {
 #pragma unroll
@@ -358,9 +361,11 @@ csr_spmm_block_kernel(const StripDev M, const __grid_constant__ CUtensorMap bmap
       const int i = __ldg(M.perm + brow0 + g * R);
       if (i < 0) continue;
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        epi.row(i, c0 + 8 * j, acc[g][j][0]);
-        epi.row(i, c0 + 8 * j + 1, acc[g][j][1]);
+      for (int cb = 0; cb < NB; ++cb) {
+        epi.row(i, c0 + 16 * cb, acc[g][2 * cb][0]);
+        epi.row(i, c0 + 16 * cb + 1, acc[g][2 * cb + 1][0]);
+        epi.row(i, c0 + 16 * cb + 2, acc[g][2 * cb][1]);
+        epi.row(i, c0 + 16 * cb + 3, acc[g][2 * cb + 1][1]);
       }
     }
   }

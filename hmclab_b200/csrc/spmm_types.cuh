@@ -51,18 +51,22 @@ struct StripDev {
 
 constexpr int SPMM_MAX_STAGES = 4;
 
-// Row-blocked tables.  A (chunk, strip) group is, in 16-byte units:
-//   header  : (warps x gw + 1) u32 -- per (warp, group) (first k-tile << 10 | number of k-tiles), then
-//             the group's total number of k-tiles n; padded to 16 bytes
-//   offsets : n x 4 u32 -- for the 4 columns of every k-tile the byte offset of its B row inside the
-//             staged strip with the 128-byte TMA swizzle of the row already applied
-//             (row_box * nb * box_rows * 128 + r * 128 + (r & 7) * 16, r = row inside the box)
-//   A       : n x 32 values in DMMA fragment order (lane l holds A[row l / 4][column l % 4] of the
-//             8 x 4 tile; 0.0 where the matrix has no entry), fp32 when every value of the matrix is
-//             exact in fp32 (`compact`), else fp64
-// The 4 columns of a k-tile are chosen so that two of their staged rows have bit 2 of the row index
-// clear and two have it set whenever possible: with the 128-byte swizzle the B fragment load of the
-// warp (4 rows x 8 chains x 8 bytes) then covers every bank exactly twice -- no conflict.
+// Row-blocked tables.  A (chunk, strip) group is
+//   header  : (warps x gw + 1) u32 -- per (warp, group) (first word of its record stream << 10 | number
+//             of k-tiles), then the group's total number of k-tiles; padded to 16 bytes
+//   records : per (warp, group) one k-tile record after the other:
+//               4 x {u32 w, u32 n}   per column c of the k-tile: w = (byte offset of its B row inside the
+//                                    staged strip) / 16 | (mask of the rows with a nonzero in this column) << 13
+//                                    | (number of values of the columns before c) << 21; n = number of
+//                                    values of the whole k-tile (the same in all four)
+//               values               the nonzeros column by column, rows ascending; fp32 when every value of
+//                                    the matrix is exact in fp32 (`compact`), else fp64; padded to 8 bytes
+//             (the 8 x 4 fragments are 30-45 % dense: storing only the nonzeros halves the bytes streamed)
+// B row offsets carry the 128-byte TMA swizzle of their row: row_box * nb * box_rows * 128 + r * 128 +
+// (r & 7) * 16 (r = row inside the box).  The chains of a 16-chain box are split over two N-tiles as
+// even / odd chains, so lane (k, n) of the B fragment needs chains 2n and 2n + 1 of row k: one 16-byte
+// load at offset ^ (n * 16).  The 4 columns of a k-tile come from 4 different classes (r >> 1) & 3
+// whenever possible: the quarter warps then read 4 x 32 bytes in 4 different bank groups.
 constexpr int SPMM_BLOCK_R = 8;
 
 }  // namespace hmcb

@@ -55,12 +55,12 @@ int hmcb_debug_spmm_tables(int64_t rows, int64_t cols, int64_t nnz, const int32_
                            double *Y, int64_t *info);
 /* Same for the row-blocked tensor-core tables (rows regrouped into groups of 8 rows with similar
  * column sets = one DMMA M-tile, `groups_per_warp` groups per consumer warp, k-tiles of 4 columns with
- * their 8 x 4 A fragments, B staged as `chain_boxes` 128-byte-swizzled TMA boxes of 16 chains):
+ * the nonzeros of their 8 x 4 A fragments, slabs of 16 `chain_boxes` chains):
  * clusters, builds, checks and walks them like csr_spmm_block_kernel.  `cap16` = size of a pipeline
  * stage in 16-byte units (B rows of a strip + k-tiles of one group).  info[0..7] = strips per chunk,
  * (chunk, strip) groups, column blocks (distinct columns per row group), table bytes, nonzeros after
- * summing duplicates, k-tiles, k-tiles whose B fragment load is free of bank conflicts, 1 if the A
- * fragments are stored in fp32. */
+ * summing duplicates, k-tiles, k-tiles that carry 4 columns, 1 if the matrix values are stored in
+ * fp32. */
 int hmcb_debug_spmm_block_tables(int64_t rows, int64_t cols, int64_t nnz, const int32_t *indptr,
                                  const int32_t *indices, const double *data, int warps,
                                  int groups_per_warp, int chain_boxes, int cap16, int allow_compact,
