@@ -59,6 +59,7 @@ SIGNATURES = {
     "hmcb_create": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
     "hmcb_destroy": (C.c_int, [C.c_void_p]),
     "hmcb_set_integrator": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "hmcb_set_exact_arithmetic": (C.c_int, [C.c_void_p, C.c_int]),
     "hmcb_set_mass_unit": (C.c_int, [C.c_void_p]),
     "hmcb_set_mass_diagonal": (C.c_int, [C.c_void_p, _c_double_p, _c_double_p]),
     "hmcb_clear_target": (C.c_int, [C.c_void_p]),
@@ -146,7 +147,8 @@ class Engine:
     """One engine = one target distribution x one mass matrix x ``chains`` chains on one GPU."""
 
     def __init__(self, plan: Dict[str, Any], mass: Dict[str, Any], chains: int, *,
-                 integrator: str = "lf", amount_of_steps: int = 10, device: Optional[int] = None):
+                 integrator: str = "lf", amount_of_steps: int = 10, device: Optional[int] = None,
+                 exact: Optional[bool] = None):
         import torch
 
         if not torch.cuda.is_available():
@@ -171,6 +173,8 @@ class Engine:
         else:
             self._ok(self.lib.hmcb_set_mass_diagonal(
                 handle, _dp(_f64(mass["diagonal"])), _dp(_f64(mass["inverse_diagonal"]))))
+        if exact is not None:
+            self._ok(self.lib.hmcb_set_exact_arithmetic(handle, int(bool(exact))))
         self._lower(plan)
         self._ok(self.lib.hmcb_finalize(handle))
         self.path = PATH_NAMES[self.lib.hmcb_path(handle)]
@@ -263,6 +267,10 @@ class Engine:
         ms, n = (C.c_double * 2)(), (C.c_int64 * 2)()
         self._ok(self.lib.hmcb_kernel_timing_end(self._handle, ms, n))
         return [(float(ms[i]), int(n[i])) for i in range(2)]
+
+    def set_exact_arithmetic(self, on: bool):
+        """True: the priors-only fused kernel rounds multiply and add separately, as numpy does."""
+        self._ok(self.lib.hmcb_set_exact_arithmetic(self._handle, int(bool(on))))
 
     def set_integrator(self, integrator: str, amount_of_steps: int):
         if integrator not in INTEGRATORS:

@@ -90,6 +90,7 @@ struct hmcb_engine {
   std::vector<double> h_rx, h_ry, h_rz, h_tobs, h_std;
 
   bool finalized = false;
+  bool exact = false;      // hmcb_set_exact_arithmetic
   int path = -1;
   bool fused_dense = false;  // run_block uses the whole-proposal small-dense kernel
   int64_t launches = 0;
@@ -989,6 +990,7 @@ FusedArgs fused_args(const hmcb_engine* e, const hmcb_block* b) {
   A.trace_q = b->trace_q; A.trace_g = b->trace_g;
   A.stepsize_chain = b->stepsize_chain; A.out_stepsize = b->out_stepsize;
   A.tune = AutotuneArgs{b->autotune ? 1 : 0, b->target_acceptance_rate, b->learning_rate};
+  A.exact = e->exact ? 1 : 0;
   return A;
 }
 
@@ -1179,6 +1181,7 @@ int hmcb_create(int device, int64_t chains, int64_t dims, hmcb_engine** out) {
   HMCB_CUDA(cudaSetDevice(device));
   hmcb_engine* e = new hmcb_engine();
   e->device = device; e->C = chains; e->d = dims;
+  e->exact = env_int("HMCB_EXACT", 0) != 0;
   *out = e;
   return 0;
 }
@@ -1206,6 +1209,12 @@ int hmcb_set_integrator(hmcb_engine* e, int integrator, int amount_of_steps) {
   HMCB_CHECK(amount_of_steps > 0, "amount_of_steps must be a positive integer");
   e->integrator = integrator; e->steps = amount_of_steps;
   build_schedule(e);  // cheap; lets the integrator change after finalize
+  return 0;
+}
+
+int hmcb_set_exact_arithmetic(hmcb_engine* e, int on) {
+  HMCB_CHECK(e, "engine is NULL");
+  e->exact = on != 0;
   return 0;
 }
 

@@ -16,10 +16,14 @@ static cudaError_t launch_fp(const FusedArgs& A, cudaStream_t s) {
   constexpr int CPB = BLOCK / TPC;
   const int grid = (A.chains + CPB - 1) / CPB;
   // AUX: reflection bounds and/or a diagonal mass matrix live in registers too
-  if (A.T.invm || A.T.refl_lb || A.T.refl_ub)
-    hmc_fused_priors_kernel<TPC, PPT, true><<<grid, BLOCK, 0, s>>>(A);
-  else
-    hmc_fused_priors_kernel<TPC, PPT, false><<<grid, BLOCK, 0, s>>>(A);
+  const bool aux = A.T.invm || A.T.refl_lb || A.T.refl_ub;
+  if (A.exact) {
+    if (aux) hmc_fused_priors_kernel<TPC, PPT, true, false><<<grid, BLOCK, 0, s>>>(A);
+    else hmc_fused_priors_kernel<TPC, PPT, false, false><<<grid, BLOCK, 0, s>>>(A);
+  } else {
+    if (aux) hmc_fused_priors_kernel<TPC, PPT, true, true><<<grid, BLOCK, 0, s>>>(A);
+    else hmc_fused_priors_kernel<TPC, PPT, false, true><<<grid, BLOCK, 0, s>>>(A);
+  }
   return cudaGetLastError();
 }
 

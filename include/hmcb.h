@@ -74,6 +74,15 @@ int hmcb_destroy(hmcb_engine *e);
 /* tuning: HMC.sample(amount_of_steps=, integrator=) -- Samplers.py:1351-1358,1379-1384 */
 int hmcb_set_integrator(hmcb_engine *e, int integrator, int amount_of_steps);
 
+/* Arithmetic of the priors-only whole-proposal kernel (Samplers.py:1539-1584: `p -= eps * g`,
+ * `q += eps * dK/dp`).  on = 0 (default): each of the two updates is one fused multiply-add -- results
+ * agree with numpy's to the last few bits (far inside the 1e-10 parity bar; accept / reject decisions
+ * are unchanged).  on = 1: multiply and add are rounded separately, in the reference's operation
+ * order, and a trajectory on a separable target is bit-identical to numpy's.  Every other kernel
+ * always works in the reference's operation order.  May be changed at any time.  The environment
+ * variable HMCB_EXACT=1 makes exact the default. */
+int hmcb_set_exact_arithmetic(hmcb_engine *e, int on);
+
 /* MassMatrices.Unit (MassMatrices.py:82-156) */
 int hmcb_set_mass_unit(hmcb_engine *e);
 /* MassMatrices.Diagonal (MassMatrices.py:159-238); HOST arrays of `dims` doubles.

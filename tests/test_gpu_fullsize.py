@@ -165,7 +165,8 @@ def test_large_dims_priors_only_uses_staged_path_and_matches_oracle():
 
 
 def test_full_size_config2_fused_equals_staged_pipeline():
-    """4096 chains x 1000 dims, device RNG: two independent implementations, same chains."""
+    """4096 chains x 1000 dims, device RNG: two independent implementations, same chains (in exact
+    arithmetic bit for bit; the fused kernel's default FMA arithmetic within a few ulp of them)."""
     import torch
 
     from hmclab_b200._engine import Engine
@@ -174,11 +175,11 @@ def test_full_size_config2_fused_equals_staged_pipeline():
     assert (w.chains, w.dims) == (4096, 1000)
     plan, mplan = flatten(describe(w.posterior)), describe_mass(w.mass_matrix)
     results = {}
-    for label, force in (("fused", None), ("staged", "1")):
+    for label, force, exact in (("fused", None, True), ("staged", "1", True), ("fused_fma", None, False)):
         if force:
             os.environ["HMCB_FORCE_STAGED"] = force
         try:
-            eng = Engine(plan, mplan, w.chains, integrator="lf", amount_of_steps=10)
+            eng = Engine(plan, mplan, w.chains, integrator="lf", amount_of_steps=10, exact=exact)
         finally:
             os.environ.pop("HMCB_FORCE_STAGED", None)
         assert eng.path == ("staged" if force else "fused_priors")
@@ -197,6 +198,12 @@ def test_full_size_config2_fused_equals_staged_pipeline():
     assert 0.05 < f[2].mean() < 0.999                 # both decisions occur at this step size
     # energy error of a leapfrog trajectory is O(eps^2): a coarse sanity bound on H1 - H0
     assert np.median(np.abs(f[4] - f[3])) < 5.0
+    # the default arithmetic of the fused kernel (one FMA per update instead of multiply + add): the
+    # same decisions, positions and energies equal to a few ulp
+    m = results["fused_fma"]
+    assert np.array_equal(m[2], f[2])
+    assert rel_err(m[0], f[0]) < 1e-12 and rel_err(m[3], f[3]) < 1e-12 and rel_err(m[4], f[4]) < 1e-12
+    assert not np.array_equal(m[0], f[0])
 
 
 @pytest.mark.parametrize("name", ["normal_iid", "dense_large", "dense_large_premult", "tomography",
