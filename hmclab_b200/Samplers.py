@@ -619,8 +619,13 @@ class ParallelSampleSMP:
     shared posterior the exponent is exactly zero, so every scheduled swap is accepted: the
     exchange is a permutation of chain states after every ``exchange_interval``-th proposal,
     following a schedule drawn like the reference's (``rng.choice`` without replacement per
-    exchange round, :1872-1880).  Exchange between *different* posteriors (tempering) is not
-    offered.
+    exchange round, :1872-1880).
+
+    Chains with DIFFERENT posteriors (tempering ladders, competing models): the chains are grouped
+    by posterior object, every group is one batch on its own engine, and an exchange round
+    evaluates each scheduled chain's posterior at its partner's model on the device
+    (``hmcb_misfit``), applies the reference's acceptance test per pair and swaps the models
+    (``_sample_grouped``).
     """
 
     def __init__(self, seed=None):
@@ -654,10 +659,11 @@ class ParallelSampleSMP:
                 raise NotImplementedError("A batch of chains shares one set of tuning kwargs.")
             kwargs = kwargs[0]
         kwargs = dict(kwargs or {})
-        if any(p is not posteriors[0] for p in posteriors[1:]):
-            raise NotImplementedError(
-                "ParallelSampleSMP on the batched engine needs one shared posterior object for all "
-                "chains (exchange between different posteriors is not offered).")
+        if not all(isinstance(smp, HMC) for smp in samplers):
+            raise NotImplementedError("Only HMC samplers run on the batched engine.")
+        if any(p is not posteriors[0] for p in posteriors[1:]) or kwargs.pop("_grouped", False):
+            return self._sample_grouped(samplers, filenames, posteriors, proposals, exchange,
+                                        exchange_interval, initial_model, kwargs)
         if not all(isinstance(smp, HMC) for smp in samplers):
             raise NotImplementedError("Only HMC samplers run on the batched engine.")
         kwargs.pop("overwrite_existing_file", None)
@@ -719,6 +725,181 @@ class ParallelSampleSMP:
                 self._split(driver, combined, filenames)
         finally:
             driver._between_blocks = None
+        return self
+
+    def _sample_grouped(self, samplers, filenames, posteriors, proposals, exchange, exchange_interval,
+                        initial_model, kwargs):
+        """Chains whose posteriors differ: one engine per distinct posterior object, replica exchange
+        between the groups exactly as the reference defines it (Samplers.py:589-669):
+
+            after proposal k with k % exchange_interval == 0, for every scheduled pair (a, b):
+            improvement_i = chi_i(m_i) - chi_i(m_partner);  swap iff exp(improvement_a +
+            improvement_b) > u, u drawn by the pair's master (the odd position of the schedule row).
+
+        The row stored for proposal k shows the exchanged model next to the misfit the chain held
+        before the exchange -- what the reference writes, since it refreshes ``current_x`` only at the
+        next proposal; the chain itself continues with chi_i(m_partner).  Settings in ``kwargs`` are
+        shared by all chains; ``host_rng=True`` draws every chain's momenta and uniforms from its own
+        sampler's Generator in the reference's order (and then reproduces a reference run)."""
+        import torch
+
+        from hmclab_b200._engine import Engine
+        from hmclab_b200._lowering import describe, describe_mass, flatten
+
+        n = len(samplers)
+        known = {"stepsize", "amount_of_steps", "integrator", "randomize_stepsize", "online_thinning",
+                 "mass_matrix", "disable_progressbar", "host_rng", "device", "diagnostic_mode"}
+        unknown = set(kwargs) - known
+        if unknown:
+            raise TypeError(f"ParallelSampleSMP with several posteriors does not take {sorted(unknown)}")
+        stepsize = float(kwargs.get("stepsize", 0.1))
+        steps = int(kwargs.get("amount_of_steps", 10))
+        integrator = kwargs.get("integrator", "lf")
+        randomize = bool(kwargs.get("randomize_stepsize", True))
+        thin = int(kwargs.get("online_thinning", 1))
+        host_rng = bool(kwargs.get("host_rng", False))
+        assert stepsize > 0 and steps > 0 and thin > 0 and proposals % thin == 0
+        d = int(posteriors[0].dimensions)
+        assert all(int(p.dimensions) == d for p in posteriors), "all posteriors need the same dimensions"
+        mass = kwargs.get("mass_matrix")
+        if mass is None:
+            from hmclab_b200 import MassMatrices as _M
+
+            mass = _M.Unit(d)
+        if initial_model is None:
+            q0 = _numpy.zeros((n, d))
+        elif type(initial_model) == list:
+            q0 = _numpy.stack([_numpy.asarray(m, dtype=_numpy.float64).reshape(d) for m in initial_model])
+        else:
+            q0 = _numpy.repeat(_numpy.asarray(initial_model, dtype=_numpy.float64).reshape(1, d), n, axis=0)
+        dev_index = kwargs.get("device")
+        dev = torch.device("cuda", torch.cuda.current_device() if dev_index is None else int(dev_index))
+
+        # groups of chains sharing a posterior object: one engine each
+        groups = []
+        for i, post in enumerate(posteriors):
+            for g in groups:
+                if g["posterior"] is post:
+                    g["chains"].append(i)
+                    break
+            else:
+                groups.append({"posterior": post, "chains": [i]})
+        offset = 0
+        for g in groups:
+            ids = g["chains"]
+            g["engine"] = Engine(flatten(describe(g["posterior"])), describe_mass(mass), len(ids),
+                                 integrator=integrator, amount_of_steps=steps, device=dev.index)
+            g["ids"] = torch.as_tensor(ids, device=dev)
+            g["q"] = torch.as_tensor(q0[ids], dtype=torch.float64).to(dev).contiguous()
+            g["x"] = g["engine"].misfit(g["q"])
+            g["accepted"] = torch.zeros(len(ids), dtype=torch.int32, device=dev)
+            g["offset"] = offset
+            offset += len(ids)
+            assert bool(torch.isfinite(g["x"]).all()), "The initial model has a non-finite misfit."
+        where = {i: (gi, l) for gi, g in enumerate(groups) for l, i in enumerate(g["chains"])}
+
+        self.samplers = list(samplers)
+        self.exchange_schedule = None
+        if exchange:
+            assert type(exchange_interval) == int and exchange_interval > 0
+            pairs, rounds = n // 2, proposals // exchange_interval
+            self.exchange_schedule = (
+                _numpy.vstack([self.rng.choice(n, pairs * 2, replace=False) for _ in range(rounds)])
+                if pairs and rounds else _numpy.zeros((0, 0), dtype=int))
+        device_seed = int(self.rng.integers(0, 2**63 - 1))
+        rows_host = [[] for _ in range(n)]       # stored rows per chain
+        self.exchanges_accepted = 0
+        done = 0
+        while done < proposals:
+            if exchange:   # blocks end right after the proposals k with k % interval == 0
+                nxt = done if done % exchange_interval == 0 else (done // exchange_interval + 1) * exchange_interval
+                B = min(nxt - done + 1, proposals - done)
+            else:
+                B = min(256, proposals - done)
+            bufs = []
+            for g in groups:
+                eng, C = g["engine"], len(g["chains"])
+                rows = eng.stored_rows(B, thin, done)
+                buf = torch.empty(rows, C, d + 1, dtype=torch.float64, device=dev) if rows else None
+                draws = {}
+                if host_rng:
+                    z, us, ua = _numpy.empty((B, C, d)), _numpy.ones((B, C)), _numpy.empty((B, C))
+                    for l, i in enumerate(g["chains"]):
+                        rng = samplers[i].rng
+                        for k in range(B):
+                            z[k, l] = rng.normal(size=(d, 1))[:, 0]
+                            if randomize:
+                                us[k, l] = rng.uniform(0.5, 1.5)
+                            ua[k, l] = rng.uniform(0, 1)
+                    draws = dict(z=torch.as_tensor(z).to(dev), u_step=torch.as_tensor(us).to(dev),
+                                 u_accept=torch.as_tensor(ua).to(dev))
+                eng.run_block(g["q"], g["x"], B, stepsize=stepsize, randomize_stepsize=randomize, thinning=thin,
+                              proposal_offset=done, chain_offset=g["offset"], seed=device_seed, out_samples=buf,
+                              accepted_total=g["accepted"], **draws)
+                bufs.append(buf)
+            k = done + B - 1
+            if exchange and k % exchange_interval == 0 and k // exchange_interval < self.exchange_schedule.shape[0]:
+                row = self.exchange_schedule[k // exchange_interval]
+                partner = _numpy.arange(n)
+                for a, b in row.reshape(-1, 2):
+                    partner[a], partner[b] = b, a
+                Q = torch.empty(n, d, dtype=torch.float64, device=dev)
+                X = torch.empty(n, dtype=torch.float64, device=dev)
+                for g in groups:
+                    Q[g["ids"]] = g["q"]
+                    X[g["ids"]] = g["x"]
+                Xex = torch.empty(n, dtype=torch.float64, device=dev)
+                for g in groups:     # chi_i(m_partner) for every chain of the group, on the device
+                    theirs = Q[torch.as_tensor(partner[g["chains"]], device=dev)].contiguous()
+                    Xex[g["ids"]] = g["engine"].misfit(theirs)
+                improvement = (X - Xex).cpu().numpy()
+                xex = Xex.cpu().numpy()
+                for a, b in row.reshape(-1, 2):          # a: even position, b: odd position = master
+                    u = samplers[b].rng.uniform(0, 1) if host_rng else self.rng.uniform(0, 1)
+                    with _numpy.errstate(all="ignore"):
+                        accept = _numpy.exp(improvement[a] + improvement[b]) > u
+                    if not accept:
+                        continue
+                    self.exchanges_accepted += 1
+                    (ga, la), (gb, lb) = where[a], where[b]
+                    ma, mb = groups[ga]["q"][la].clone(), groups[gb]["q"][lb].clone()
+                    groups[ga]["q"][la], groups[gb]["q"][lb] = mb, ma
+                    groups[ga]["x"][la], groups[gb]["x"][lb] = float(xex[a]), float(xex[b])
+                    if k % thin == 0:      # the stored row: exchanged model, misfit from before the exchange
+                        bufs[ga][-1, la, :d] = mb
+                        bufs[gb][-1, lb, :d] = ma
+            for g, buf in zip(groups, bufs):
+                if buf is not None:
+                    host = buf.cpu().numpy()
+                    for l, i in enumerate(g["chains"]):
+                        rows_host[i].append(host[:, l, :])
+            done += B
+        torch.cuda.synchronize(dev)
+        for g in groups:
+            acc = g["accepted"].cpu().numpy()
+            qf, xf = g["q"].cpu().numpy(), g["x"].cpu().numpy()
+            for l, i in enumerate(g["chains"]):
+                smp = samplers[i]
+                smp.accepted_proposals = int(acc[l])
+                smp.current_proposal = proposals - 1
+                smp.current_model = qf[l][:, None].copy()
+                smp.current_x = float(xf[l])
+            g["engine"].close()
+        for i, name in enumerate(filenames):
+            rows = _numpy.concatenate(rows_host[i]) if rows_host[i] else _numpy.zeros((0, d + 1))
+            out = _Samples(name, mode="w", overwrite=True)
+            out.allocate(1, rows.shape[0], d)
+            if rows.shape[0]:
+                out.write_block(_numpy.ascontiguousarray(rows[:, None, :]))
+            out.write_attribute("proposals", proposals)
+            out.write_attribute("online_thinning", thin)
+            out.write_attribute("sampler", "Hamiltonian Monte Carlo")
+            out.write_attribute("stepsize", stepsize)
+            out.write_attribute("amount_of_steps", steps)
+            out.write_attribute("integrator", integrator)
+            out.write_attribute("acceptance_rate", samplers[i].accepted_proposals / max(1, proposals))
+            out.write_attribute("chain_index", i)
+            out.close()
         return self
 
     @staticmethod

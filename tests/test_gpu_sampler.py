@@ -341,3 +341,52 @@ def test_diagnostic_mode_reports_block_shares(tmp_path, capsys):
                        chains=4, diagnostic_mode=True)
     out = capsys.readouterr().out
     assert "Detailed statistics" in out and "device blocks" in out and "fused_priors" in out
+
+
+def test_replica_exchange_between_different_posteriors_matches_the_reference(tmp_path):
+    """ParallelSampleSMP with two different posteriors (a cold and a hot Normal, two chains each):
+    the reference's own multi-process run (tests/golden/exchange_runs.npz, written by
+    tests/golden/make_golden_exchange.py from the unmodified hmclab) is reproduced file by file --
+    HMC proposals, exchange decisions (Samplers.py:589-669), swapped models, and the misfit column
+    that still shows the pre-exchange value in the row written right after a swap."""
+    from hmclab_b200 import Distributions as D
+    from hmclab_b200.Samplers import HMC, ParallelSampleSMP
+    from hmclab_b200.Samples import Samples
+
+    gold = np.load(os.path.join(GOLDEN_DIR, "exchange_runs.npz"))
+    st = {k[len("setting_"):]: gold[k] for k in gold.files if k.startswith("setting_")}
+    n, d = int(st["chains"]), int(st["dims"])
+    mean, var = gold["mean"][:, None], gold["var"][:, None]
+    cold, hot = D.Normal(mean, var), D.Normal(mean + 0.3, 3.0 * var)
+    posts = [cold, hot, cold, hot]
+    names = [str(tmp_path / f"chain{i}.npy") for i in range(n)]
+    samplers = [HMC(seed=int(s)) for s in st["sampler_seeds"]]
+    smp = ParallelSampleSMP(seed=int(st["smp_seed"]))
+    smp.sample(samplers, names, posts, overwrite_existing_files=True, proposals=int(st["proposals"]),
+               exchange=True, exchange_interval=int(st["exchange_interval"]),
+               initial_model=[q[:, None] for q in gold["q0"]],
+               kwargs=dict(stepsize=float(st["stepsize"]), amount_of_steps=int(st["amount_of_steps"]),
+                           integrator=str(st["integrator"]), randomize_stepsize=bool(st["randomize_stepsize"]),
+                           online_thinning=int(st["online_thinning"]), disable_progressbar=True, host_rng=True))
+    assert np.array_equal(smp.exchange_schedule, gold["schedule"])
+    assert smp.exchanges_accepted > 0
+    moved = 0
+    for i in range(n):
+        ref = gold[f"samples{i}"]
+        got = np.load(names[i])
+        assert got.shape == ref.shape
+        assert rel_err(got, ref) < TOL
+        # rows where the model changed although the misfit column did not: accepted exchanges
+        same_x = np.diff(ref[:, -1]) == 0
+        changed = np.any(np.diff(ref[:, :-1], axis=0) != 0, axis=1)
+        moved += int(np.sum(same_x & changed))
+        with Samples(names[i]) as s:
+            assert s.numpy.shape == (d + 1, ref.shape[0])
+    assert moved > 0      # the golden run does contain accepted exchanges
+    # device random streams: the same call runs without host draws, chains keep their own posterior
+    smp2 = ParallelSampleSMP(seed=1)
+    smp2.sample([HMC(seed=i) for i in range(n)], names, posts, overwrite_existing_files=True, proposals=40,
+                exchange=True, exchange_interval=4, initial_model=[q[:, None] for q in gold["q0"]],
+                kwargs=dict(stepsize=0.3, amount_of_steps=4, online_thinning=2))
+    for i in range(n):
+        assert np.load(names[i]).shape == (20, d + 1) and np.all(np.isfinite(np.load(names[i])))
