@@ -266,8 +266,8 @@ def test_parallel_sample_smp_front_end(tmp_path):
     assert np.array_equal(far, plain)
     with pytest.raises(AssertionError, match="overwriting"):
         ParallelSampleSMP().sample([HMC()], names[:1], [w.posterior])
-    with pytest.raises(NotImplementedError):
-        other = workloads.dense_small(chains=1).posterior
+    with pytest.raises(AssertionError, match="same dimensions"):   # different posteriors are fine, different sizes not
+        other = workloads.normal_iid(dims=w.dims + 3, chains=1).posterior
         ParallelSampleSMP().sample([HMC(), HMC()], names[:2], [w.posterior, other],
                                    overwrite_existing_files=True)
 
