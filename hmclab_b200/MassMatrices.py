@@ -1,6 +1,6 @@
-"""Mass matrices (HMC metrics) of the batched engine: ``Unit`` and ``Diagonal``.
+"""Mass matrices (HMC metrics) of the batched engine: ``Unit``, ``Diagonal`` and ``Full``.
 
-Host-side mirror of hmclab/MassMatrices.py:27-238.  The objects hold the metric;
+Host-side mirror of hmclab/MassMatrices.py:27-327.  The objects hold the metric;
 momentum generation, kinetic energy and its gradient are fused into the CUDA
 integrator kernels.  The single-vector methods below run those kernels on a batch
 of one chain (they exist so the reference's mass-matrix tests can be replayed).
@@ -86,3 +86,34 @@ class Diagonal(_AbstractMassMatrix):
     @staticmethod
     def create_default(dimensions: int, rng=None) -> "Diagonal":
         return Diagonal(_numpy.ones((dimensions, 1)), rng=rng)
+
+
+class Full(_AbstractMassMatrix):
+    """Dense symmetric positive definite metric (MassMatrices.py:241-327): momentum
+    ``cholesky @ normal``, kinetic energy ``0.5 p . M^-1 p``, gradient ``M^-1 p``.  The reference
+    solves with the Cholesky factor (scipy ``cho_solve``) per call; on the batch ``M^-1`` (formed
+    once from that factor) and the factor itself are applied as fp64 tensor-core products."""
+
+    def __init__(self, full, rng=None, do_hermitian_check=True):
+        from scipy.linalg import cho_factor, cho_solve
+
+        self.name = "diagonal mass matrix"      # sic: the reference's Full carries this name (:258)
+        self.mass_matrix = _numpy.asarray(full, dtype=_numpy.float64)
+        if do_hermitian_check:
+            assert _numpy.allclose(self.mass_matrix, self.mass_matrix.T)
+        self.cholesky, self.cholesky_lower = cho_factor(self.mass_matrix, lower=True)
+        self.cholesky = _numpy.tril(self.cholesky)
+        self.dimensions = int(self.mass_matrix.shape[0])
+        self.inverse = cho_solve((self.cholesky, self.cholesky_lower), _numpy.eye(self.dimensions))
+        if rng is not None:
+            self.rng = rng
+
+    @property
+    def matrix(self):
+        return self.mass_matrix
+
+    @staticmethod
+    def create_default(dimensions: int, rng=None) -> "Full":
+        mass_matrix = (_numpy.eye(dimensions) + 0.1 * _numpy.eye(dimensions, k=-1)
+                       + 0.1 * _numpy.eye(dimensions, k=1))
+        return Full(mass_matrix, rng=rng)

@@ -62,6 +62,7 @@ SIGNATURES = {
     "hmcb_set_exact_arithmetic": (C.c_int, [C.c_void_p, C.c_int]),
     "hmcb_set_mass_unit": (C.c_int, [C.c_void_p]),
     "hmcb_set_mass_diagonal": (C.c_int, [C.c_void_p, _c_double_p, _c_double_p]),
+    "hmcb_set_mass_full": (C.c_int, [C.c_void_p, _c_double_p, _c_double_p]),
     "hmcb_clear_target": (C.c_int, [C.c_void_p]),
     "hmcb_add_prior": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, _c_double_p,
                                  _c_double_p, C.c_double]),
@@ -170,6 +171,8 @@ class Engine:
         self._ok(self.lib.hmcb_set_integrator(handle, INTEGRATORS[integrator], int(amount_of_steps)))
         if mass["kind"] == "unit":
             self._ok(self.lib.hmcb_set_mass_unit(handle))
+        elif mass["kind"] == "full":
+            self._ok(self.lib.hmcb_set_mass_full(handle, _dp(_f64(mass["cholesky"])), _dp(_f64(mass["inverse"]))))
         else:
             self._ok(self.lib.hmcb_set_mass_diagonal(
                 handle, _dp(_f64(mass["diagonal"])), _dp(_f64(mass["inverse_diagonal"]))))

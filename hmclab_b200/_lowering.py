@@ -200,8 +200,20 @@ def describe_mass(mass) -> Dict[str, Any]:
             "diagonal": _vec(mass.diagonal, n, "diagonal"),
             "inverse_diagonal": _vec(mass.inverse_diagonal, n, "inverse_diagonal"),
         }
+    if cls == "Full":
+        # MassMatrices.py:241-327; genuine reference objects carry the factor but no inverse
+        from scipy.linalg import cho_solve
+
+        chol = np.ascontiguousarray(np.tril(np.asarray(mass.cholesky, dtype=np.float64)))
+        if chol.shape != (n, n):
+            raise ValueError("Full mass matrix: the Cholesky factor has the wrong shape.")
+        inverse = getattr(mass, "inverse", None)
+        if inverse is None:
+            inverse = cho_solve((chol, True), np.eye(n))
+        return {"kind": "full", "dims": n, "cholesky": chol,
+                "inverse": np.ascontiguousarray(inverse, dtype=np.float64)}
     raise NotImplementedError(
-        f"Mass matrix `{cls}` is not on the batched B200 path (Unit, Diagonal)."
+        f"Mass matrix `{cls}` is not on the batched B200 path (Unit, Diagonal, Full)."
     )
 
 

@@ -23,6 +23,7 @@ constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 16;
 constexpr int GEMM_LDA_S = GEMM_BK + 4;   // 20 doubles
 constexpr int GEMM_LDB_S = GEMM_BN + 4;   // 132 doubles
 constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_GROUP_M = 16;   // row tiles per group of the tile order (L2 reuse)
 constexpr int GEMM_THREADS = 256;                      // 8 consumer warps
 constexpr int GEMM_LAUNCH_THREADS = GEMM_THREADS + 32;  // + 1 producer warp
 constexpr int GEMM_A_STAGE = GEMM_BM * GEMM_LDA_S;  // doubles
@@ -87,7 +88,16 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps
-  const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * GEMM_BN;
+  // Tile order: the blocks of a launch are numbered along x first; walking the tiles in that order
+  // row by row re-reads the whole chain batch B once per wave (5 GB of DRAM reads for a product whose
+  // operands are 0.8 GB).  Grouped order instead: GEMM_GROUP_M row tiles are swept column by column, so
+  // a wave of 148 blocks works on ~16 row tiles x ~9 column tiles whose operands stay in L2.
+  const int tiles_n = gridDim.x, tiles_m = gridDim.y;
+  const int lin = blockIdx.y * tiles_n + blockIdx.x;
+  const int group = lin / (GEMM_GROUP_M * tiles_n), first_m = group * GEMM_GROUP_M;
+  const int gsz = min(tiles_m - first_m, GEMM_GROUP_M), in_group = lin - group * GEMM_GROUP_M * tiles_n;
+  const int tile_m = first_m + in_group % gsz, tile_n = in_group / gsz;
+  const int m0 = tile_m * GEMM_BM, n0 = tile_n * GEMM_BN;
   const int ktiles = K / GEMM_BK;
 
   double acc[8][4][2];
@@ -135,7 +145,7 @@ dmma_gemm_kernel(const double* __restrict__ A, int lda, const double* __restrict
   __syncthreads();
   constexpr unsigned kStageBytes = (GEMM_A_STAGE + GEMM_BK * GEMM_BN) * sizeof(double);
   if (warp == GEMM_THREADS / 32) {
-    const double* a_tiles = A + (size_t)blockIdx.y * ktiles * GEMM_A_STAGE;
+    const double* a_tiles = A + (size_t)tile_m * ktiles * GEMM_A_STAGE;
     for (int kt = 0; kt < ktiles; ++kt) {
       const int stage = kt % GEMM_STAGES, use = kt / GEMM_STAGES;
       if (use > 0) mbar_wait(&empty_bar[stage], (unsigned)((use - 1) & 1));

@@ -70,6 +70,9 @@ struct hmcb_engine {
   int steps = 10;
   bool mass_diag = false;
   std::vector<double> h_diag, h_invdiag;
+  bool mass_full = false;              // MassMatrices.Full: p = L z, dK/dp = M^-1 p as GEMMs over the batch
+  std::vector<double> h_L, h_Minv;     // [d x d] row-major: lower Cholesky factor, inverse
+  double *dL = nullptr, *dMinv = nullptr, *v_w = nullptr;
   std::vector<HostPrior> priors;
   std::vector<HostCheck> checks;
   bool has_rlb = false, has_rub = false;
@@ -211,6 +214,7 @@ void free_device(hmcb_engine* e) {
   e->fused_dense = false;
   e->rw_qp = e->rw_x1 = nullptr;
   e->dA = e->dAt = e->dA_rowmajor = e->dvec = e->dvar = e->dsigma = nullptr;
+  e->dL = e->dMinv = e->v_w = nullptr;
   e->q_cur = e->q_w[0] = e->q_w[1] = e->p_w = e->R = nullptr;
   e->eps = e->uacc = e->k0part = e->k1part = e->upart = e->lpart = nullptr;
   e->flags[0] = e->flags[1] = e->flags[2] = nullptr;
@@ -894,6 +898,78 @@ DecideArgs decide_args(const hmcb_engine* e) {
   return D;
 }
 
+// dK/dp = M^-1 p for the whole batch (Full mass matrix): v_w = Minv . p_w
+int full_mass_velocity(hmcb_engine* e, cudaStream_t s) {
+  StoreEpi st{(int)e->d, (int)e->C, e->ld, e->v_w};
+  HMCB_CUDA(launch_gemm_store(e->dMinv, e->dpad, e->dpad, e->p_w, e->ld, e->dpad, st, s));
+  e->launches += 1;
+  return 0;
+}
+
+// One trajectory with a Full mass matrix (MassMatrices.py:241-327): p = L z and dK/dp = M^-1 p are DMMA
+// GEMMs over the chain batch; the momentum update stays fused into the likelihood GEMM / SpMM epilogue,
+// the position update (which needs M^-1 p of the updated momentum over all coordinates) follows as a
+// GEMM + an elementwise kernel.  Works in place on q_w[0]; q_w[1] is the scratch plane of the draws.
+int full_mass_trajectory(hmcb_engine* e, const hmcb_block* b, const StagedCommon& SC, int64_t kglob, size_t kc,
+                         bool grad_checks, int* cur_out, int* fcur_out, cudaStream_t s) {
+  const int C = (int)e->C, d = (int)e->d, ld = e->ld;
+  const size_t flag_bytes = (size_t)ld * sizeof(unsigned);
+  const int G = e->S.grads_per_proposal;
+  const bool reflects = e->T.refl_lb != nullptr || e->T.refl_ub != nullptr;
+  int fcur = *fcur_out;
+  double* q = e->q_w[0];
+  StagedCommon SD = SC;
+  SD.draw_only = 1;
+  HMCB_CUDA(launch_st_begin(SD, kglob, 0.0, e->q_cur, q, e->q_w[1], b->z_in ? b->z_in + kc * d : nullptr,
+                            b->u_step_in ? b->u_step_in + kc : nullptr,
+                            b->u_accept_in ? b->u_accept_in + kc : nullptr, e->eps, e->uacc, e->k0part, nullptr,
+                            b->out_stepsize ? b->out_stepsize + kc : nullptr, s));
+  StoreEpi to_p{d, C, ld, e->p_w};
+  HMCB_CUDA(launch_gemm_store(e->dL, e->dpad, e->dpad, e->q_w[1], ld, e->dpad, to_p, s));   // p = L z
+  e->launches += 2;
+  if (full_mass_velocity(e, s)) return -1;
+  StagedCommon SV = SC;
+  SV.v = e->v_w;
+  bool v_valid = true;
+  // first (lone) position update + the kinetic energy of the drawn momentum
+  HMCB_CUDA(launch_st_kpos(SV, e->ops[0].a, e->q_cur, q, e->p_w, e->eps, e->k0part,
+                           grad_checks ? e->flags[fcur] : nullptr, s));
+  e->launches += 1;
+  if (reflects) v_valid = false;
+  int gi = 0;
+  for (size_t o = 1; o < e->ops.size(); ++o) {
+    const StageOp& op = e->ops[o];
+    if (op.has_b) {
+      UpdateEpi epi{};
+      epi.T = e->T; epi.C = C; epi.ld = ld;
+      epi.q_out = q; epi.p = e->p_w; epi.eps = e->eps;
+      epi.b_mult = op.b; epi.a_mult = 0.0; epi.momentum_only = 1;
+      if (grad_checks) epi.flags_in = e->flags[fcur];
+      if (b->trace_q) {
+        const size_t off = (((size_t)(kglob - b->proposal_offset) * G + gi) * C) * d;
+        epi.trace_q = b->trace_q + off;
+        epi.trace_g = b->trace_g + off;
+      }
+      if (staged_gradient_pass(e, q, epi, s)) return -1;
+      ++gi;
+      v_valid = false;
+    }
+    if (!v_valid && full_mass_velocity(e, s)) return -1;
+    v_valid = true;
+    if (grad_checks) {
+      fcur ^= 1;
+      HMCB_CUDA(cudaMemsetAsync(e->flags[fcur], 0, flag_bytes, s));
+    }
+    HMCB_CUDA(launch_st_kpos(SV, op.a, q, q, e->p_w, e->eps, nullptr, grad_checks ? e->flags[fcur] : nullptr, s));
+    e->launches += 1;
+    if (reflects) v_valid = false;
+  }
+  if (!v_valid && full_mass_velocity(e, s)) return -1;   // the energies need M^-1 p of the final momentum
+  *cur_out = 0;
+  *fcur_out = fcur;
+  return 0;
+}
+
 int staged_run_block(hmcb_engine* e, const hmcb_block* b, cudaStream_t s) {
   const int C = (int)e->C, d = (int)e->d, ld = e->ld;
   const bool grad_checks = e->T.grad_check_mask != 0u;
@@ -912,6 +988,9 @@ int staged_run_block(hmcb_engine* e, const hmcb_block* b, cudaStream_t s) {
     const size_t kc = (size_t)kb * C;
     int cur = 0, fcur = 0;
     if (grad_checks) HMCB_CUDA(cudaMemsetAsync(e->flags[fcur], 0, flag_bytes, s));
+    if (e->mass_full) {
+      if (full_mass_trajectory(e, b, SC, kglob, kc, grad_checks, &cur, &fcur, s)) return -1;
+    } else {
     HMCB_CUDA(launch_st_begin(SC, kglob, e->ops[0].a, e->q_cur, e->q_w[cur], e->p_w,
                               b->z_in ? b->z_in + kc * d : nullptr,
                               b->u_step_in ? b->u_step_in + kc : nullptr,
@@ -946,9 +1025,12 @@ int staged_run_block(hmcb_engine* e, const hmcb_block* b, cudaStream_t s) {
         e->launches += 1;
       }
     }
+    }   // !mass_full
     // energies, decision, state update
     if (any_checks) HMCB_CUDA(cudaMemsetAsync(e->flags[2], 0, flag_bytes, s));
-    HMCB_CUDA(launch_st_energy(SC, e->q_w[cur], e->p_w, e->k1part, e->upart,
+    StagedCommon SE = SC;
+    if (e->mass_full) SE.v = e->v_w;      // K = 0.5 p . M^-1 p (full_mass_trajectory left v current)
+    HMCB_CUDA(launch_st_energy(SE, e->q_w[cur], e->p_w, e->k1part, e->upart,
                                any_checks ? e->flags[2] : nullptr, s));
     e->launches += 1;
     if (staged_misfit_pass(e, e->q_w[cur], s)) return -1;
@@ -1221,7 +1303,7 @@ int hmcb_set_exact_arithmetic(hmcb_engine* e, int on) {
 int hmcb_set_mass_unit(hmcb_engine* e) {
   HMCB_CHECK(e, "engine is NULL");
   HMCB_CHECK(!e->finalized, "mass matrix must be set before hmcb_finalize");
-  e->mass_diag = false;
+  e->mass_diag = false; e->mass_full = false;
   return 0;
 }
 
@@ -1232,7 +1314,20 @@ int hmcb_set_mass_diagonal(hmcb_engine* e, const double* diagonal, const double*
     HMCB_CHECK(diagonal[j] > 0.0, "hmcb_set_mass_diagonal: diagonal entries must be positive");
   copy_vec(e->h_diag, diagonal, e->d);
   copy_vec(e->h_invdiag, inverse_diagonal, e->d);
-  e->mass_diag = true;
+  e->mass_diag = true; e->mass_full = false;
+  return 0;
+}
+
+int hmcb_set_mass_full(hmcb_engine* e, const double* cholesky_lower, const double* inverse) {
+  HMCB_CHECK(e && cholesky_lower && inverse, "hmcb_set_mass_full: NULL argument");
+  HMCB_CHECK(!e->finalized, "mass matrix must be set before hmcb_finalize");
+  for (int64_t j = 0; j < e->d; ++j)
+    HMCB_CHECK(cholesky_lower[(size_t)j * e->d + j] > 0.0, "hmcb_set_mass_full: the Cholesky factor needs a positive diagonal");
+  copy_vec(e->h_L, cholesky_lower, e->d * e->d);
+  copy_vec(e->h_Minv, inverse, e->d * e->d);
+  for (int64_t i = 0; i < e->d; ++i)          // the factor is lower triangular: make that exact
+    for (int64_t j = i + 1; j < e->d; ++j) e->h_L[(size_t)i * e->d + j] = 0.0;
+  e->mass_full = true; e->mass_diag = false;
   return 0;
 }
 
@@ -1460,6 +1555,7 @@ int hmcb_finalize(hmcb_engine* e) {
 
   // ---- path ------------------------------------------------------------------------
   if (e->lik == LK_SRCLOC) {
+    HMCB_CHECK(!e->mass_full, "a Full mass matrix is not supported together with a SourceLocation likelihood");
     e->path = HMCB_PATH_FUSED_SRCLOC;
     SrcLocDev& L = e->L;
     L.events = (int)e->events; L.stations = (int)e->stations; L.infer_velocity = e->infer_velocity;
@@ -1468,7 +1564,8 @@ int hmcb_finalize(hmcb_engine* e) {
     if (dev_upload(e, e->h_rx, &L.rx) || dev_upload(e, e->h_ry, &L.ry) || dev_upload(e, e->h_rz, &L.rz) ||
         dev_upload(e, e->h_tobs, &L.tobs) || dev_upload(e, e->h_std, &L.std))
       return -1;
-  } else if (e->lik == LK_NONE && T.n_terms <= 1 && fused_priors_supported(d) && !std::getenv("HMCB_FORCE_STAGED")) {
+  } else if (e->lik == LK_NONE && T.n_terms <= 1 && fused_priors_supported(d) && !e->mass_full &&
+             !std::getenv("HMCB_FORCE_STAGED")) {
     e->path = HMCB_PATH_FUSED_PRIORS;
   } else {
     e->path = HMCB_PATH_STAGED;
@@ -1537,8 +1634,13 @@ int hmcb_finalize(hmcb_engine* e) {
     if (e->ltiles && dev_alloc(e, (size_t)e->ltiles * e->ld, &e->lpart)) return -1;
     // small premultiplied dense models: the whole block of proposals runs in one kernel with
     // GtG resident in shared memory (the staged workspaces still serve hmcb_misfit/gradient)
-    e->fused_dense = e->lik == LK_DENSE_PREMULT && e->dpad == 128 && T.n_terms <= 1 &&
+    e->fused_dense = e->lik == LK_DENSE_PREMULT && e->dpad == 128 && T.n_terms <= 1 && !e->mass_full &&
                      !std::getenv("HMCB_FORCE_STAGED");
+    if (e->mass_full) {
+      if (dev_upload_tiled(e, e->h_L.data(), d, d, e->dpad, e->dpad, &e->dL) ||
+          dev_upload_tiled(e, e->h_Minv.data(), d, d, e->dpad, e->dpad, &e->dMinv) ||
+          dev_alloc(e, plane, &e->v_w)) return -1;
+    }
     // the host copies of the big operands are no longer needed
     std::vector<double>().swap(e->h_A);
     std::vector<double>().swap(e->h_At);
@@ -1655,9 +1757,21 @@ int hmcb_reflect(hmcb_engine* e, double* q, double* p, void* stream) {
   return 0;
 }
 
+// Full mass matrix: out = A . in for chain-major [C x d] batches through the transposed planes
+static int full_mass_apply(hmcb_engine* e, const double* A_tiled, const double* in, double* out, cudaStream_t s) {
+  const int C = (int)e->C, d = (int)e->d;
+  HMCB_CUDA(launch_st_transpose(in, C, d, d, e->q_w[1], e->ld, s));
+  StoreEpi st{d, C, e->ld, e->v_w};
+  HMCB_CUDA(launch_gemm_store(A_tiled, e->dpad, e->dpad, e->q_w[1], e->ld, e->dpad, st, s));
+  if (out) HMCB_CUDA(launch_st_transpose(e->v_w, d, C, e->ld, out, d, s));
+  e->launches += out ? 3 : 2;
+  return 0;
+}
+
 int hmcb_scale_momentum(hmcb_engine* e, const double* z, double* p, void* stream) {
   HMCB_READY(e);
   HMCB_CHECK(z && p, "hmcb_scale_momentum: NULL argument");
+  if (e->mass_full) return full_mass_apply(e, e->dL, z, p, static_cast<cudaStream_t>(stream));
   HMCB_CUDA(launch_mass_elementwise(e->T, (int)e->C, 0, z, p, static_cast<cudaStream_t>(stream)));
   e->launches += 1;
   return 0;
@@ -1666,6 +1780,16 @@ int hmcb_scale_momentum(hmcb_engine* e, const double* z, double* p, void* stream
 int hmcb_kinetic_energy(hmcb_engine* e, const double* p, double* k, void* stream) {
   HMCB_READY(e);
   HMCB_CHECK(p && k, "hmcb_kinetic_energy: NULL argument");
+  if (e->mass_full) {   // K = 0.5 p . M^-1 p: v_w = M^-1 p, p is still in q_w[1]
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (full_mass_apply(e, e->dMinv, p, nullptr, s)) return -1;
+    StagedCommon SV = staged_common(e, nullptr);
+    SV.v = e->v_w;
+    HMCB_CUDA(launch_st_energy(SV, e->q_w[1], e->q_w[1], e->k1part, e->upart, nullptr, s));
+    HMCB_CUDA(launch_st_colsum(e->k1part, e->jtiles, e->ld, (int)e->C, 0.5, k, s));
+    e->launches += 2;
+    return 0;
+  }
   HMCB_CUDA(launch_kinetic_energy(e->T, (int)e->C, p, k, static_cast<cudaStream_t>(stream)));
   e->launches += 1;
   return 0;
@@ -1674,6 +1798,7 @@ int hmcb_kinetic_energy(hmcb_engine* e, const double* p, double* k, void* stream
 int hmcb_kinetic_gradient(hmcb_engine* e, const double* p, double* dk, void* stream) {
   HMCB_READY(e);
   HMCB_CHECK(p && dk, "hmcb_kinetic_gradient: NULL argument");
+  if (e->mass_full) return full_mass_apply(e, e->dMinv, p, dk, static_cast<cudaStream_t>(stream));
   HMCB_CUDA(launch_mass_elementwise(e->T, (int)e->C, 1, p, dk, static_cast<cudaStream_t>(stream)));
   e->launches += 1;
   return 0;

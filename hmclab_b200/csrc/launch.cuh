@@ -52,6 +52,12 @@ cudaError_t launch_gemm_residual(const double* A, int lda, int M, const double* 
                                  const ResidualEpi& epi, cudaStream_t s);
 cudaError_t launch_gemm_misfit(const double* A, int lda, int M, const double* B, int ldb, int K,
                                const MisfitEpi& epi, cudaStream_t s);
+cudaError_t launch_gemm_store(const double* A, int lda, int M, const double* B, int ldb, int K,
+                              const StoreEpi& epi, cudaStream_t s);
+cudaError_t launch_st_kpos(const StagedCommon& S, double a_mult, const double* q_in, double* q_out, double* p,
+                           const double* eps, double* k0part, unsigned* flags_out, cudaStream_t s);
+cudaError_t launch_st_colsum(const double* part, int tiles, int ld, int C, double scale, double* out,
+                             cudaStream_t s);
 struct CsrDev {
   const int* indptr;
   const int* indices;

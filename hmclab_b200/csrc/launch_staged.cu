@@ -13,7 +13,10 @@ cudaError_t staged_init() {
   e = cudaFuncSetAttribute(dmma_gemm_kernel<ResidualEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)GEMM_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(dmma_gemm_kernel<MisfitEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(dmma_gemm_kernel<MisfitEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)GEMM_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(dmma_gemm_kernel<StoreEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)GEMM_SMEM_BYTES);
 }
 
@@ -78,6 +81,23 @@ cudaError_t launch_st_begin(const StagedCommon& S, long long kglob, double a_mul
 cudaError_t launch_st_position(const StagedCommon& S, double a_mult, double* q_w, double* p,
                                const double* eps, unsigned* flags_out, cudaStream_t s) {
   st_position_kernel<<<st_grid(S), ST_THREADS, 0, s>>>(S, a_mult, q_w, p, eps, flags_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_store(const double* A, int lda, int M, const double* B, int ldb, int K,
+                              const StoreEpi& epi, cudaStream_t s) {
+  return launch_gemm(A, lda, M, B, ldb, K, epi, s);
+}
+
+cudaError_t launch_st_kpos(const StagedCommon& S, double a_mult, const double* q_in, double* q_out, double* p,
+                           const double* eps, double* k0part, unsigned* flags_out, cudaStream_t s) {
+  st_kpos_kernel<<<st_grid(S), ST_THREADS, 0, s>>>(S, a_mult, q_in, q_out, p, eps, k0part, flags_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_st_colsum(const double* part, int tiles, int ld, int C, double scale, double* out,
+                             cudaStream_t s) {
+  st_colsum_kernel<<<(C + ST_THREADS - 1) / ST_THREADS, ST_THREADS, 0, s>>>(part, tiles, ld, C, scale, out);
   return cudaGetLastError();
 }
 

@@ -38,6 +38,8 @@ struct UpdateEpi {
   double* trace_q;           // chain-major [C x d] slices for this gradient evaluation, or null
   double* trace_g;
   int grad_only;             // 1: store the total gradient into p and stop
+  int momentum_only;         // 1: p -= b*eps*g only (Full mass matrix: the position update needs M^-1 p,
+                             //    a product over all coordinates, and follows as its own launches)
 
   __device__ __forceinline__ void apply(int j, int c, double y) const {
     if (j >= T.dims || c >= C) return;
@@ -54,6 +56,7 @@ struct UpdateEpi {
     const double e = eps[c];
     double pp = p[o];
     momentum_update(__dmul_rn(b_mult, e), g, pp);
+    if (momentum_only) { p[o] = pp; return; }
     position_update(T, j, __dmul_rn(a_mult, e), q, pp);
     p[o] = pp;
     q_out[o] = q;
@@ -68,7 +71,7 @@ struct UpdateEpi {
   // pair, and q / p move as 16-byte pairs.
   __device__ __forceinline__ void tile(int, int, int base_m, int base_n, const double (&acc)[8][4][2],
                                        double*) const {
-    if (T.n_terms > 1 || grad_only || trace_q) {   // generic element-wise path
+    if (T.n_terms > 1 || grad_only || trace_q || momentum_only) {   // generic element-wise path
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -164,6 +167,28 @@ struct ResidualEpi {
   __device__ __forceinline__ void chunk_end(int, int) {}
 };
 
+// out[i][c] = Y   (Full mass matrix: p = L z and dK/dp = M^-1 p over the chain batch,
+// MassMatrices.py:241-327)
+struct StoreEpi {
+  static constexpr bool kPerChainSum = false;
+  int rows, C, ld;
+  double* out;
+  __device__ __forceinline__ void tile(int, int, int base_m, int base_n, const double (&acc)[8][4][2],
+                                       double*) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = base_m + 8 * i;
+      if (m >= rows) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = base_n + 8 * j;
+        if (c >= C) continue;
+        *reinterpret_cast<double2*>(out + (size_t)m * ld + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+      }
+    }
+  }
+};
+
 // Per-chain partial sums of the likelihood misfit over the rows of one tile / chunk:
 //   premultiplied: q_j * (Y_j - 2*Gtd0_j)            (LinearMatrix.py:185-191)
 //   direct       : ((Y_i - d_i) / sigma_i)^2         (LinearMatrix.py:192-202)
@@ -224,6 +249,8 @@ struct StagedCommon {
   double stepsize;
   int randomize;
   const double* stepsize_chain;  // [C] per-chain step sizes or null
+  const double* v;               // Full mass matrix: dK/dp = M^-1 p [dpad x ld] (null otherwise)
+  int draw_only;                 // st_begin: store the standard normals into p and stop (Full mass)
 };
 
 #ifdef HMCB_STAGED_KERNELS
@@ -268,6 +295,7 @@ st_begin_kernel(const StagedCommon S, long long kglob, double a_mult,
       const int jj = j + h;
       if (jj < j_end) {
         const size_t o = (size_t)jj * S.ld + c;
+        if (S.draw_only) { p[o] = z[h]; continue; }
         double pp = T.sqrtm ? __dmul_rn(__ldg(T.sqrtm + jj), z[h]) : z[h];
         k0 = __dadd_rn(k0, kinetic_term(T, jj, pp));
         double q = q_cur[o];
@@ -278,8 +306,49 @@ st_begin_kernel(const StagedCommon S, long long kglob, double a_mult,
       }
     }
   }
+  if (S.draw_only) return;
   k0part[(size_t)jt * S.ld + c] = k0;
   if (flags_out && mask) atomicOr(flags_out + c, mask);
+}
+
+// Full mass matrix: position update q_out = q_in + a*eps*v with v = M^-1 p (S.v), reflection, bound
+// flags, and (k0part != null) the kinetic-energy partial sums p . v of the momentum it was given.
+__global__ void __launch_bounds__(ST_THREADS)
+st_kpos_kernel(const StagedCommon S, double a_mult, const double* __restrict__ q_in,
+               double* __restrict__ q_out, double* __restrict__ p, const double* __restrict__ eps,
+               double* __restrict__ k0part, unsigned* __restrict__ flags_out) {
+  const int c = blockIdx.x * ST_THREADS + threadIdx.x;
+  if (c >= S.C) return;
+  const DevTarget& T = S.T;
+  const double ca = __dmul_rn(a_mult, eps[c]);
+  double k0 = 0.0;
+  unsigned mask = 0;
+  const int j_end = min(T.dims, ((int)blockIdx.y + 1) * ST_DT);
+  for (int j = blockIdx.y * ST_DT; j < j_end; ++j) {
+    const size_t o = (size_t)j * S.ld + c;
+    double q = q_in[o], pp = p[o];
+    const double vv = S.v[o];
+    k0 = __dadd_rn(k0, __dmul_rn(pp, vv));
+    q = __dadd_rn(q, __dmul_rn(ca, vv));
+    const double before = pp;
+    reflect(T, j, q, pp);
+    q_out[o] = q;
+    if (pp != before) p[o] = pp;
+    mask |= bound_violations(T, j, q);
+  }
+  if (k0part) k0part[(size_t)blockIdx.y * S.ld + c] = k0;
+  if (flags_out && mask) atomicOr(flags_out + c, mask);
+}
+
+// [C] = scale * column sums of part [tiles x ld]
+__global__ void __launch_bounds__(ST_THREADS)
+st_colsum_kernel(const double* __restrict__ part, int tiles, int ld, int C, double scale,
+                 double* __restrict__ out) {
+  const int c = blockIdx.x * ST_THREADS + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int t = 0; t < tiles; ++t) s = __dadd_rn(s, part[(size_t)t * ld + c]);
+  out[c] = __dmul_rn(scale, s);
 }
 
 // Lone position update (the leading a1 sub-step of every 3s/4s step).
@@ -327,7 +396,7 @@ st_energy_kernel(const StagedCommon S, const double* __restrict__ q, const doubl
   for (int j = blockIdx.y * ST_DT; j < j_end; ++j) {
     const size_t o = (size_t)j * S.ld + c;
     const double qq = q[o];
-    if (p) k1 = __dadd_rn(k1, kinetic_term(T, j, p[o]));
+    if (p) k1 = __dadd_rn(k1, S.v ? __dmul_rn(p[o], S.v[o]) : kinetic_term(T, j, p[o]));
     u1 = __dadd_rn(u1, prior_misfit(T, j, qq));
     if (flags_out) mask |= bound_violations(T, j, qq);
   }

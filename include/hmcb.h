@@ -91,6 +91,13 @@ int hmcb_set_mass_unit(hmcb_engine *e);
 int hmcb_set_mass_diagonal(hmcb_engine *e, const double *diagonal,
                            const double *inverse_diagonal);
 
+/* MassMatrices.Full (MassMatrices.py:241-327): momentum = cholesky @ normal, kinetic energy
+ * 0.5 p . M^-1 p, dK/dp = M^-1 p (the reference calls scipy's cho_solve; here M^-1 is applied as a
+ * dense product over the chain batch on the fp64 tensor cores).  HOST arrays [dims x dims] row-major:
+ * the lower Cholesky factor of the mass matrix and its inverse.  Runs on the staged path (also for
+ * priors-only targets); not available together with a SourceLocation likelihood. */
+int hmcb_set_mass_full(hmcb_engine *e, const double *cholesky_lower, const double *inverse);
+
 /* target distribution ----------------------------------------------------------------
  * Built from a distribution object tree (BayesRule / Composite / priors / likelihood) by
  * hmclab_b200/_lowering.py.  All HOST arrays. */

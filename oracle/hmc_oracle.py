@@ -257,22 +257,35 @@ def corrector(lb, ub, q: np.ndarray, p: np.ndarray) -> None:
 # ------------------------------------------------------------------ mass matrices ----
 
 
+def _cho_solve_lower(chol, b):
+    """scipy.linalg.cho_solve((L, lower=True), b), as MassMatrices.Full calls it."""
+    from scipy.linalg import cho_solve
+
+    return cho_solve((chol, True), b)
+
+
 def momentum_from_normal(mass, z: np.ndarray) -> np.ndarray:
     """MassMatrices.py:135-142 (Unit), :220-227 (Diagonal); z is the N(0,1) draw."""
     if mass["kind"] == "unit":
         return z
+    if mass["kind"] == "full":
+        return mass["cholesky"] @ z  # MassMatrices.py:311-317
     return np.sqrt(_col(mass["diagonal"])) * z
 
 
 def kinetic_energy(mass, p: np.ndarray) -> float:
     if mass["kind"] == "unit":
         return 0.5 * (p.T @ p).item(0)  # MassMatrices.py:100-114
+    if mass["kind"] == "full":
+        return 0.5 * np.vdot(p, _cho_solve_lower(mass["cholesky"], p))  # :269-284
     return 0.5 * np.vdot(p, _col(mass["inverse_diagonal"]) * p)  # :185-199
 
 
 def kinetic_gradient(mass, p: np.ndarray) -> np.ndarray:
     if mass["kind"] == "unit":
         return p  # MassMatrices.py:116-133
+    if mass["kind"] == "full":
+        return _cho_solve_lower(mass["cholesky"], p)  # :286-309
     return _col(mass["inverse_diagonal"]) * p  # :201-218
 
 

@@ -44,6 +44,10 @@ SETTINGS = {
     "srcloc2d_infer_v": _settings("lf", 6, 0.03, True, 5, 6),
     # dense (N x N) data covariance, premultiplied form (LinearMatrix.py:226-305)
     "dense_fullcov_premult": _settings("3s", 2, 0.35, True, 4, 4),
+    # Full (dense) mass matrix (MassMatrices.py:241-327), dense direct likelihood, 3-stage
+    "dense_full_mass_3s": _settings("3s", 2, 0.9, True, 4, 4),
+    # Full mass matrix on a bounded priors-only target: reflection flips momenta between sub-steps
+    "bounded_full_mass_lf": _settings("lf", 5, 0.3, True, 6, 6),
 }
 
 CASES = tuple(SETTINGS)
@@ -87,6 +91,17 @@ def make_inputs(name: str) -> dict:
         A = rng.normal(size=(N, N)) / np.sqrt(N)
         inp.update(G=rng.normal(size=(N, dims)) / np.sqrt(N), d=rng.normal(size=(N, 1)),
                    cov=A @ A.T + 0.5 * np.eye(N), mass=rng.uniform(0.5, 2.0, size=(dims, 1)))
+    elif name == "dense_full_mass_3s":
+        dims = 30
+        A = rng.normal(size=(dims, dims)) / np.sqrt(dims)
+        inp.update(G=rng.normal(size=(45, dims)) / np.sqrt(45), d=rng.normal(size=(45, 1)),
+                   var=rng.uniform(0.5, 1.5, size=(45, 1)), mass_full=A @ A.T + np.eye(dims))
+    elif name == "bounded_full_mass_lf":
+        dims = 10
+        A = rng.normal(size=(dims, dims)) / np.sqrt(dims)
+        inp.update(mu=rng.normal(size=(dims, 1)) * 0.2, var=rng.uniform(0.5, 2, size=(dims, 1)),
+                   lo=np.full((dims, 1), -1.0), hi=np.full((dims, 1), 1.0),
+                   mass_full=0.5 * (A @ A.T) + np.eye(dims))
     elif name == "dense_direct_f64":
         dims = 33
         inp.update(G=rng.normal(size=(21, dims)), d=rng.normal(size=(21, 1)),
@@ -146,7 +161,7 @@ def make_inputs(name: str) -> dict:
             base = np.concatenate([base, [3.0]])
         q0 = base[None, :] + 0.3 * rng.normal(size=(C, dims))
         q0 = np.clip(q0, inp["lo"][:, 0] + 1e-3, inp["hi"][:, 0] - 1e-3)
-    elif name in ("composite_top", "normal_bounded"):
+    elif name in ("composite_top", "normal_bounded", "bounded_full_mass_lf"):
         q0 = rng.uniform(-0.5, 0.5, size=(C, dims))
     elif name == "composite_in_bayes":
         q0 = rng.uniform(-0.5, 0.5, size=(C, dims))
@@ -186,6 +201,13 @@ def build(name: str, inp: dict, ns):
         post = D.BayesRule([D.Normal(np.zeros((dims, 1)), 2.0),
                             D.LinearMatrix(cp("G"), cp("d"), cp("cov"))])
         mass = M.Diagonal(cp("mass"))
+    elif name == "dense_full_mass_3s":
+        post = D.BayesRule([D.Normal(np.zeros((dims, 1)), 1.0),
+                            D.LinearMatrix(cp("G"), cp("d"), cp("var"), premultiplication=False)])
+        mass = M.Full(cp("mass_full"))
+    elif name == "bounded_full_mass_lf":
+        post = D.Normal(cp("mu"), cp("var"), lower_bounds=cp("lo"), upper_bounds=cp("hi"))
+        mass = M.Full(cp("mass_full"))
     elif name == "dense_direct_f64":
         inner = D.LinearMatrix.__module__
         import importlib
