@@ -39,7 +39,26 @@ def test_diagonal_mass_uses_the_rounded_reciprocal():
     assert np.array_equal(plan["inverse_diagonal"], (1.0 / diag)[:, 0])
     assert describe_mass(M.Unit(3)) == {"kind": "unit", "dims": 3}
     with pytest.raises(NotImplementedError):
-        describe_mass(type("Full", (), {"dimensions": 3})())
+        describe_mass(type("BFGS", (), {"dimensions": 3})())
+
+
+def test_full_mass_lowers_to_the_cholesky_factor_and_the_inverse():
+    """MassMatrices.Full (MassMatrices.py:241-327): lower factor as scipy's cho_factor gives it, the
+    inverse through cho_solve; an object without a stored inverse (the reference's) gets one."""
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(5, 5))
+    full = A @ A.T + 5 * np.eye(5)
+    mass = M.Full(full)
+    plan = describe_mass(mass)
+    assert plan["kind"] == "full" and plan["dims"] == 5
+    assert np.allclose(plan["cholesky"] @ plan["cholesky"].T, full, atol=1e-12)
+    assert np.array_equal(plan["cholesky"], np.tril(plan["cholesky"]))
+    assert np.allclose(plan["inverse"] @ full, np.eye(5), atol=1e-12)
+    bare = type("Full", (), {"dimensions": 5, "cholesky": mass.cholesky})()
+    assert np.allclose(describe_mass(bare)["inverse"], plan["inverse"], atol=1e-14)
+    with pytest.raises(AssertionError):
+        M.Full(full + np.triu(np.ones((5, 5)), 1))          # not symmetric
+    assert M.Full.create_default(4).matrix.shape == (4, 4)
 
 
 def test_linear_matrix_dtype_quirks_are_inherited():
