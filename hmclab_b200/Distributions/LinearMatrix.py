@@ -135,10 +135,11 @@ class _LinearMatrix_dense_forward_simple_covariance(_AbstractDistribution):
 
 
 class _LinearMatrix_dense_forward_dense_covariance(_AbstractDistribution):
-    """Dense G with a dense (N x N) data covariance (LinearMatrix.py:226-305).  In its
-    premultiplied form (the default when N > dimensions) it reduces to the same GtG / Gtd0 /
-    dtd arithmetic as the simple-covariance class; the direct form (two N x N products per
-    evaluation) is not lowered."""
+    """Dense G with a dense (N x N) data covariance (LinearMatrix.py:226-305).  The premultiplied
+    form (the default when N > dimensions) reduces to the GtG / Gtd0 / dtd arithmetic of the
+    simple-covariance class.  The direct form keeps G, the inverse covariance and the upper
+    Cholesky factor of the inverse covariance like the reference (all in ``dtype``, default
+    float32): gradient ``Gt @ invcov @ (G m - d)``, misfit ``0.5 |U (G m - d)|^2``."""
 
     def __init__(self, G, d, data_covariance, dtype=_numpy.single, premultiplication=None):
         self.name = "dense linear forward model, dense data covariance"
@@ -150,15 +151,15 @@ class _LinearMatrix_dense_forward_dense_covariance(_AbstractDistribution):
             self.premultiplication = premultiplication
         else:
             self.premultiplication = self.G.shape[0] > self.G.shape[1]
-        if not self.premultiplication:
-            raise NotImplementedError(
-                "LinearMatrix with a dense data covariance is lowered in its premultiplied form "
-                "only (pass premultiplication=True).")
         self.invcov = _numpy.linalg.inv(self.data_covariance)
-        self.GtG = self.G.T @ self.invcov @ self.G
-        self.Gtd0 = G.T @ self.invcov @ self.d
-        self.dtd = (self.d.T @ self.invcov @ self.d).item()
-        del self.G, self.d, self.data_covariance
+        if self.premultiplication:
+            self.GtG = self.G.T @ self.invcov @ self.G
+            self.Gtd0 = G.T @ self.invcov @ self.d
+            self.dtd = (self.d.T @ self.invcov @ self.d).item()
+            del self.G, self.d, self.data_covariance
+        else:
+            self.Gt = self.G.T
+            self.cholesky_upper_inv_covariance = _numpy.linalg.cholesky(self.invcov).T
 
 
 class _LinearMatrix_sparse_forward_simple_covariance(_AbstractDistribution):

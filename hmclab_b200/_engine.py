@@ -74,6 +74,8 @@ SIGNATURES = {
     "hmcb_set_likelihood_dense_direct": (C.c_int, [C.c_void_p, C.c_int64, _c_double_p,
                                                    _c_double_p, _c_double_p, _c_double_p,
                                                    _c_double_p]),
+    "hmcb_set_likelihood_dense_direct_cov": (C.c_int, [C.c_void_p, C.c_int64, _c_double_p, _c_double_p, _c_double_p,
+                                                       _c_double_p, _c_double_p]),
     "hmcb_set_likelihood_csr_direct": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _c_int32_p,
                                                  _c_int32_p, _c_double_p, _c_int32_p, _c_int32_p,
                                                  _c_double_p, _c_double_p, _c_double_p,
@@ -223,6 +225,10 @@ class Engine:
         if kind == "linear_dense" and lik["premult"]:
             self._ok(lib.hmcb_set_likelihood_dense_premult(
                 h, _dp(_f64(lik["GtG"])), _dp(_f64(lik["Gtd0"])), float(lik["dtd"])))
+        elif kind == "linear_dense" and lik.get("misfit_G") is not None:
+            self._ok(lib.hmcb_set_likelihood_dense_direct_cov(
+                h, int(lik["N"]), _dp(_f64(lik["G"])), _dp(_f64(lik["Gt"])), _dp(_f64(lik["d"])),
+                _dp(_f64(lik["misfit_G"])), _dp(_f64(lik["misfit_d"]))))
         elif kind == "linear_dense":
             Gt = None if lik.get("Gt") is None else _f64(lik["Gt"])
             self._ok(lib.hmcb_set_likelihood_dense_direct(

@@ -95,9 +95,19 @@ def describe(dist) -> Dict[str, Any]:
                  "_LinearMatrix_dense_forward_dense_covariance"):
         node.update(kind="linear_dense", premult=bool(dist.premultiplication))
         if cls.endswith("dense_covariance") and not dist.premultiplication:
-            raise NotImplementedError(
-                "LinearMatrix with a dense data covariance is lowered in its premultiplied form only.")
-        if dist.premultiplication:
+            # LinearMatrix.py:257-288: gradient Gt @ invcov @ (G m - d), evaluated left to right, so
+            # the reference forms W = Gt @ invcov (a product in the class's dtype, float32 by default)
+            # at every call; it is formed ONCE here with the same numpy expression.  Misfit:
+            # 0.5 |U (G m - d)|^2 with the upper Cholesky factor U of the inverse covariance; the
+            # engine gets U G and U d (float64 products of the float32 operands).
+            N = int(dist.G.shape[0])
+            G = np.ascontiguousarray(dist.G, dtype=np.float64)
+            W = np.ascontiguousarray(dist.Gt @ dist.invcov, dtype=np.float64)
+            U = np.ascontiguousarray(dist.cholesky_upper_inv_covariance, dtype=np.float64)
+            dvec = _vec(dist.d, N, "d")
+            node.update(N=N, G=G, Gt=W, d=dvec, var=np.ones(N), sigma=np.ones(N), chol_upper=U,
+                        misfit_G=np.ascontiguousarray(U @ G), misfit_d=np.ascontiguousarray(U @ dvec))
+        elif dist.premultiplication:
             node.update(
                 GtG=np.ascontiguousarray(dist.GtG, dtype=np.float64),
                 Gtd0=_vec(dist.Gtd0, n, "Gtd0"),

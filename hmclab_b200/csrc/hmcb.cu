@@ -82,6 +82,8 @@ struct hmcb_engine {
   int64_t N = 0;                       // data dimension (direct forms)
   std::vector<double> h_A, h_At;       // dense: GtG or G ; Gt
   bool has_At = false;
+  std::vector<double> h_Amis, h_vecmis;  // dense data covariance, direct form: U G and U d of the misfit pass
+  double *dAmis = nullptr, *dvecmis = nullptr;
   std::vector<double> h_vec, h_var, h_sigma;  // Gtd0 or d ; var ; sigma
   double dtd = 0.0;
   HostCsr csr, csr_t;
@@ -215,6 +217,7 @@ void free_device(hmcb_engine* e) {
   e->rw_qp = e->rw_x1 = nullptr;
   e->dA = e->dAt = e->dA_rowmajor = e->dvec = e->dvar = e->dsigma = nullptr;
   e->dL = e->dMinv = e->v_w = nullptr;
+  e->dAmis = e->dvecmis = nullptr;
   e->q_cur = e->q_w[0] = e->q_w[1] = e->p_w = e->R = nullptr;
   e->eps = e->uacc = e->k0part = e->k1part = e->upart = e->lpart = nullptr;
   e->flags[0] = e->flags[1] = e->flags[2] = nullptr;
@@ -869,8 +872,8 @@ int staged_misfit_pass(hmcb_engine* e, const double* q, cudaStream_t s) {
       HMCB_CUDA(launch_gemm_misfit(e->dA, e->dpad, e->dpad, q, e->ld, e->dpad, m, s));
       break;
     case LK_DENSE_DIRECT:
-      m.rows = (int)e->N; m.vec = e->dvec; m.sigma = e->dsigma;
-      HMCB_CUDA(launch_gemm_misfit(e->dA, e->dpad, e->npad, q, e->ld, e->dpad, m, s));
+      m.rows = (int)e->N; m.vec = e->dAmis ? e->dvecmis : e->dvec; m.sigma = e->dsigma;
+      HMCB_CUDA(launch_gemm_misfit(e->dAmis ? e->dAmis : e->dA, e->dpad, e->npad, q, e->ld, e->dpad, m, s));
       break;
     case LK_CSR_DIRECT:
       m.rows = (int)e->N; m.vec = e->dvec; m.sigma = e->dsigma;
@@ -1339,6 +1342,7 @@ int hmcb_clear_target(hmcb_engine* e) {
   e->has_rlb = e->has_rub = false;
   e->lik = LK_NONE;
   e->h_A.clear(); e->h_At.clear(); e->h_vec.clear(); e->h_var.clear(); e->h_sigma.clear();
+  e->h_Amis.clear(); e->h_vecmis.clear();
   e->csr = HostCsr(); e->csr_t = HostCsr();
   return 0;
 }
@@ -1407,6 +1411,16 @@ int hmcb_set_likelihood_dense_direct(hmcb_engine* e, int64_t N, const double* G,
   }
   copy_vec(e->h_vec, d, N); copy_vec(e->h_var, var, N); copy_vec(e->h_sigma, sigma, N);
   e->lik = LK_DENSE_DIRECT;
+  return 0;
+}
+
+int hmcb_set_likelihood_dense_direct_cov(hmcb_engine* e, int64_t N, const double* G, const double* GtCinv,
+                                         const double* d, const double* UG, const double* Ud) {
+  HMCB_CHECK(e && G && GtCinv && d && UG && Ud, "hmcb_set_likelihood_dense_direct_cov: NULL argument");
+  const std::vector<double> ones((size_t)std::max<int64_t>(N, 1), 1.0);
+  if (hmcb_set_likelihood_dense_direct(e, N, G, GtCinv, d, ones.data(), ones.data())) return -1;
+  copy_vec(e->h_Amis, UG, N * e->d);
+  copy_vec(e->h_vecmis, Ud, N);
   return 0;
 }
 
@@ -1598,6 +1612,12 @@ int hmcb_finalize(hmcb_engine* e) {
       case LK_DENSE_DIRECT:
         if (dev_upload_tiled(e, e->h_A.data(), e->N, d, e->npad, e->dpad, &e->dA)) return -1;
         if (dev_upload_tiled(e, e->h_At.data(), d, e->N, e->dpad, e->npad, &e->dAt)) return -1;
+        if (!e->h_Amis.empty()) {   // dense data covariance: the misfit pass applies U G, U d
+          const double* um = nullptr;
+          if (dev_upload_tiled(e, e->h_Amis.data(), e->N, d, e->npad, e->dpad, &e->dAmis) ||
+              dev_upload(e, e->h_vecmis, &um)) return -1;
+          e->dvecmis = const_cast<double*>(um);
+        }
         e->ltiles = e->npad / GEMM_BM;
         break;
       case LK_CSR_DIRECT:
@@ -1644,6 +1664,7 @@ int hmcb_finalize(hmcb_engine* e) {
     // the host copies of the big operands are no longer needed
     std::vector<double>().swap(e->h_A);
     std::vector<double>().swap(e->h_At);
+    std::vector<double>().swap(e->h_Amis);
   }
   HMCB_CUDA(cudaDeviceSynchronize());
   e->finalized = true;

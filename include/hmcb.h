@@ -127,6 +127,13 @@ int hmcb_set_likelihood_dense_premult(hmcb_engine *e, const double *GtG,
 int hmcb_set_likelihood_dense_direct(hmcb_engine *e, int64_t N, const double *G,
                                      const double *Gt, const double *d, const double *var,
                                      const double *sigma);
+/* LinearMatrix, dense G, dense (N x N) data covariance, direct form (LinearMatrix.py:257-288):
+ * gradient Gt @ invcov @ (G m - d), misfit 0.5 |U (G m - d)|^2 with U the upper Cholesky factor of
+ * the inverse covariance.  G [N x dims], GtCinv = Gt @ invcov [dims x N] (the product the reference
+ * re-forms in its dtype at every call), d [N], UG = U @ G [N x dims], Ud = U @ d [N]; row-major. */
+int hmcb_set_likelihood_dense_direct_cov(hmcb_engine *e, int64_t N, const double *G,
+                                         const double *GtCinv, const double *d, const double *UG,
+                                         const double *Ud);
 /* LinearMatrix, sparse G, direct form (LinearMatrix.py:406-426; replaces the MKL
  * mkl_cspblas_dcsrgemv binding, InterfaceMKL.py:87-121): CSR of G [N x dims] and CSR of
  * G^T [dims x N], int32 indices, float64 values.  Both hold nnz entries; rows need not be

@@ -85,7 +85,11 @@ def misfit(node, m: np.ndarray) -> float:
         else:
             # LinearMatrix.py:192-202 / 406-415
             G = _matrix(node, "G")
-            res = (G @ m - _col(node["d"])) / _col(node["sigma"])
+            if node.get("chol_upper") is not None:
+                # dense data covariance, direct form (LinearMatrix.py:267-279)
+                res = node["chol_upper"] @ (G @ m - _col(node["d"]))
+            else:
+                res = (G @ m - _col(node["d"])) / _col(node["sigma"])
             inner = own + (0.5 * np.linalg.norm(res) ** 2).item()
         return inner + wrapper  # LinearMatrix.py:114-116
     if kind == "srcloc2d":

@@ -44,6 +44,8 @@ SETTINGS = {
     "srcloc2d_infer_v": _settings("lf", 6, 0.03, True, 5, 6),
     # dense (N x N) data covariance, premultiplied form (LinearMatrix.py:226-305)
     "dense_fullcov_premult": _settings("3s", 2, 0.35, True, 4, 4),
+    # dense (N x N) data covariance, direct form: float32 Gt @ invcov re-formed per call in the reference
+    "dense_fullcov_direct": _settings("lf", 4, 0.3, True, 4, 4),
     # Full (dense) mass matrix (MassMatrices.py:241-327), dense direct likelihood, 3-stage
     "dense_full_mass_3s": _settings("3s", 2, 0.9, True, 4, 4),
     # Full mass matrix on a bounded priors-only target: reflection flips momenta between sub-steps
@@ -85,6 +87,12 @@ def make_inputs(name: str) -> dict:
                    std=rng.uniform(0.08, 0.2, size=tt.shape), lo=lo, hi=hi,
                    mass=rng.uniform(0.5, 2.0, size=(dims, 1)),
                    truth=np.hstack([ex, ez, eT]).reshape(-1, 1))
+    elif name == "dense_fullcov_direct":
+        dims = 28
+        N = 19
+        A = rng.normal(size=(N, N)) / np.sqrt(N)
+        inp.update(G=rng.normal(size=(N, dims)) / np.sqrt(N), d=rng.normal(size=(N, 1)),
+                   cov=A @ A.T + 0.5 * np.eye(N))
     elif name == "dense_fullcov_premult":
         dims = 24
         N = 40
@@ -201,6 +209,9 @@ def build(name: str, inp: dict, ns):
         post = D.BayesRule([D.Normal(np.zeros((dims, 1)), 2.0),
                             D.LinearMatrix(cp("G"), cp("d"), cp("cov"))])
         mass = M.Diagonal(cp("mass"))
+    elif name == "dense_fullcov_direct":
+        post = D.BayesRule([D.Normal(np.zeros((dims, 1)), 2.0),
+                            D.LinearMatrix(cp("G"), cp("d"), cp("cov"))])      # N < dims: direct form
     elif name == "dense_full_mass_3s":
         post = D.BayesRule([D.Normal(np.zeros((dims, 1)), 1.0),
                             D.LinearMatrix(cp("G"), cp("d"), cp("var"), premultiplication=False)])

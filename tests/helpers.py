@@ -15,6 +15,18 @@ def load_golden(name):
     return inp, ref
 
 
+# Cases whose reference arithmetic contains a float32 BLAS product that the reference re-forms at every
+# call (LinearMatrix.py:288, `Gt @ invcov` of the dense-covariance direct form): its rounding belongs to
+# the sgemm kernel of the host that ran the reference, so on another CPU the stored outputs are
+# reproduced to float32 level only.  The 1e-10 check for these cases is against the oracle evaluated on
+# the SAME host (same numpy expression, same BLAS) -- see test_gpu_parity.py.
+FLOAT32_BLAS_CASES = {"dense_fullcov_direct": 3e-5}
+
+
+def tol_for(name, tight):
+    return FLOAT32_BLAS_CASES.get(name, tight)
+
+
 def build_mirror(name, inp):
     import hmclab_b200
 

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import cases
-from helpers import build_mirror, load_golden, rel_err
+from helpers import FLOAT32_BLAS_CASES, build_mirror, load_golden, rel_err, tol_for
 from hmclab_b200._lowering import describe, describe_mass, flatten
 
 pytestmark = pytest.mark.gpu
@@ -65,10 +65,23 @@ def test_trajectories_and_decisions_match_reference(name):
                     ("out_p_prop", "p_prop"), ("out_h0", "H0"), ("out_h1", "H1"),
                     ("out_samples", "samples")):
         err = rel_err(got[key], ref[rk])
-        assert err < TOL, f"{key}: rel err {err:.3e}"
+        assert err < tol_for(name, TOL), f"{key}: rel err {err:.3e}"
     assert np.array_equal(got["accepted_total"], ref["accept"].sum(axis=0))
-    assert rel_err(q.cpu().numpy(), ref["samples"][-1, :, :d]) < TOL
-    assert rel_err(x.cpu().numpy(), ref["samples"][-1, :, d]) < TOL
+    assert rel_err(q.cpu().numpy(), ref["samples"][-1, :, :d]) < tol_for(name, TOL)
+    assert rel_err(x.cpu().numpy(), ref["samples"][-1, :, d]) < tol_for(name, TOL)
+    if name in FLOAT32_BLAS_CASES:
+        # the reference's float32 operator product is host dependent: 1e-10 against the same-host oracle
+        from oracle import hmc_oracle as oracle
+
+        post, mass = build_mirror(name, inp)
+        with np.errstate(all="ignore"):
+            here = oracle.run_chains(describe(post), describe_mass(mass), q0=inp["q0"], z=inp["z"],
+                                     u_step=inp["u_step"], u_acc=inp["u_acc"], integrator=s["integrator"],
+                                     steps=s["steps"], stepsize=s["stepsize"], randomize=s["randomize"])
+        assert np.array_equal(got["out_accept"].astype(bool), here["accept"])
+        for key, rk in (("out_q_prop", "q_prop"), ("out_p_prop", "p_prop"), ("out_h0", "H0"),
+                        ("out_h1", "H1"), ("out_samples", "samples")):
+            assert rel_err(got[key], here[rk]) < TOL, key
 
 
 @pytest.mark.parametrize("name", cases.CASES)
@@ -79,9 +92,9 @@ def test_misfit_gradient_contract(name):
     q = _dev(torch, pts)
     x = eng.misfit(q).cpu().numpy()
     g = eng.gradient(q).cpu().numpy()
-    assert rel_err(x, ref["probe_misfit"]) < TOL
+    assert rel_err(x, ref["probe_misfit"]) < tol_for(name, TOL)
     for i in range(pts.shape[0]):
-        assert rel_err(g[i], ref["probe_gradient"][i]) < TOL, i
+        assert rel_err(g[i], ref["probe_gradient"][i]) < tol_for(name, TOL), i
 
 
 @pytest.mark.parametrize("name", ["normal_unit_lf", "dense_direct_4s", "srcloc_fixed_v"])
