@@ -512,7 +512,8 @@ def bench_workload(ctx, name, steps, warmup, block=0, chains=0):
             rate = ops * (C * B * w.grads_per_proposal) / (kernel_ms * 1e-3) / 1e9
             roofline["fp64_pipe"] = {"achieved_ginst_per_s": rate, "peak_ginst_per_s": fp64["dfma_ginst_per_s"],
                                      "frac": rate / fp64["dfma_ginst_per_s"], "fp64_ops_per_grad_eval": ops,
-                                     "ops_source": "executed-instruction counts of the committed ncu capture"}
+                                     "ops_source": "instruction-count estimate (workloads.py); the measured pipe "
+                                                   "activity is ncu_counters.fp64_pipe_active_pct"}
     else:
         peak = fp64["dgemm_tflops_sustained"] if ms_per_step > 50 else fp64["dgemm_tflops_burst"]
         flops = w.extra.get("flops_per_grad")
@@ -543,6 +544,8 @@ def bench_workload(ctx, name, steps, warmup, block=0, chains=0):
     roofline["timing"] = timing
     if traffic_rec:
         roofline["traffic_source"] = traffic_rec.get("source", "committed ncu capture (profiles/)")
+        if traffic_rec.get("ncu"):     # pipe activity counters of the same committed capture
+            roofline["ncu_counters"] = traffic_rec["ncu"]
 
     return {
         "baseline_config": BASELINE_CONFIG.get(name), "workload": w.description,

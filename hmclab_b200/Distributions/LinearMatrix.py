@@ -65,6 +65,11 @@ class LinearMatrix(_AbstractDistribution):
             d.size,
         ):
             simple = False
+        elif _sparse.issparse(data_covariance) and data_covariance.shape == (d.size, d.size):
+            raise NotImplementedError(
+                "LinearMatrix with a sparse data covariance (LinearMatrix.py:444-519: a sparse LU solve "
+                "per evaluation, in the covariance's dtype) is outside the batched B200 path."
+            )
         else:
             raise ValueError("Didn't understand the data covariance object.")
         if not simple and not dense:

@@ -61,13 +61,13 @@ def normal_iid(dims: int = 1000, chains: int = 4096) -> Workload:
     rng = np.random.default_rng(1)
     post = D.Normal(np.zeros((dims, 1)), 1.0)
     q0 = rng.normal(size=(chains, dims))
-    # fp64 instructions per gradient evaluation per chain, from the executed-instruction counts
-    # of the fused kernel (profiles/ncu_fused_priors_r01.txt: 162 M warp-level DADD/DMUL/DFMA per
-    # 4.1e7 coordinate-proposals): 6 unfused ops per coordinate and leapfrog step plus ~63 per
-    # coordinate and proposal for Box-Muller, energies and reductions, spread over L=10
+    # fp64 instructions per gradient evaluation per chain (estimate): 4 per coordinate and leapfrog
+    # step since the two updates are one FMA each (6 in exact mode), plus ~63 per coordinate and
+    # proposal for Box-Muller, energies and reductions (executed-instruction counts of
+    # profiles/ncu_fused_priors_r01.txt), spread over L=10
     return Workload("normal_iid", post, M.Unit(dims), chains, "lf", 10, 0.05, q0,
                     f"StandardNormal {dims}-dim posterior, {chains} chains, lf L=10, Unit mass",
-                    extra={"fp64_ops_per_grad": dims * (6.0 + 63.0 / 10)})
+                    extra={"fp64_ops_per_grad": dims * (4.0 + 63.0 / 10)})
 
 
 # ----------------------------------------------------------------------------- config 3 --

@@ -80,8 +80,14 @@ def test_linear_matrix_dtype_quirks_are_inherited():
         D.LinearMatrix(G, d, np.ones((3, 1)))
     full = D.LinearMatrix(G, d, np.eye(7) * 2.0)            # dense covariance, premultiplied
     assert np.allclose(full.Distribution.GtG, inner.GtG, rtol=1e-6)
-    with pytest.raises(NotImplementedError):
-        D.LinearMatrix(G, d, np.eye(7), premultiplication=False)
+    direct = D.LinearMatrix(G, d, np.eye(7) * 2.0, premultiplication=False)   # dense covariance, direct form
+    node = describe(direct)
+    assert node["kind"] == "linear_dense" and not node["premult"] and node["Gt"].shape == (3, 7)
+    inv32 = np.linalg.inv((np.eye(7) * 2.0).astype(np.float32))
+    assert np.array_equal(node["Gt"], (G.astype(np.float32).T @ inv32).astype(np.float64))   # float32 product
+    assert np.allclose(node["misfit_G"].T @ node["misfit_G"], G32.T @ G32 / 2.0, rtol=1e-6)
+    with pytest.raises(NotImplementedError, match="sparse data covariance|sparse LU"):
+        D.LinearMatrix(sp.csr_matrix(G), d, sp.eye(7).tocsr())
     sparse = D.LinearMatrix(sp.csr_matrix(G), d, 0.5, premultiplication=False)
     node = describe(sparse)
     assert node["kind"] == "linear_csr" and node["indices"].dtype == np.int32
