@@ -34,7 +34,7 @@ NVCC_FLAGS = [
 UNITS = (
     [("hmcb.cu", "", []), ("launch_fused.cu", "", []), ("launch_srcloc.cu", "", []),
      ("launch_staged.cu", "", []), ("launch_spmm.cu", "", []), ("launch_fused_dense.cu", "", []),
-     ("debug_peak.cu", "", [])]
+     ("debug_peak.cu", "", []), ("launch_ozaki.cu", "", [])]
     + [("launch_fused_ppt.cu", f"_{p}", [f"-DHMCB_PPT={p}"]) for p in (1, 2, 4)]
     + [("launch_srcloc_lpe.cu", f"_{l}_{n}", [f"-DHMCB_LPE={l}", f"-DHMCB_NP={n}"])
        for l in (1, 2, 4) for n in (3, 4)]

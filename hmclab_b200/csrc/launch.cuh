@@ -103,4 +103,12 @@ cudaError_t launch_st_commit(int C, int d, int ld, const unsigned char* acc, con
 cudaError_t launch_st_transpose(const double* in, int R, int Cc, int ldin, double* out, int ldout,
                                 cudaStream_t s);
 
+// ---- launch_ozaki.cu: int8-sliced dense products on tcgen05 (ozaki.cuh) ---------------------------
+cudaError_t ozaki_init();
+cudaError_t ozaki_slice_map(const signed char* base, long long K, long long rows, int slices, int box_rows,
+                            CUtensorMap* out);
+cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, long long M, long long N,
+                                  long long K, int SA, int SB, int orders, int* C, long long plane_stride, int ldc,
+                                  cudaStream_t s);
+
 }  // namespace hmcb

@@ -98,6 +98,12 @@ int hmcb_set_mass_diagonal(hmcb_engine *e, const double *diagonal,
  * priors-only targets); not available together with a SourceLocation likelihood. */
 int hmcb_set_mass_full(hmcb_engine *e, const double *cholesky_lower, const double *inverse);
 
+/* Exact int8 slice products on the tcgen05 tensor cores (building block of the Ozaki-sliced dense
+ * products, csrc/ozaki.cuh): A [SA][M x K], B [SB][N x K] int8 DEVICE arrays (K contiguous; M, K, N
+ * multiples of 128), C [orders][M x N] int32 DEVICE: C[o] = sum over s + t = o of A_s B_t^T. */
+int hmcb_debug_i8_gemm(int device, int64_t M, int64_t N, int64_t K, int SA, int SB, int orders,
+                       const signed char *A, const signed char *B, int32_t *C, void *stream);
+
 /* target distribution ----------------------------------------------------------------
  * Built from a distribution object tree (BayesRule / Composite / priors / likelihood) by
  * hmclab_b200/_lowering.py.  All HOST arrays. */
