@@ -84,6 +84,13 @@ struct hmcb_engine {
   bool has_At = false;
   std::vector<double> h_Amis, h_vecmis;  // dense data covariance, direct form: U G and U d of the misfit pass
   double *dAmis = nullptr, *dvecmis = nullptr;
+  // Ozaki-sliced tcgen05 path of the dense direct products (ozaki.cuh)
+  bool oz = false;
+  int oz_sa = OZ_SLICES_A;             // slices of the model matrix: 5 when it is exact in float32, else 7
+  signed char *oz_AG = nullptr, *oz_AGt = nullptr, *oz_B = nullptr;   // int8 slices of G, G^T, the chain batch
+  int *oz_eaG = nullptr, *oz_eaGt = nullptr, *oz_C = nullptr;         // row exponents, int32 order planes
+  unsigned long long *oz_maxQ = nullptr, *oz_maxR = nullptr;          // per-chain max |.| (bit patterns)
+  CUtensorMap oz_mapAG, oz_mapAGt, oz_mapBq, oz_mapBr;
   std::vector<double> h_vec, h_var, h_sigma;  // Gtd0 or d ; var ; sigma
   double dtd = 0.0;
   HostCsr csr, csr_t;
@@ -218,6 +225,9 @@ void free_device(hmcb_engine* e) {
   e->dA = e->dAt = e->dA_rowmajor = e->dvec = e->dvar = e->dsigma = nullptr;
   e->dL = e->dMinv = e->v_w = nullptr;
   e->dAmis = e->dvecmis = nullptr;
+  e->oz = false;
+  e->oz_AG = e->oz_AGt = e->oz_B = nullptr; e->oz_eaG = e->oz_eaGt = e->oz_C = nullptr;
+  e->oz_maxQ = e->oz_maxR = nullptr;
   e->q_cur = e->q_w[0] = e->q_w[1] = e->p_w = e->R = nullptr;
   e->eps = e->uacc = e->k0part = e->k1part = e->upart = e->lpart = nullptr;
   e->flags[0] = e->flags[1] = e->flags[2] = nullptr;
@@ -787,6 +797,66 @@ int upload_csr_both(hmcb_engine* e, const HostCsr& m, CsrDev* gather, StripDev* 
   return upload_csr_strips(e, m, sh, kb, emax, stages, strip);
 }
 
+// int8 slices of a host matrix [rows x cols] (row-major), zero padded to [rows_pad x cols_pad]:
+// a[i][k] = 2^ea[i] * sum_s slice_s[i][k] 2^(-7 (s+1)) + (what is below 2^(ea - 7 S)); see ozaki.cuh
+void oz_slice_rows_host(const double* A, int64_t rows, int64_t cols, int64_t rows_pad, int64_t cols_pad, int S,
+                        std::vector<signed char>* slices, std::vector<int>* ea) {
+  slices->assign((size_t)S * rows_pad * cols_pad, 0);
+  ea->assign((size_t)rows_pad, 0);
+  for (int64_t i = 0; i < rows; ++i) {
+    double m = 0.0;
+    for (int64_t k = 0; k < cols; ++k) m = std::max(m, std::fabs(A[(size_t)i * cols + k]));
+    if (!(m > 0.0) || !std::isfinite(m)) continue;
+    int ex = 0;
+    std::frexp(m, &ex);                       // m = f 2^ex, f in [0.5, 1)
+    (*ea)[(size_t)i] = ex;
+    for (int64_t k = 0; k < cols; ++k) {
+      double x = std::ldexp(A[(size_t)i * cols + k], -ex);
+      for (int s = 0; s < S; ++s) {
+        x *= 128.0;
+        const double v = std::trunc(x);
+        x -= v;
+        (*slices)[((size_t)s * rows_pad + i) * cols_pad + k] = (signed char)(int)v;
+      }
+    }
+  }
+}
+
+// Sets up the Ozaki-sliced tcgen05 path for the dense direct products when it is valid and pays:
+// int32 accumulation must not overflow (K * pairs * 127^2 < 2^31) and the products must be large.
+int oz_setup(hmcb_engine* e) {
+  const int want = env_int("HMCB_OZAKI", -1);   // -1: when it pays, 0: never, 1: whenever valid
+  if (want == 0) return 0;
+  const int64_t Kmax = std::max<int64_t>(e->dpad, e->npad);
+  // 5 slices hold a float32 matrix (the reference's default rounding); a genuine fp64 matrix gets 7
+  bool exact32 = true;
+  for (size_t k = 0; exact32 && k < e->h_A.size(); ++k) exact32 = (double)(float)e->h_A[k] == e->h_A[k];
+  for (size_t k = 0; exact32 && k < e->h_At.size(); ++k) exact32 = (double)(float)e->h_At[k] == e->h_At[k];
+  e->oz_sa = exact32 ? OZ_SLICES_A : OZ_SLICES_B;
+  if (Kmax * e->oz_sa * 127 * 127 >= (1ll << 31)) return 0;
+  if (want < 0 && ((int64_t)e->dpad * e->npad < (1ll << 20) || e->C < 1024)) return 0;
+  const int d = (int)e->d;
+  std::vector<signed char> sl;
+  std::vector<int> ea;
+  const signed char* p = nullptr; const int* q = nullptr;
+  oz_slice_rows_host(e->h_A.data(), e->N, d, e->npad, e->dpad, e->oz_sa, &sl, &ea);
+  if (dev_upload(e, sl, &p) || dev_upload(e, ea, &q)) return -1;
+  e->oz_AG = const_cast<signed char*>(p); e->oz_eaG = const_cast<int*>(q);
+  oz_slice_rows_host(e->h_At.data(), d, e->N, e->dpad, e->npad, e->oz_sa, &sl, &ea);
+  if (dev_upload(e, sl, &p) || dev_upload(e, ea, &q)) return -1;
+  e->oz_AGt = const_cast<signed char*>(p); e->oz_eaGt = const_cast<int*>(q);
+  if (dev_alloc(e, (size_t)OZ_SLICES_B * e->ld * Kmax, &e->oz_B) ||
+      dev_alloc(e, (size_t)OZ_NUM_ORDERS * e->npad * e->ld, &e->oz_C) ||
+      dev_alloc(e, (size_t)e->ld, &e->oz_maxQ) || dev_alloc(e, (size_t)e->ld, &e->oz_maxR)) return -1;
+  HMCB_CUDA(ozaki_init());
+  HMCB_CUDA(ozaki_slice_map(e->oz_AG, e->dpad, e->npad, e->oz_sa, 128, &e->oz_mapAG));
+  HMCB_CUDA(ozaki_slice_map(e->oz_AGt, e->npad, e->dpad, e->oz_sa, 128, &e->oz_mapAGt));
+  HMCB_CUDA(ozaki_slice_map(e->oz_B, e->dpad, e->ld, OZ_SLICES_B, 256, &e->oz_mapBq));
+  HMCB_CUDA(ozaki_slice_map(e->oz_B, e->npad, e->ld, OZ_SLICES_B, 256, &e->oz_mapBr));
+  e->oz = true;
+  return 0;
+}
+
 StagedCommon staged_common(const hmcb_engine* e, const hmcb_block* b) {
   StagedCommon S{};
   S.T = e->T; S.C = (int)e->C; S.ld = e->ld; S.jtiles = e->jtiles;
@@ -829,8 +899,25 @@ int staged_gradient_pass(hmcb_engine* e, const double* q_in, UpdateEpi epi, cuda
     }
     case LK_DENSE_DIRECT: {
       ResidualEpi r{(int)e->N, (int)e->C, e->ld, e->dvec, e->dvar, e->R};
-      HMCB_CUDA(launch_gemm_residual(e->dA, e->dpad, e->npad, q_in, e->ld, e->dpad, r, s));
       epi.sub = nullptr;
+      if (e->oz) {
+        // both products as int8 slice products on the tcgen05 tensor cores (ozaki.cuh): per-chain scale,
+        // slices of the chain batch, 25 exact slice products in 7 int32 order planes, fp64 recombination
+        // fused with the residual / update epilogue
+        const long long plane_q = (long long)e->npad * e->ld, plane_r = (long long)e->dpad * e->ld;
+        HMCB_CUDA(launch_oz_colmax(q_in, e->dpad, e->ld, e->oz_maxQ, s));
+        HMCB_CUDA(launch_oz_slice_chains(q_in, e->dpad, e->ld, e->oz_maxQ, e->oz_B, s));
+        HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAG, e->oz_mapBq, e->npad, e->ld, e->dpad, e->oz_sa, OZ_SLICES_B,
+                                        OZ_NUM_ORDERS, e->oz_C, plane_q, e->ld, s));
+        HMCB_CUDA(launch_oz_combine_residual(e->oz_C, plane_q, e->npad, e->ld, e->oz_eaG, e->oz_maxQ, r, e->oz_maxR, s));
+        HMCB_CUDA(launch_oz_slice_chains(e->R, e->npad, e->ld, e->oz_maxR, e->oz_B, s));
+        HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAGt, e->oz_mapBr, e->dpad, e->ld, e->npad, e->oz_sa, OZ_SLICES_B,
+                                        OZ_NUM_ORDERS, e->oz_C, plane_r, e->ld, s));
+        HMCB_CUDA(launch_oz_combine_update(e->oz_C, plane_r, e->dpad, e->ld, e->oz_eaGt, e->oz_maxR, epi, s));
+        e->launches += 7;
+        break;
+      }
+      HMCB_CUDA(launch_gemm_residual(e->dA, e->dpad, e->npad, q_in, e->ld, e->dpad, r, s));
       HMCB_CUDA(launch_gemm_update(e->dAt, e->npad, e->dpad, e->R, e->ld, e->npad, epi, s));
       e->launches += 2;
       break;
@@ -1612,6 +1699,7 @@ int hmcb_finalize(hmcb_engine* e) {
       case LK_DENSE_DIRECT:
         if (dev_upload_tiled(e, e->h_A.data(), e->N, d, e->npad, e->dpad, &e->dA)) return -1;
         if (dev_upload_tiled(e, e->h_At.data(), d, e->N, e->dpad, e->npad, &e->dAt)) return -1;
+        if (oz_setup(e)) return -1;
         if (!e->h_Amis.empty()) {   // dense data covariance: the misfit pass applies U G, U d
           const double* um = nullptr;
           if (dev_upload_tiled(e, e->h_Amis.data(), e->N, d, e->npad, e->dpad, &e->dAmis) ||

@@ -107,6 +107,15 @@ cudaError_t launch_st_transpose(const double* in, int R, int Cc, int ldin, doubl
 cudaError_t ozaki_init();
 cudaError_t ozaki_slice_map(const signed char* base, long long K, long long rows, int slices, int box_rows,
                             CUtensorMap* out);
+constexpr int OZ_SLICES_A = 5, OZ_SLICES_B = 7, OZ_NUM_ORDERS = 7, OZ_SLICE_BITS = 7;
+cudaError_t launch_oz_colmax(const double* X, int rows, int ld, unsigned long long* maxbits, cudaStream_t s);
+cudaError_t launch_oz_slice_chains(const double* X, int K, int ld, const unsigned long long* maxbits,
+                                   signed char* out, cudaStream_t s);
+cudaError_t launch_oz_combine_residual(const int* C, long long plane_stride, int rows, int ld, const int* ea,
+                                       const unsigned long long* maxbits_in, const ResidualEpi& epi,
+                                       unsigned long long* maxbits_out, cudaStream_t s);
+cudaError_t launch_oz_combine_update(const int* C, long long plane_stride, int rows, int ld, const int* ea,
+                                     const unsigned long long* maxbits_in, const UpdateEpi& epi, cudaStream_t s);
 cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, long long M, long long N,
                                   long long K, int SA, int SB, int orders, int* C, long long plane_stride, int ldc,
                                   cudaStream_t s);

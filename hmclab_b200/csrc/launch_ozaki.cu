@@ -49,6 +49,37 @@ cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& ma
   return cudaGetLastError();
 }
 
+cudaError_t launch_oz_colmax(const double* X, int rows, int ld, unsigned long long* maxbits, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(maxbits, 0, (size_t)ld * sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
+  oz_colmax_kernel<<<dim3(ld / 128, (rows + 63) / 64), 128, 0, s>>>(X, rows, ld, maxbits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_oz_slice_chains(const double* X, int K, int ld, const unsigned long long* maxbits,
+                                   signed char* out, cudaStream_t s) {
+  if (K % 128 || ld % 32) return cudaErrorInvalidValue;
+  oz_slice_chains_kernel<<<dim3(ld / 32, K / 128), 256, 0, s>>>(X, K, ld, maxbits, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_oz_combine_residual(const int* C, long long plane_stride, int rows, int ld, const int* ea,
+                                       const unsigned long long* maxbits_in, const ResidualEpi& epi,
+                                       unsigned long long* maxbits_out, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(maxbits_out, 0, (size_t)ld * sizeof(unsigned long long), s);
+  if (e != cudaSuccess) return e;
+  oz_combine_kernel<ResidualEpi, true><<<dim3(ld / 128, (rows + 15) / 16), 128, 0, s>>>(C, plane_stride, rows, ld, ea,
+                                                                                      maxbits_in, epi, maxbits_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_oz_combine_update(const int* C, long long plane_stride, int rows, int ld, const int* ea,
+                                     const unsigned long long* maxbits_in, const UpdateEpi& epi, cudaStream_t s) {
+  oz_combine_kernel<UpdateEpi, false><<<dim3(ld / 128, (rows + 15) / 16), 128, 0, s>>>(C, plane_stride, rows, ld, ea,
+                                                                                     maxbits_in, epi, nullptr);
+  return cudaGetLastError();
+}
+
 }  // namespace hmcb
 
 // Test / measurement entry: exact int8 slice products on the tcgen05 tensor cores.
