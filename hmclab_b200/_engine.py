@@ -92,6 +92,7 @@ SIGNATURES = {
                                                C.c_double]),
     "hmcb_finalize": (C.c_int, [C.c_void_p]),
     "hmcb_path": (C.c_int, [C.c_void_p]),
+    "hmcb_dense_products_on_tcgen05": (C.c_int, [C.c_void_p]),
     "hmcb_grads_per_proposal": (C.c_int64, [C.c_void_p]),
     "hmcb_launch_count": (C.c_int64, [C.c_void_p]),
     "hmcb_kernel_timing_begin": (C.c_int, [C.c_void_p]),
@@ -265,6 +266,11 @@ class Engine:
     @property
     def grads_per_proposal(self) -> int:
         return int(self.lib.hmcb_grads_per_proposal(self._handle))
+
+    @property
+    def tcgen05_slices(self) -> int:
+        """0, or the int8 slices of the model matrix when the dense products run on tcgen05."""
+        return int(self.lib.hmcb_dense_products_on_tcgen05(self._handle))
 
     @property
     def launch_count(self) -> int:

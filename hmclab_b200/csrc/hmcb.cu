@@ -1763,6 +1763,7 @@ int hmcb_path(const hmcb_engine* e) {
   if (!e) return -1;
   return (e->path == HMCB_PATH_STAGED && e->fused_dense) ? HMCB_PATH_FUSED_DENSE : e->path;
 }
+int hmcb_dense_products_on_tcgen05(const hmcb_engine* e) { return e && e->oz ? e->oz_sa : 0; }
 int64_t hmcb_grads_per_proposal(const hmcb_engine* e) { return e ? e->S.grads_per_proposal : -1; }
 int64_t hmcb_launch_count(const hmcb_engine* e) { return e ? e->launches : -1; }
 

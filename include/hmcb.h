@@ -175,6 +175,10 @@ int hmcb_set_likelihood_srcloc2d(hmcb_engine *e, int64_t events, int64_t station
  * workspaces.  Must be called after the setters and before any evaluation. */
 int hmcb_finalize(hmcb_engine *e);
 int hmcb_path(const hmcb_engine *e);
+/* 0, or the number of int8 slices of the model matrix when the dense direct products G q and
+ * G^T r run as int8 slice products on the tcgen05 tensor cores (Ozaki scheme, csrc/ozaki.cuh; chosen
+ * by hmcb_finalize for large problems, HMCB_OZAKI=0 / 1 forces it off / on where valid) */
+int hmcb_dense_products_on_tcgen05(const hmcb_engine *e);
 /* gradient evaluations per proposal: amount_of_steps x {1,3,4} */
 int64_t hmcb_grads_per_proposal(const hmcb_engine *e);
 /* number of kernels launched by this engine since creation (bench bookkeeping) */
