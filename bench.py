@@ -478,7 +478,7 @@ def bench_workload(ctx, name, steps, warmup, block=0, chains=0):
             e2e["d2h_frac_of_ceiling"] = e2e["d2h_gbs_per_gpu"] / ctx.d2h_ceiling["d2h_ceiling_gbs_per_gpu"]
         del q0_host, out_host, acc_host
     path = eng.path
-    oz_slices = eng.tcgen05_slices
+    oz_pairs = eng.tcgen05_slice_pairs
     eng.close()
     del q, x, samples, accepted
     torch.cuda.empty_cache()
@@ -524,8 +524,8 @@ def bench_workload(ctx, name, steps, warmup, block=0, chains=0):
         achieved = per_pass / (kernel_ms * 1e-3) / 1e12
         kernel = {"fused_dense": "hmc_fused_dense_kernel (one launch per step)"}.get(
             path, "dmma_gemm_kernel (launch group = the GEMMs of one gradient evaluation of the batch)")
-        if oz_slices:
-            kernel = ("i8_gemm_orders_kernel (tcgen05 int8 slice products) + slicing / recombination kernels "
+        if oz_pairs:
+            kernel = ("i8_gemm_groups_kernel (tcgen05 int8 slice products) + slicing / recombination kernels "
                       "(launch group = everything of one gradient evaluation of the batch)")
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic, "kernel": kernel,
@@ -533,11 +533,11 @@ def bench_workload(ctx, name, steps, warmup, block=0, chains=0):
                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (%s), see fp64_peak" %
                                    ("sustained: median of a 2 s loop" if ms_per_step > 50 else "burst: best launch"),
                     "whole_step_tflops": flops * value / world / 1e12}
-        if oz_slices:
+        if oz_pairs:
             # Ozaki scheme: the fp64 products run as exact int8 slice products on tcgen05, so the
             # fp64-equivalent rate may exceed the native fp64 tensor peak it is quoted against
-            pairs = sum(1 for a in range(oz_slices) for b in range(7) if a + b < 7)
-            i8_ops = pairs * flops * C        # 2 M N K per pair and product = flops/2 * 2 products ... per evaluation
+            pairs = oz_pairs                      # slice products of G q and G^T r together
+            i8_ops = pairs * flops / 2.0 * C      # 2 N d int8 operations per slice product and chain
             sustained = committed_json("../MEASURED_PEAKS.json").get("bf16_tflops_sustained")
             roofline["note"] = ("fp64-equivalent rate of the int8-sliced (Ozaki) products: frac > 1 means faster than "
                                 "the native fp64 tensor path could be; the work actually executed is in `int8`")

@@ -65,6 +65,7 @@ SIGNATURES = {
     "hmcb_set_mass_full": (C.c_int, [C.c_void_p, _c_double_p, _c_double_p]),
     "hmcb_debug_i8_gemm": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmcb_debug_oz_slice_rows": (C.c_double, [_c_double_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "hmcb_clear_target": (C.c_int, [C.c_void_p]),
     "hmcb_add_prior": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, _c_double_p,
                                  _c_double_p, C.c_double]),
@@ -268,8 +269,8 @@ class Engine:
         return int(self.lib.hmcb_grads_per_proposal(self._handle))
 
     @property
-    def tcgen05_slices(self) -> int:
-        """0, or the int8 slices of the model matrix when the dense products run on tcgen05."""
+    def tcgen05_slice_pairs(self) -> int:
+        """0, or the int8 slice products per gradient evaluation when the dense products run on tcgen05."""
         return int(self.lib.hmcb_dense_products_on_tcgen05(self._handle))
 
     @property

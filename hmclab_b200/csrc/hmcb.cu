@@ -86,7 +86,8 @@ struct hmcb_engine {
   double *dAmis = nullptr, *dvecmis = nullptr;
   // Ozaki-sliced tcgen05 path of the dense direct products (ozaki.cuh)
   bool oz = false;
-  int oz_sa = OZ_SLICES_A;             // slices of the model matrix: 5 when it is exact in float32, else 7
+  int oz_saG = 0, oz_saGt = 0;         // int8 digits of G / G^T (what their rows need, at most the orders kept)
+  int oz_sb = OZ_SLICES_B, oz_orders = OZ_NUM_ORDERS;   // digits of the chain batch, orders kept
   signed char *oz_AG = nullptr, *oz_AGt = nullptr, *oz_B = nullptr;   // int8 slices of G, G^T, the chain batch
   int *oz_eaG = nullptr, *oz_eaGt = nullptr, *oz_C = nullptr;         // row exponents, int32 order planes
   unsigned long long *oz_maxQ = nullptr, *oz_maxR = nullptr;          // per-chain max |.| (bit patterns)
@@ -797,63 +798,59 @@ int upload_csr_both(hmcb_engine* e, const HostCsr& m, CsrDev* gather, StripDev* 
   return upload_csr_strips(e, m, sh, kb, emax, stages, strip);
 }
 
-// int8 slices of a host matrix [rows x cols] (row-major), zero padded to [rows_pad x cols_pad]:
-// a[i][k] = 2^ea[i] * sum_s slice_s[i][k] 2^(-7 (s+1)) + (what is below 2^(ea - 7 S)); see ozaki.cuh
-void oz_slice_rows_host(const double* A, int64_t rows, int64_t cols, int64_t rows_pad, int64_t cols_pad, int S,
-                        std::vector<signed char>* slices, std::vector<int>* ea) {
-  slices->assign((size_t)S * rows_pad * cols_pad, 0);
-  ea->assign((size_t)rows_pad, 0);
-  for (int64_t i = 0; i < rows; ++i) {
-    double m = 0.0;
-    for (int64_t k = 0; k < cols; ++k) m = std::max(m, std::fabs(A[(size_t)i * cols + k]));
-    if (!(m > 0.0) || !std::isfinite(m)) continue;
-    int ex = 0;
-    std::frexp(m, &ex);                       // m = f 2^ex, f in [0.5, 1)
-    (*ea)[(size_t)i] = ex;
-    for (int64_t k = 0; k < cols; ++k) {
-      double x = std::ldexp(A[(size_t)i * cols + k], -ex);
-      for (int s = 0; s < S; ++s) {
-        x *= 128.0;
-        const double v = std::trunc(x);
-        x -= v;
-        (*slices)[((size_t)s * rows_pad + i) * cols_pad + k] = (signed char)(int)v;
-      }
-    }
-  }
+// Digits of a model matrix for the Ozaki-sliced products: the fewest digit planes whose row-wise
+// representation error stays below 2^-45 of the row's absolute sum (at most `cap`), uploaded with the
+// row exponents.
+int oz_upload_matrix(hmcb_engine* e, const double* A, int64_t rows, int64_t cols, int64_t rows_pad, int64_t cols_pad,
+                     int cap, int* S_out, signed char** slices_out, int** ea_out) {
+  std::vector<int> ea((size_t)rows_pad);
+  int S = std::min(5, cap);
+  while (S < cap && oz_slice_rows_host(A, rows, cols, rows_pad, cols_pad, S, nullptr, ea.data()) > 0x1p-45) ++S;
+  std::vector<signed char> sl((size_t)S * rows_pad * cols_pad);
+  oz_slice_rows_host(A, rows, cols, rows_pad, cols_pad, S, sl.data(), ea.data());
+  const signed char* p = nullptr; const int* q = nullptr;
+  if (dev_upload(e, sl, &p) || dev_upload(e, ea, &q)) return -1;
+  *S_out = S; *slices_out = const_cast<signed char*>(p); *ea_out = const_cast<int*>(q);
+  return 0;
 }
 
 // Sets up the Ozaki-sliced tcgen05 path for the dense direct products when it is valid and pays:
-// int32 accumulation must not overflow (K * pairs * 127^2 < 2^31) and the products must be large.
+// int32 accumulation must not overflow (K * pairs * 128^2 < 2^31) and the products must be large.
 int oz_setup(hmcb_engine* e) {
   const int want = env_int("HMCB_OZAKI", -1);   // -1: when it pays, 0: never, 1: whenever valid
   if (want == 0) return 0;
+  e->oz_orders = std::min(std::max(env_int("HMCB_OZAKI_ORDERS", OZ_NUM_ORDERS), 4), OZ_SLICES_MAX);
+  e->oz_sb = e->oz_orders;
   const int64_t Kmax = std::max<int64_t>(e->dpad, e->npad);
-  // 5 slices hold a float32 matrix (the reference's default rounding); a genuine fp64 matrix gets 7
-  bool exact32 = true;
-  for (size_t k = 0; exact32 && k < e->h_A.size(); ++k) exact32 = (double)(float)e->h_A[k] == e->h_A[k];
-  for (size_t k = 0; exact32 && k < e->h_At.size(); ++k) exact32 = (double)(float)e->h_At[k] == e->h_At[k];
-  e->oz_sa = exact32 ? OZ_SLICES_A : OZ_SLICES_B;
-  if (Kmax * e->oz_sa * 127 * 127 >= (1ll << 31)) return 0;
+  if (Kmax * e->oz_orders * 128 * 128 >= (1ll << 31)) return 0;
   if (want < 0 && ((int64_t)e->dpad * e->npad < (1ll << 20) || e->C < 1024)) return 0;
+  for (double v : e->h_A) if (!std::isfinite(v)) return 0;
+  for (double v : e->h_At) if (!std::isfinite(v)) return 0;
   const int d = (int)e->d;
-  std::vector<signed char> sl;
-  std::vector<int> ea;
-  const signed char* p = nullptr; const int* q = nullptr;
-  oz_slice_rows_host(e->h_A.data(), e->N, d, e->npad, e->dpad, e->oz_sa, &sl, &ea);
-  if (dev_upload(e, sl, &p) || dev_upload(e, ea, &q)) return -1;
-  e->oz_AG = const_cast<signed char*>(p); e->oz_eaG = const_cast<int*>(q);
-  oz_slice_rows_host(e->h_At.data(), d, e->N, e->dpad, e->npad, e->oz_sa, &sl, &ea);
-  if (dev_upload(e, sl, &p) || dev_upload(e, ea, &q)) return -1;
-  e->oz_AGt = const_cast<signed char*>(p); e->oz_eaGt = const_cast<int*>(q);
-  if (dev_alloc(e, (size_t)OZ_SLICES_B * e->ld * Kmax, &e->oz_B) ||
-      dev_alloc(e, (size_t)OZ_NUM_ORDERS * e->npad * e->ld, &e->oz_C) ||
+  if (oz_upload_matrix(e, e->h_A.data(), e->N, d, e->npad, e->dpad, e->oz_orders, &e->oz_saG, &e->oz_AG, &e->oz_eaG) ||
+      oz_upload_matrix(e, e->h_At.data(), d, e->N, e->dpad, e->npad, e->oz_orders, &e->oz_saGt, &e->oz_AGt,
+                       &e->oz_eaGt))
+    return -1;
+  if (dev_alloc(e, (size_t)e->oz_sb * e->ld * Kmax, &e->oz_B) ||
+      dev_alloc(e, (size_t)e->oz_orders * e->npad * e->ld, &e->oz_C) ||
       dev_alloc(e, (size_t)e->ld, &e->oz_maxQ) || dev_alloc(e, (size_t)e->ld, &e->oz_maxR)) return -1;
   HMCB_CUDA(ozaki_init());
-  HMCB_CUDA(ozaki_slice_map(e->oz_AG, e->dpad, e->npad, e->oz_sa, 128, &e->oz_mapAG));
-  HMCB_CUDA(ozaki_slice_map(e->oz_AGt, e->npad, e->dpad, e->oz_sa, 128, &e->oz_mapAGt));
-  HMCB_CUDA(ozaki_slice_map(e->oz_B, e->dpad, e->ld, OZ_SLICES_B, 256, &e->oz_mapBq));
-  HMCB_CUDA(ozaki_slice_map(e->oz_B, e->npad, e->ld, OZ_SLICES_B, 256, &e->oz_mapBr));
+  HMCB_CUDA(ozaki_slice_map(e->oz_AG, e->dpad, e->npad, e->oz_saG, 128, &e->oz_mapAG));
+  HMCB_CUDA(ozaki_slice_map(e->oz_AGt, e->npad, e->dpad, e->oz_saGt, 128, &e->oz_mapAGt));
+  HMCB_CUDA(ozaki_slice_map(e->oz_B, e->dpad, e->ld, e->oz_sb, 256, &e->oz_mapBq));
+  HMCB_CUDA(ozaki_slice_map(e->oz_B, e->npad, e->ld, e->oz_sb, 256, &e->oz_mapBr));
   e->oz = true;
+  return 0;
+}
+
+// Y = G q as int8 slice products on the tcgen05 tensor cores (ozaki.cuh): per-chain scale, digits of the
+// chain batch, the exact slice products in int32 order planes -> oz_C (recombined by the caller's epilogue)
+int oz_forward_product(hmcb_engine* e, const double* q_in, cudaStream_t s) {
+  HMCB_CUDA(launch_oz_colmax(q_in, e->dpad, e->ld, e->oz_maxQ, s));
+  HMCB_CUDA(launch_oz_slice_chains(q_in, e->dpad, e->ld, e->oz_sb, e->oz_maxQ, e->oz_B, s));
+  HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAG, e->oz_mapBq, e->npad, e->ld, e->dpad, e->oz_saG, e->oz_sb, e->oz_orders,
+                                  e->oz_C, (long long)e->npad * e->ld, e->ld, s));
+  e->launches += 3;
   return 0;
 }
 
@@ -901,20 +898,18 @@ int staged_gradient_pass(hmcb_engine* e, const double* q_in, UpdateEpi epi, cuda
       ResidualEpi r{(int)e->N, (int)e->C, e->ld, e->dvec, e->dvar, e->R};
       epi.sub = nullptr;
       if (e->oz) {
-        // both products as int8 slice products on the tcgen05 tensor cores (ozaki.cuh): per-chain scale,
-        // slices of the chain batch, 25 exact slice products in 7 int32 order planes, fp64 recombination
-        // fused with the residual / update epilogue
+        // both products as int8 slice products on the tcgen05 tensor cores (ozaki.cuh), the fp64
+        // recombination fused with the residual / update epilogue
         const long long plane_q = (long long)e->npad * e->ld, plane_r = (long long)e->dpad * e->ld;
-        HMCB_CUDA(launch_oz_colmax(q_in, e->dpad, e->ld, e->oz_maxQ, s));
-        HMCB_CUDA(launch_oz_slice_chains(q_in, e->dpad, e->ld, e->oz_maxQ, e->oz_B, s));
-        HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAG, e->oz_mapBq, e->npad, e->ld, e->dpad, e->oz_sa, OZ_SLICES_B,
-                                        OZ_NUM_ORDERS, e->oz_C, plane_q, e->ld, s));
-        HMCB_CUDA(launch_oz_combine_residual(e->oz_C, plane_q, e->npad, e->ld, e->oz_eaG, e->oz_maxQ, r, e->oz_maxR, s));
-        HMCB_CUDA(launch_oz_slice_chains(e->R, e->npad, e->ld, e->oz_maxR, e->oz_B, s));
-        HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAGt, e->oz_mapBr, e->dpad, e->ld, e->npad, e->oz_sa, OZ_SLICES_B,
-                                        OZ_NUM_ORDERS, e->oz_C, plane_r, e->ld, s));
-        HMCB_CUDA(launch_oz_combine_update(e->oz_C, plane_r, e->dpad, e->ld, e->oz_eaGt, e->oz_maxR, epi, s));
-        e->launches += 7;
+        if (oz_forward_product(e, q_in, s)) return -1;
+        HMCB_CUDA(launch_oz_combine_residual(e->oz_C, plane_q, e->npad, e->ld, e->oz_orders, e->oz_eaG, e->oz_maxQ, r,
+                                             e->oz_maxR, s));
+        HMCB_CUDA(launch_oz_slice_chains(e->R, e->npad, e->ld, e->oz_sb, e->oz_maxR, e->oz_B, s));
+        HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAGt, e->oz_mapBr, e->dpad, e->ld, e->npad, e->oz_saGt, e->oz_sb,
+                                        e->oz_orders, e->oz_C, plane_r, e->ld, s));
+        HMCB_CUDA(launch_oz_combine_update(e->oz_C, plane_r, e->dpad, e->ld, e->oz_orders, e->oz_eaGt, e->oz_maxR, epi,
+                                           s));
+        e->launches += 4;
         break;
       }
       HMCB_CUDA(launch_gemm_residual(e->dA, e->dpad, e->npad, q_in, e->ld, e->dpad, r, s));
@@ -960,6 +955,12 @@ int staged_misfit_pass(hmcb_engine* e, const double* q, cudaStream_t s) {
       break;
     case LK_DENSE_DIRECT:
       m.rows = (int)e->N; m.vec = e->dAmis ? e->dvecmis : e->dvec; m.sigma = e->dsigma;
+      if (e->oz && !e->dAmis) {   // G q on tcgen05, the misfit sums in the recombination (one partial per 128 rows)
+        if (oz_forward_product(e, q, s)) return -1;
+        HMCB_CUDA(launch_oz_combine_misfit(e->oz_C, (long long)e->npad * e->ld, e->npad, e->ld, e->oz_orders, e->oz_eaG,
+                                           e->oz_maxQ, m, s));
+        break;
+      }
       HMCB_CUDA(launch_gemm_misfit(e->dAmis ? e->dAmis : e->dA, e->dpad, e->npad, q, e->ld, e->dpad, m, s));
       break;
     case LK_CSR_DIRECT:
@@ -1763,7 +1764,15 @@ int hmcb_path(const hmcb_engine* e) {
   if (!e) return -1;
   return (e->path == HMCB_PATH_STAGED && e->fused_dense) ? HMCB_PATH_FUSED_DENSE : e->path;
 }
-int hmcb_dense_products_on_tcgen05(const hmcb_engine* e) { return e && e->oz ? e->oz_sa : 0; }
+int hmcb_dense_products_on_tcgen05(const hmcb_engine* e) {
+  if (!e || !e->oz) return 0;
+  // slice pairs of the two products of one gradient evaluation: digits s of the matrix, t of the batch, s + t < orders
+  int pairs = 0;
+  for (int sa : {e->oz_saG, e->oz_saGt})
+    for (int a = 0; a < sa; ++a)
+      for (int b = 0; b < e->oz_sb; ++b) pairs += (a + b < e->oz_orders) ? 1 : 0;
+  return pairs;
+}
 int64_t hmcb_grads_per_proposal(const hmcb_engine* e) { return e ? e->S.grads_per_proposal : -1; }
 int64_t hmcb_launch_count(const hmcb_engine* e) { return e ? e->launches : -1; }
 

@@ -107,15 +107,21 @@ cudaError_t launch_st_transpose(const double* in, int R, int Cc, int ldin, doubl
 cudaError_t ozaki_init();
 cudaError_t ozaki_slice_map(const signed char* base, long long K, long long rows, int slices, int box_rows,
                             CUtensorMap* out);
-constexpr int OZ_SLICES_A = 5, OZ_SLICES_B = 7, OZ_NUM_ORDERS = 7, OZ_SLICE_BITS = 7;
+// digits of the chain batch / orders kept by default (HMCB_OZAKI_ORDERS=7: one more of each); the model
+// matrix gets the digits its rows need, at most OZ_SLICES_MAX
+constexpr int OZ_SLICES_B = 6, OZ_NUM_ORDERS = 6, OZ_SLICES_MAX = 7, OZ_SLICE_BITS = 8;
+double oz_slice_rows_host(const double* A, long long rows, long long cols, long long rows_pad, long long cols_pad,
+                          int S, signed char* slices, int* ea);
 cudaError_t launch_oz_colmax(const double* X, int rows, int ld, unsigned long long* maxbits, cudaStream_t s);
-cudaError_t launch_oz_slice_chains(const double* X, int K, int ld, const unsigned long long* maxbits,
+cudaError_t launch_oz_slice_chains(const double* X, int K, int ld, int SB, const unsigned long long* maxbits,
                                    signed char* out, cudaStream_t s);
-cudaError_t launch_oz_combine_residual(const int* C, long long plane_stride, int rows, int ld, const int* ea,
-                                       const unsigned long long* maxbits_in, const ResidualEpi& epi,
+cudaError_t launch_oz_combine_residual(const int* C, long long plane_stride, int rows, int ld, int orders,
+                                       const int* ea, const unsigned long long* maxbits_in, const ResidualEpi& epi,
                                        unsigned long long* maxbits_out, cudaStream_t s);
-cudaError_t launch_oz_combine_update(const int* C, long long plane_stride, int rows, int ld, const int* ea,
+cudaError_t launch_oz_combine_update(const int* C, long long plane_stride, int rows, int ld, int orders, const int* ea,
                                      const unsigned long long* maxbits_in, const UpdateEpi& epi, cudaStream_t s);
+cudaError_t launch_oz_combine_misfit(const int* C, long long plane_stride, int rows, int ld, int orders, const int* ea,
+                                     const unsigned long long* maxbits_in, const MisfitEpi& epi, cudaStream_t s);
 cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, long long M, long long N,
                                   long long K, int SA, int SB, int orders, int* C, long long plane_stride, int ldc,
                                   cudaStream_t s);

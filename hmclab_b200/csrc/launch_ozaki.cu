@@ -1,6 +1,10 @@
 // launch_ozaki.cu -- launchers of the int8-sliced (Ozaki) dense products on tcgen05 (ozaki.cuh).
 #include <cudaTypedefs.h>
 
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 #include "launch.cuh"
 #include "ozaki.cuh"
 
@@ -35,17 +39,78 @@ cudaError_t ozaki_slice_map(const signed char* base, long long K, long long rows
 }
 
 cudaError_t ozaki_init() {
-  return cudaFuncSetAttribute(i8_gemm_orders_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES);
+  return cudaFuncSetAttribute(i8_gemm_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES);
+}
+
+// The dataflow program of the order group {orders[0], orders[1]}: walking the B digits t upward, B_t meets
+// A_(o - t) for each order o of the group; a tile is loaded right before its first product and its ring
+// slot is released by the last product that reads it.
+static bool build_program(int SA, int SB, const int* orders, int n_acc, OzProgram* P) {
+  std::memset(P, 0, sizeof(*P));
+  P->n_acc = n_acc;
+  int a_idx[OZ_MAX_SLICES], last_a[OZ_MAX_OPS], last_b[OZ_MAX_OPS];
+  bool acc_seen[OZ_MAX_ACC] = {false, false};
+  for (int s = 0; s < OZ_MAX_SLICES; ++s) a_idx[s] = -1;
+  for (int a = 0; a < n_acc; ++a) P->order[a] = orders[a];
+  for (int t = 0; t < SB; ++t) {
+    int b_idx = -1;
+    for (int a = 0; a < n_acc; ++a) {
+      const int s = orders[a] - t;
+      if (s < 0 || s >= SA) continue;
+      if (P->n_loads + 2 > OZ_MAX_OPS || P->n_mma >= OZ_MAX_OPS) return false;
+      if (b_idx < 0) {
+        b_idx = P->nB++;
+        P->load_is_b[P->n_loads] = 1; P->load_slice[P->n_loads++] = (unsigned char)t;
+      }
+      if (a_idx[s] < 0) {
+        a_idx[s] = P->nA++;
+        P->load_is_b[P->n_loads] = 0; P->load_slice[P->n_loads++] = (unsigned char)s;
+      }
+      const int m = P->n_mma++;
+      P->mma_a[m] = (unsigned char)a_idx[s]; P->mma_b[m] = (unsigned char)b_idx; P->mma_acc[m] = (unsigned char)a;
+      P->mma_flags[m] = acc_seen[a] ? 0 : 4;
+      acc_seen[a] = true;
+      last_a[a_idx[s]] = m; last_b[b_idx] = m;
+    }
+  }
+  for (int i = 0; i < P->nA; ++i) P->mma_flags[last_a[i]] |= 1;
+  for (int i = 0; i < P->nB; ++i) P->mma_flags[last_b[i]] |= 2;
+  // the A ring must hold the tiles in flight between a load and its release: every product may only wait
+  // for tiles that precede, in load order, the tiles the producer can be blocked on
+  return P->n_mma > 0 && P->nA > 0 && P->nB > 0;
+}
+
+// orders 0 .. orders-1 in groups of two consecutive orders (the last one alone when `orders` is odd),
+// heaviest group first
+bool oz_build_plan(int SA, int SB, int orders, long long M, long long N, OzPlan* plan) {
+  std::memset(plan, 0, sizeof(*plan));
+  if (SA < 1 || SB < 1 || SA > OZ_MAX_SLICES || SB > OZ_MAX_SLICES || orders < 1 || orders > OZ_MAX_ORDERS ||
+      orders > SA + SB - 1)
+    return false;
+  plan->tiles_m = (int)(M / OZ_BM);
+  plan->tiles_n = (int)((N + OZ_BN - 1) / OZ_BN);
+  for (int o = orders - 1; o >= 0; o -= 2) {
+    if (plan->n_groups >= OZ_MAX_GROUPS) return false;
+    int ord[2] = {o > 0 ? o - 1 : 0, o};
+    const int n_acc = o > 0 ? 2 : 1;
+    if (!build_program(SA, SB, n_acc == 2 ? ord : &ord[1], n_acc, &plan->g[plan->n_groups++])) return false;
+  }
+  std::stable_sort(plan->g, plan->g + plan->n_groups,
+                   [](const OzProgram& a, const OzProgram& b) { return a.n_mma > b.n_mma; });
+  return true;
 }
 
 // C[o] (o < orders) = sum_{s+t=o} A_s B_t^T;  M % 128 == 0, K % 128 == 0, ldc = padded N (% 128 == 0)
 cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, long long M, long long N,
                                   long long K, int SA, int SB, int orders, int* C, long long plane_stride, int ldc,
                                   cudaStream_t s) {
-  if (M % OZ_BM || K % OZ_BK || N % 128 || orders < 1 || orders > SA + SB - 1) return cudaErrorInvalidValue;
-  const dim3 grid((unsigned)((N + OZ_BN - 1) / OZ_BN), (unsigned)(M / OZ_BM), (unsigned)orders);
-  i8_gemm_orders_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, s>>>(mapA, mapB, (int)(K / OZ_BK), SA, SB, C, plane_stride,
-                                                               ldc);
+  if (M % OZ_BM || K % OZ_BK || N % 128) return cudaErrorInvalidValue;
+  OzPlan plan;
+  if (!oz_build_plan(SA, SB, orders, M, N, &plan)) return cudaErrorInvalidValue;
+  const long long ctas = (long long)plan.n_groups * plan.tiles_m * plan.tiles_n;
+  if (ctas <= 0 || ctas > 0x7fffffffll) return cudaErrorInvalidValue;
+  i8_gemm_groups_kernel<<<(unsigned)ctas, OZ_THREADS, OZ_SMEM_BYTES, s>>>(mapA, mapB, plan, (int)(K / OZ_BK), C,
+                                                                           plane_stride, ldc);
   return cudaGetLastError();
 }
 
@@ -56,28 +121,70 @@ cudaError_t launch_oz_colmax(const double* X, int rows, int ld, unsigned long lo
   return cudaGetLastError();
 }
 
-cudaError_t launch_oz_slice_chains(const double* X, int K, int ld, const unsigned long long* maxbits,
+cudaError_t launch_oz_slice_chains(const double* X, int K, int ld, int SB, const unsigned long long* maxbits,
                                    signed char* out, cudaStream_t s) {
-  if (K % 128 || ld % 32) return cudaErrorInvalidValue;
-  oz_slice_chains_kernel<<<dim3(ld / 32, K / 128), 256, 0, s>>>(X, K, ld, maxbits, out);
+  if (K % 128 || ld % 32 || SB < 1 || SB > OZ_MAX_SLICES) return cudaErrorInvalidValue;
+  oz_slice_chains_kernel<<<dim3(ld / 32, K / 128), 256, 0, s>>>(X, K, ld, SB, maxbits, out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_oz_combine_residual(const int* C, long long plane_stride, int rows, int ld, const int* ea,
-                                       const unsigned long long* maxbits_in, const ResidualEpi& epi,
+cudaError_t launch_oz_combine_residual(const int* C, long long plane_stride, int rows, int ld, int orders,
+                                       const int* ea, const unsigned long long* maxbits_in, const ResidualEpi& epi,
                                        unsigned long long* maxbits_out, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(maxbits_out, 0, (size_t)ld * sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
-  oz_combine_kernel<ResidualEpi, true><<<dim3(ld / 128, (rows + 15) / 16), 128, 0, s>>>(C, plane_stride, rows, ld, ea,
-                                                                                      maxbits_in, epi, maxbits_out);
+  oz_combine_kernel<ResidualEpi, true, 16><<<dim3(ld / 128, (rows + 15) / 16), 128, 0, s>>>(
+      C, plane_stride, rows, ld, orders, ea, maxbits_in, epi, maxbits_out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_oz_combine_update(const int* C, long long plane_stride, int rows, int ld, const int* ea,
+cudaError_t launch_oz_combine_update(const int* C, long long plane_stride, int rows, int ld, int orders, const int* ea,
                                      const unsigned long long* maxbits_in, const UpdateEpi& epi, cudaStream_t s) {
-  oz_combine_kernel<UpdateEpi, false><<<dim3(ld / 128, (rows + 15) / 16), 128, 0, s>>>(C, plane_stride, rows, ld, ea,
-                                                                                     maxbits_in, epi, nullptr);
+  oz_combine_kernel<UpdateEpi, false, 16><<<dim3(ld / 128, (rows + 15) / 16), 128, 0, s>>>(
+      C, plane_stride, rows, ld, orders, ea, maxbits_in, epi, nullptr);
   return cudaGetLastError();
+}
+
+// per-chain misfit partial sums: one partial per 128-row chunk, like the tiles of the DMMA GEMM (epi.part
+// holds [rows / 128 x ld])
+cudaError_t launch_oz_combine_misfit(const int* C, long long plane_stride, int rows, int ld, int orders, const int* ea,
+                                     const unsigned long long* maxbits_in, const MisfitEpi& epi, cudaStream_t s) {
+  oz_combine_kernel<MisfitEpi, false, 128><<<dim3(ld / 128, (rows + 127) / 128), 128, 0, s>>>(
+      C, plane_stride, rows, ld, orders, ea, maxbits_in, epi, nullptr);
+  return cudaGetLastError();
+}
+
+// Host side of the slicing: balanced radix-256 digits of a row-major matrix [rows x cols], zero padded to
+// [rows_pad x cols_pad], S digit planes; a[i][k] = 2^ea[i] * sum_s slice_s[i][k] 256^-(s+1) + rounding.
+// Returns max over the rows of (sum_k |rounding|) / (sum_k |a[i][k]|).
+double oz_slice_rows_host(const double* A, long long rows, long long cols, long long rows_pad, long long cols_pad,
+                          int S, signed char* slices, int* ea) {
+  double worst = 0.0;
+  if (slices) std::memset(slices, 0, (size_t)S * rows_pad * cols_pad);
+  std::memset(ea, 0, sizeof(int) * (size_t)rows_pad);
+  const double up = std::ldexp(1.0, OZ_BITS * S);
+  for (long long i = 0; i < rows; ++i) {
+    const double* a = A + (size_t)i * cols;
+    double m = 0.0, sum = 0.0, err = 0.0;
+    for (long long k = 0; k < cols; ++k) { m = std::max(m, std::fabs(a[k])); sum += std::fabs(a[k]); }
+    unsigned long long bits;
+    std::memcpy(&bits, &m, sizeof(bits));
+    const int e = oz_exponent(bits);
+    if (e == INT_MIN || !(m > 0.0)) continue;   // non-finite rows are refused by the caller
+    ea[i] = e;
+    for (long long k = 0; k < cols; ++k) {
+      const double y = oz_scale_down(a[k], e) * up;   // exact
+      const double r = std::nearbyint(y);
+      err += std::fabs(y - r);
+      if (slices) {
+        signed char digit[OZ_MAX_SLICES];
+        oz_digits((long long)r, S, digit);
+        for (int s = 0; s < S; ++s) slices[((size_t)s * rows_pad + i) * cols_pad + k] = digit[s];
+      }
+    }
+    if (sum > 0.0) worst = std::max(worst, std::ldexp(err, e - OZ_BITS * S) / sum);
+  }
+  return worst;
 }
 
 }  // namespace hmcb
@@ -96,4 +203,11 @@ extern "C" int hmcb_debug_i8_gemm(int device, int64_t M, int64_t N, int64_t K, i
       cudaSuccess)
     return -4;
   return 0;
+}
+
+// Test entry (host only): the digits oz_slice_rows_host gives a matrix, and its representation error.
+extern "C" double hmcb_debug_oz_slice_rows(const double* A, int64_t rows, int64_t cols, int S, signed char* slices,
+                                           int32_t* ea) {
+  if (!A || !ea || rows <= 0 || cols <= 0 || S < 1 || S > hmcb::OZ_MAX_SLICES) return -1.0;
+  return hmcb::oz_slice_rows_host(A, rows, cols, rows, cols, S, slices, ea);
 }

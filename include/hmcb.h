@@ -103,6 +103,11 @@ int hmcb_set_mass_full(hmcb_engine *e, const double *cholesky_lower, const doubl
  * multiples of 128), C [orders][M x N] int32 DEVICE: C[o] = sum over s + t = o of A_s B_t^T. */
 int hmcb_debug_i8_gemm(int device, int64_t M, int64_t N, int64_t K, int SA, int SB, int orders,
                        const signed char *A, const signed char *B, int32_t *C, void *stream);
+/* Host side of the slicing (no GPU needed): balanced radix-256 digits of a HOST matrix [rows x cols],
+ * a[i][k] = 2^ea[i] * sum_s slices[s][i][k] 256^-(s+1) + rounding; slices [S][rows x cols] int8 (may be
+ * NULL), ea [rows].  Returns max over rows of sum_k |rounding| / sum_k |a[i][k]|, or -1 on bad input. */
+double hmcb_debug_oz_slice_rows(const double *A, int64_t rows, int64_t cols, int S, signed char *slices,
+                                int32_t *ea);
 
 /* target distribution ----------------------------------------------------------------
  * Built from a distribution object tree (BayesRule / Composite / priors / likelihood) by
@@ -175,9 +180,10 @@ int hmcb_set_likelihood_srcloc2d(hmcb_engine *e, int64_t events, int64_t station
  * workspaces.  Must be called after the setters and before any evaluation. */
 int hmcb_finalize(hmcb_engine *e);
 int hmcb_path(const hmcb_engine *e);
-/* 0, or the number of int8 slices of the model matrix when the dense direct products G q and
- * G^T r run as int8 slice products on the tcgen05 tensor cores (Ozaki scheme, csrc/ozaki.cuh; chosen
- * by hmcb_finalize for large problems, HMCB_OZAKI=0 / 1 forces it off / on where valid) */
+/* 0, or the number of int8 slice products per gradient evaluation (both products together) when the
+ * dense direct products G q and G^T r run as int8 slice products on the tcgen05 tensor cores (Ozaki
+ * scheme, csrc/ozaki.cuh; chosen by hmcb_finalize for large problems, HMCB_OZAKI=0 / 1 forces it off /
+ * on where valid, HMCB_OZAKI_ORDERS=4..7 sets the orders kept, default 6) */
 int hmcb_dense_products_on_tcgen05(const hmcb_engine *e);
 /* gradient evaluations per proposal: amount_of_steps x {1,3,4} */
 int64_t hmcb_grads_per_proposal(const hmcb_engine *e);

@@ -24,19 +24,25 @@ def _i8_gemm(A, B, orders):
     return out
 
 
-@pytest.mark.parametrize("M,N,K,SA,SB", [(128, 256, 128, 1, 1), (256, 512, 384, 2, 3), (384, 384, 1152, 3, 2)])
-def test_i8_slice_products_are_exact(M, N, K, SA, SB):
+@pytest.mark.parametrize("M,N,K,SA,SB,orders", [
+    (128, 256, 128, 1, 1, 1), (256, 512, 384, 2, 3, 4), (384, 384, 1152, 3, 2, 4),
+    (256, 1280, 640, 5, 6, 6),      # the default scheme: digits 5 x 6, orders 0..5 in three groups of two
+    (128, 2304, 256, 6, 6, 6), (256, 256, 2048, 7, 7, 7), (128, 128, 256, 5, 6, 3), (2560, 256, 128, 4, 7, 5)])
+def test_i8_slice_products_are_exact(M, N, K, SA, SB, orders):
+    """Every order plane equals the integer sum of its slice products, over the full int8 range; the
+    grouped kernel (two orders per CTA sharing operand tiles) with odd and even order counts, column
+    panels that do not fill (N / 256 not a multiple of 8) and a half-empty last column tile."""
     import torch
 
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
-    A = torch.randint(-64, 64, (SA, M, K), generator=g, device="cuda", dtype=torch.int8)
-    B = torch.randint(-64, 64, (SB, N, K), generator=g, device="cuda", dtype=torch.int8)
-    orders = SA + SB - 1
+    A = torch.randint(-128, 128, (SA, M, K), generator=g, device="cuda", dtype=torch.int8)
+    B = torch.randint(-128, 128, (SB, N, K), generator=g, device="cuda", dtype=torch.int8)
     got = _i8_gemm(A, B, orders)
     ref = torch.zeros(orders, M, N, dtype=torch.float64, device="cuda")
     for s in range(SA):
         for t in range(SB):
-            ref[s + t] += A[s].double() @ B[t].double().T
+            if s + t < orders:
+                ref[s + t] += A[s].double() @ B[t].double().T
     assert torch.equal(got.double(), ref)
 
 
@@ -81,3 +87,40 @@ def test_ozaki_path_reproduces_the_golden_trajectories(monkeypatch, name):
     qq[0, 0] = float("inf")
     g1 = eng.gradient(qq).cpu().numpy()
     assert np.all(np.isnan(g1[0]) | np.isinf(g1[0])) and np.array_equal(g1[1:], g0[1:])
+
+
+def test_ozaki_gradient_follows_chain_scales_over_many_magnitudes():
+    """Per-chain scaling: chains whose coordinates differ by hundreds of binades (and an all-zero chain)
+    share one batch; each chain's gradient agrees with numpy to fp64-BLAS accuracy relative to its own
+    natural scale sum_k |G^T|_jk |r_k|."""
+    import os
+
+    import torch
+
+    import hmclab_b200.Distributions as D
+    import hmclab_b200.MassMatrices as Mm
+    from hmclab_b200._engine import Engine
+    from hmclab_b200._lowering import describe, describe_mass, flatten
+
+    os.environ["HMCB_OZAKI"] = "1"
+    try:
+        rng = np.random.default_rng(5)
+        N, d, C_ = 300, 200, 64
+        G = rng.normal(size=(N, d)) * np.exp(rng.normal(size=(N, 1)) * 3.0)
+        dat = rng.normal(size=(N, 1))
+        var = rng.uniform(0.5, 2.0, size=(N, 1))
+        lik = D.LinearMatrix(G, dat, var, premultiplication=False)
+        eng = Engine(flatten(describe(lik)), describe_mass(Mm.Unit(d)), C_, integrator="lf", amount_of_steps=1)
+        assert eng.tcgen05_slice_pairs > 0
+        q = rng.normal(size=(C_, d)) * np.exp2(rng.integers(-300, 300, size=(C_, 1)).astype(np.float64))
+        q[7] = 0.0
+        got = eng.gradient(torch.as_tensor(q).cuda()).cpu().numpy()
+    finally:
+        os.environ.pop("HMCB_OZAKI", None)
+    inner = lik.Distribution
+    G32, Gt = np.asarray(inner.G, dtype=np.float64), np.asarray(inner.Gt, dtype=np.float64)
+    d32, v32 = np.asarray(inner.d, dtype=np.float64), np.asarray(inner.data_variance, dtype=np.float64)
+    r = (G32 @ q.T - d32) / v32
+    ref = (Gt @ r).T
+    scale = (np.abs(Gt) @ np.abs(r)).T + (np.abs(Gt) @ ((np.abs(G32) @ np.abs(q.T)) / v32)).T
+    assert np.all(np.abs(got - ref) <= 1e-12 * scale)
