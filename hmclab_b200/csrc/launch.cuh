@@ -122,8 +122,10 @@ cudaError_t launch_oz_combine_update(const int* C, long long plane_stride, int r
                                      const unsigned long long* maxbits_in, const UpdateEpi& epi, cudaStream_t s);
 cudaError_t launch_oz_combine_misfit(const int* C, long long plane_stride, int rows, int ld, int orders, const int* ea,
                                      const unsigned long long* maxbits_in, const MisfitEpi& epi, cudaStream_t s);
-cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, long long M, long long N,
-                                  long long K, int SA, int SB, int orders, int* C, long long plane_stride, int ldc,
+cudaError_t ozaki_plane_map(const int* base, long long ldc, long long M, int orders, long long plane_stride,
+                            CUtensorMap* out);
+cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapC,
+                                  long long M, long long N, long long K, int SA, int SB, int orders, int ldc,
                                   cudaStream_t s);
 
 }  // namespace hmcb

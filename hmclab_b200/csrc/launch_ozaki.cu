@@ -38,6 +38,22 @@ cudaError_t ozaki_slice_map(const signed char* base, long long K, long long rows
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// order planes [orders][M x ldc] int32 -> 3-D tensor {ldc, M, orders}, box {32, 32, 1}, 128-byte swizzle: what one
+// epilogue warp stores at a time
+cudaError_t ozaki_plane_map(const int* base, long long ldc, long long M, int orders, long long plane_stride,
+                            CUtensorMap* out) {
+  PFN_cuTensorMapEncodeTiled_v12000 encode = tensor_map_encoder();
+  if (!encode) return cudaErrorNotSupported;
+  const cuuint64_t dims[3] = {(cuuint64_t)ldc, (cuuint64_t)M, (cuuint64_t)orders};
+  const cuuint64_t strides[2] = {(cuuint64_t)ldc * 4u, (cuuint64_t)plane_stride * 4u};
+  const cuuint32_t box[3] = {32u, 32u, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, const_cast<int*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 cudaError_t ozaki_init() {
   return cudaFuncSetAttribute(i8_gemm_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES);
 }
@@ -100,17 +116,17 @@ bool oz_build_plan(int SA, int SB, int orders, long long M, long long N, OzPlan*
   return true;
 }
 
-// C[o] (o < orders) = sum_{s+t=o} A_s B_t^T;  M % 128 == 0, K % 128 == 0, ldc = padded N (% 128 == 0)
-cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, long long M, long long N,
-                                  long long K, int SA, int SB, int orders, int* C, long long plane_stride, int ldc,
+// C[o] (o < orders) = sum_{s+t=o} A_s B_t^T;  M % 128 == 0, K % 128 == 0, ldc = padded N (% 128 == 0);
+// mapC = ozaki_plane_map of the order planes
+cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapC,
+                                  long long M, long long N, long long K, int SA, int SB, int orders, int ldc,
                                   cudaStream_t s) {
   if (M % OZ_BM || K % OZ_BK || N % 128) return cudaErrorInvalidValue;
   OzPlan plan;
   if (!oz_build_plan(SA, SB, orders, M, N, &plan)) return cudaErrorInvalidValue;
   const long long ctas = (long long)plan.n_groups * plan.tiles_m * plan.tiles_n;
   if (ctas <= 0 || ctas > 0x7fffffffll) return cudaErrorInvalidValue;
-  i8_gemm_groups_kernel<<<(unsigned)ctas, OZ_THREADS, OZ_SMEM_BYTES, s>>>(mapA, mapB, plan, (int)(K / OZ_BK), C,
-                                                                           plane_stride, ldc);
+  i8_gemm_groups_kernel<<<(unsigned)ctas, OZ_THREADS, OZ_SMEM_BYTES, s>>>(mapA, mapB, mapC, plan, (int)(K / OZ_BK), ldc);
   return cudaGetLastError();
 }
 
@@ -196,10 +212,11 @@ extern "C" int hmcb_debug_i8_gemm(int device, int64_t M, int64_t N, int64_t K, i
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || SA < 1 || SB < 1) return -1;
   if (cudaSetDevice(device) != cudaSuccess) return -1;
   if (ozaki_init() != cudaSuccess) return -2;
-  CUtensorMap mapA, mapB;
+  CUtensorMap mapA, mapB, mapC;
   if (ozaki_slice_map(A, K, M, SA, OZ_BM, &mapA) != cudaSuccess) return -3;
   if (ozaki_slice_map(B, K, N, SB, OZ_BN, &mapB) != cudaSuccess) return -3;
-  if (launch_i8_gemm_orders(mapA, mapB, M, N, K, SA, SB, orders, C, M * N, (int)N, static_cast<cudaStream_t>(stream)) !=
+  if (ozaki_plane_map(C, N, M, orders, M * N, &mapC) != cudaSuccess) return -3;
+  if (launch_i8_gemm_orders(mapA, mapB, mapC, M, N, K, SA, SB, orders, (int)N, static_cast<cudaStream_t>(stream)) !=
       cudaSuccess)
     return -4;
   return 0;

@@ -42,10 +42,10 @@
 namespace hmcb {
 
 constexpr int OZ_BM = 128, OZ_BN = 256, OZ_BK = 128;   // CTA tile; BK int8 = one 128-byte swizzle row
-constexpr int OZ_NA = 4, OZ_NB = 4;                    // slots of the A / B tile rings
+constexpr int OZ_NA = 6, OZ_NB = 4;                    // slots of the A / B tile rings
 constexpr int OZ_A_BYTES = OZ_BM * OZ_BK, OZ_B_BYTES = OZ_BN * OZ_BK;   // 16 KB, 32 KB
 constexpr size_t OZ_SMEM_BYTES = (size_t)OZ_NA * OZ_A_BYTES + (size_t)OZ_NB * OZ_B_BYTES + 1024;   // + alignment slack
-constexpr int OZ_THREADS = 256;    // warp 0: TMA, warp 1: MMA, warp 2: TMEM allocation, warps 4-7: epilogue
+constexpr int OZ_THREADS = 256;    // warp 0: TMA (A), warp 1: MMA, warp 2: TMEM allocation, warp 3: TMA (B), warps 4-7: epilogue
 constexpr int OZ_BITS = 8;         // bits per slice (balanced digits in [-128, 127])
 constexpr int OZ_MAX_SLICES = 7, OZ_MAX_ORDERS = 7;
 constexpr int OZ_MAX_ACC = 2, OZ_MAX_OPS = 16, OZ_MAX_GROUPS = 4, OZ_PANEL = 8;
@@ -96,7 +96,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {   // arrives when t
 // fastest inside a panel, so a wave of CTAs covers a near-square region and shares its operand tiles in L2
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 i8_gemm_groups_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                      const __grid_constant__ OzPlan plan, int kblocks, int* __restrict__ C, long long plane_stride,
+                      const __grid_constant__ CUtensorMap mapC, const __grid_constant__ OzPlan plan, int kblocks,
                       int ldc) {
   extern __shared__ __align__(1024) unsigned char oz_smem[];
   __shared__ uint64_t fullA[OZ_NA], emptyA[OZ_NA], fullB[OZ_NB], emptyB[OZ_NB], tmem_full_bar;
@@ -127,27 +127,24 @@ i8_gemm_groups_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = tmem_base_s;
 
-  if (warp == 0) {
-    if (lane == 0) {   // ---- TMA producer: the group's load list, k-block after k-block
-      int a_seq = 0, b_seq = 0;
+  if (warp == 0 || warp == 3) {
+    if (lane == 0) {   // ---- TMA producers: warp 0 walks the A loads of the group's list, warp 3 the B loads
+      const bool is_b = warp == 3;
+      const CUtensorMap* map = is_b ? &mapB : &mapA;
+      uint64_t* full = is_b ? fullB : fullA;
+      uint64_t* empty = is_b ? emptyB : emptyA;
+      const int slots = is_b ? OZ_NB : OZ_NA, bytes = is_b ? OZ_B_BYTES : OZ_A_BYTES, row0 = is_b ? n0 : m0;
+      const unsigned base = is_b ? smemB : smemA;
+      int seq = 0;
       for (int kb = 0; kb < kblocks; ++kb)
         for (int l = 0; l < P.n_loads; ++l) {
-          const int slice = P.load_slice[l];
-          if (P.load_is_b[l]) {
-            const int slot = b_seq % OZ_NB;
-            if (b_seq >= OZ_NB) mbar_wait(&emptyB[slot], (unsigned)((b_seq / OZ_NB - 1) & 1));
-            mbar_expect_tx(&fullB[slot], (unsigned)OZ_B_BYTES);
-            tma_load_3d_raw(smemB + (unsigned)slot * OZ_B_BYTES, &mapB, kb * OZ_BK, n0, slice,
-                            (unsigned)__cvta_generic_to_shared(&fullB[slot]));
-            ++b_seq;
-          } else {
-            const int slot = a_seq % OZ_NA;
-            if (a_seq >= OZ_NA) mbar_wait(&emptyA[slot], (unsigned)((a_seq / OZ_NA - 1) & 1));
-            mbar_expect_tx(&fullA[slot], (unsigned)OZ_A_BYTES);
-            tma_load_3d_raw(smemA + (unsigned)slot * OZ_A_BYTES, &mapA, kb * OZ_BK, m0, slice,
-                            (unsigned)__cvta_generic_to_shared(&fullA[slot]));
-            ++a_seq;
-          }
+          if ((P.load_is_b[l] != 0) != is_b) continue;
+          const int slot = seq % slots;
+          if (seq >= slots) mbar_wait(&empty[slot], (unsigned)((seq / slots - 1) & 1));
+          mbar_expect_tx(&full[slot], (unsigned)bytes);
+          tma_load_3d_raw(base + (unsigned)slot * bytes, map, kb * OZ_BK, row0, P.load_slice[l],
+                          (unsigned)__cvta_generic_to_shared(&full[slot]));
+          ++seq;
         }
     }
   } else if (warp == 1) {
@@ -180,15 +177,20 @@ i8_gemm_groups_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       umma_commit(&tmem_full_bar);
     }
   } else if (warp >= 4) {
-    // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 = rows m0 + 32 (w - 4) + lane
+    // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 = rows m0 + 32 (w - 4) + lane, 32 columns at a
+    // time, lays the 32 x 32 block out in shared memory the way a 128-byte-swizzled TMA box expects it (lane =
+    // row: its eight 16-byte pieces land in eight different bank groups) and one lane hands it to the TMA
+    // engine, which writes whole 128-byte lines of the order plane.  The operand rings are free by now (every
+    // MMA has completed): two 4 KB buffers per warp out of the A ring.
     mbar_wait(&tmem_full_bar, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const int row = m0 + (warp - 4) * 32 + lane;
+    const int row0 = m0 + (warp - 4) * 32;
+    const unsigned stage0 = smemA + (unsigned)(warp - 4) * 8192u;
+    int it = 0;
     for (int a = 0; a < P.n_acc; ++a) {
-      int* crow = C + (size_t)P.order[a] * plane_stride + (size_t)row * ldc + n0;
       const uint32_t taddr = tmem + ((uint32_t)((warp - 4) * 32) << 16) + (uint32_t)(a * OZ_BN);
 #pragma unroll 1
-      for (int c = 0; c < OZ_BN; c += 32) {
+      for (int c = 0; c < OZ_BN && n0 + c < ldc; c += 32, ++it) {
         uint32_t r[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -198,15 +200,26 @@ i8_gemm_groups_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
               "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr + (uint32_t)c));
+        if (it >= 2) {   // the buffer written two blocks ago must have been read by its store
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+          __syncwarp();
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        if (n0 + c < ldc) {
+        const unsigned buf = stage0 + (unsigned)(it & 1) * 4096u, line = buf + (unsigned)lane * 128u;
 #pragma unroll
-          for (int v = 0; v < 8; ++v)
-            *reinterpret_cast<int4*>(crow + c + 4 * v) =
-                make_int4((int)r[4 * v], (int)r[4 * v + 1], (int)r[4 * v + 2], (int)r[4 * v + 3]);
+        for (int v = 0; v < 8; ++v)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(line + (unsigned)((v ^ (lane & 7)) << 4)),
+                       "r"(r[4 * v]), "r"(r[4 * v + 1]), "r"(r[4 * v + 2]), "r"(r[4 * v + 3]) : "memory");
+        fence_async_proxy();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];\n" ::"l"(&mapC),
+                       "r"(n0 + c), "r"(row0), "r"(P.order[a]), "r"(buf) : "memory");
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // before the buffers go away
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
