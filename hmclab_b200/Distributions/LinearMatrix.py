@@ -6,7 +6,8 @@ the CUDA engine are the ones the reference would multiply with:
 * dispatcher ``LinearMatrix``  -- hmclab/Distributions/LinearMatrix.py:15-135
 * dense G, scalar/vector variance  -- LinearMatrix.py:139-222
 * sparse G, scalar/vector variance -- LinearMatrix.py:309-440
-* dense G, dense data covariance (premultiplied form) -- LinearMatrix.py:226-305
+* dense G, dense data covariance (both forms) -- LinearMatrix.py:226-305
+* sparse G, sparse data covariance -- LinearMatrix.py:444-519
 
 Inherited quirks (they are part of the contract):
 
@@ -65,19 +66,13 @@ class LinearMatrix(_AbstractDistribution):
             d.size,
         ):
             simple = False
-        elif _sparse.issparse(data_covariance) and data_covariance.shape == (d.size, d.size):
-            raise NotImplementedError(
-                "LinearMatrix with a sparse data covariance (LinearMatrix.py:444-519: a sparse LU solve "
-                "per evaluation, in the covariance's dtype) is outside the batched B200 path."
-            )
         else:
+            # like the reference (LinearMatrix.py:74-95) the dispatcher only recognises an ndarray
+            # covariance; a scipy.sparse covariance goes to the inner class directly
             raise ValueError("Didn't understand the data covariance object.")
         if not simple and not dense:
-            raise NotImplementedError(
-                "The sparse-G / sparse-covariance LinearMatrix variant (LinearMatrix.py:444-519, a "
-                "sparse LU solve per evaluation) is outside the batched B200 path."
-            )
-        if not simple:
+            inner = _LinearMatrix_sparse_forward_sparse_covariance
+        elif not simple:
             inner = _LinearMatrix_dense_forward_dense_covariance
         elif dense:
             inner = _LinearMatrix_dense_forward_simple_covariance
@@ -207,3 +202,29 @@ class _LinearMatrix_sparse_forward_simple_covariance(_AbstractDistribution):
             del self.G, self.d, self.data_variance, self.data_sigma
         else:
             self.Gt = self.G.T.astype(dtype)
+
+
+class _LinearMatrix_sparse_forward_sparse_covariance(_AbstractDistribution):
+    """Sparse G with a sparse (N x N) data covariance (LinearMatrix.py:444-519): gradient
+    ``Gt @ solve(cov, G m - d)``, misfit ``0.5 (G m - d)^T solve(cov, G m - d)``.  The reference
+    factorises the covariance once (SuperLU) and solves per evaluation; the batched engine applies
+    the inverse as a dense operator instead (``_lowering.describe``), so only the constructor
+    arithmetic is mirrored here: ``G`` and ``d`` rounded to ``dtype`` (default float32), a
+    covariance that is not sparse yet converted to CSR in ``dtype``, a sparse one kept as given."""
+
+    def __init__(self, G, d, data_covariance, dtype=_numpy.single):
+        self.name = "sparse linear forward model, sparse data covariance"
+        self.dimensions = int(G.shape[1])
+        self.G = G.astype(dtype)
+        self.d = d.astype(dtype)
+        if not _sparse.issparse(data_covariance):
+            data_covariance = _sparse.csr_matrix(data_covariance, dtype=dtype)
+        self.data_covariance = data_covariance
+        self.Gt = self.G.T.tocsr()
+        self.dt = d.T.astype(dtype)
+
+    @staticmethod
+    def create_default(dimensions: int, dtype=_numpy.dtype("float64")):
+        return _LinearMatrix_sparse_forward_sparse_covariance(
+            _sparse.eye(dimensions, dtype=dtype).tocsr(), _numpy.ones((dimensions, 1)),
+            _sparse.eye(dimensions).tocsr(), dtype=dtype)

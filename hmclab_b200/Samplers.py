@@ -29,11 +29,6 @@ from hmclab_b200.MassMatrices import Unit as _Unit
 from hmclab_b200.MassMatrices import _AbstractMassMatrix
 from hmclab_b200.Samples import Samples as _Samples
 
-_SUPPORTED_DISTRIBUTIONS = ("Normal", "Laplace", "Uniform", "CompositeDistribution",
-                            "AdditiveDistribution", "BayesRule", "LinearMatrix",
-                            "_LinearMatrix_dense_forward_simple_covariance",
-                            "_LinearMatrix_sparse_forward_simple_covariance", "SourceLocation3D")
-
 
 def _is_distribution(obj) -> bool:
     """Objects of this package, or genuine hmclab distributions (read by attribute name)."""

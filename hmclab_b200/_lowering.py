@@ -125,6 +125,37 @@ def describe(dist) -> Dict[str, Any]:
                 var=_vec(dist.data_variance, N, "data_variance"),
                 sigma=_vec(dist.data_sigma, N, "data_sigma"),
             )
+    elif cls == "_LinearMatrix_sparse_forward_sparse_covariance":
+        # LinearMatrix.py:444-519: gradient Gt @ solve(cov, G m - d) with a sparse LU factorisation
+        # formed once by the constructor.  The batched engine has no sparse triangular solve; the
+        # factorisation is applied to the identity ONCE here (host set-up, like the reference's
+        # constructor) and the products run in the dense direct dense-covariance form:
+        # W = Gt invcov, misfit 0.5 |U (G m - d)|^2 with U^T U = invcov.  Everything is float64 on
+        # the stored values; a float32 covariance (what the public dispatcher produces) makes the
+        # reference solve in single precision, which this path does not imitate.
+        import scipy.sparse.linalg as spla
+        N = int(dist.G.shape[0])
+        if 8.0 * N * (N + 2 * n) > 6e9:
+            raise NotImplementedError(
+                f"sparse-covariance LinearMatrix with {N} data x {n} parameters: the dense lowering "
+                "(N x N inverse covariance, N x d operators) would need more than 6 GB")
+        cov = dist.data_covariance.tocsc()
+        invcov = spla.splu(cov.astype(np.float64)).solve(np.eye(N))
+        sym = 0.5 * (invcov + invcov.T)
+        if not np.allclose(invcov, sym, rtol=1e-9, atol=1e-12 * np.max(np.abs(invcov))):
+            raise ValueError("the data covariance of a LinearMatrix must be symmetric")
+        try:
+            U = np.ascontiguousarray(np.linalg.cholesky(sym).T)
+        except np.linalg.LinAlgError as err:
+            raise ValueError("the data covariance of a LinearMatrix must be positive definite") from err
+        G = np.ascontiguousarray(dist.G.toarray(), dtype=np.float64)
+        dvec = _vec(dist.d, N, "d")
+        node.update(kind="linear_dense", premult=False, N=N, G=G,
+                    Gt=np.ascontiguousarray(G.T @ invcov), d=dvec, var=np.ones(N), sigma=np.ones(N),
+                    chol_upper=U, misfit_G=np.ascontiguousarray(U @ G),
+                    misfit_d=np.ascontiguousarray(U @ dvec),
+                    cov_csc=(cov.data.copy(), cov.indices.copy(), cov.indptr.copy()),
+                    G_csr=_csr_arrays(dist.G), d_stored=np.asarray(dist.d).copy())
     elif cls == "_LinearMatrix_sparse_forward_simple_covariance":
         node.update(kind="linear_csr", premult=bool(dist.premultiplication))
         if dist.premultiplication:

@@ -85,6 +85,12 @@ def misfit(node, m: np.ndarray) -> float:
         else:
             # LinearMatrix.py:192-202 / 406-415
             G = _matrix(node, "G")
+            if node.get("cov_csc") is not None:
+                # sparse G, sparse data covariance (LinearMatrix.py:470-480): LU solve per call
+                Gs, solve, dcol = _sparse_cov_parts(node)
+                res = Gs @ m - dcol
+                inner = own + 0.5 * ((m.T @ Gs.T.tocsr() - dcol.T) @ solve(res)).item()
+                return inner + wrapper
             if node.get("chol_upper") is not None:
                 # dense data covariance, direct form (LinearMatrix.py:267-279)
                 res = node["chol_upper"] @ (G @ m - _col(node["d"]))
@@ -138,6 +144,10 @@ def gradient(node, m: np.ndarray) -> np.ndarray:
         # no bounds term in the gradient (LinearMatrix.py:118-120, 204-208, 417-426)
         if node["premult"]:
             return _matrix(node, "GtG") @ m - _col(node["Gtd0"])
+        if node.get("cov_csc") is not None:
+            # LinearMatrix.py:482-485
+            Gs, solve, dcol = _sparse_cov_parts(node)
+            return Gs.T.tocsr() @ solve(Gs @ m - dcol)
         G, Gt = _matrix(node, "G"), _matrix(node, "Gt")
         return Gt @ ((G @ m - _col(node["d"])) / _col(node["var"]))
     if kind == "srcloc2d":
@@ -193,6 +203,26 @@ def _split_events_2d(node, m):
 
 
 _MATRIX_CACHE = {}
+
+
+def _sparse_cov_parts(node):
+    """(G as CSR, solve(rhs) of the factorised covariance, d) of the sparse-covariance LinearMatrix:
+    ``scipy.sparse.linalg.factorized`` of the CSC covariance, right-hand side cast to the
+    covariance's dtype first (LinearMatrix.py:462-464, 476, 484)."""
+    key = (id(node), "sparse_cov")
+    if key not in _MATRIX_CACHE:
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+
+        N, d = node["N"], node["dims"]
+        indptr, indices, data = node["G_csr"]
+        Gs = sp.csr_matrix((data, indices, indptr), shape=(N, d))
+        cdata, cind, cptr = node["cov_csc"]
+        cov = sp.csc_matrix((cdata, cind, cptr), shape=(N, N))
+        lu = spla.factorized(cov)
+        dtype = cov.dtype
+        _MATRIX_CACHE[key] = (Gs, lambda rhs: lu(rhs.astype(dtype)), np.asarray(node["d_stored"]).reshape(N, 1))
+    return _MATRIX_CACHE[key]
 
 
 def _matrix(node, name):

@@ -46,6 +46,8 @@ SETTINGS = {
     "dense_fullcov_premult": _settings("3s", 2, 0.35, True, 4, 4),
     # dense (N x N) data covariance, direct form: float32 Gt @ invcov re-formed per call in the reference
     "dense_fullcov_direct": _settings("lf", 4, 0.3, True, 4, 4),
+    # sparse G with a sparse (banded) data covariance: an LU solve per evaluation in the reference
+    "sparse_fullcov_lf": _settings("lf", 4, 0.05, True, 4, 4),
     # Full (dense) mass matrix (MassMatrices.py:241-327), dense direct likelihood, 3-stage
     "dense_full_mass_3s": _settings("3s", 2, 0.9, True, 4, 4),
     # Full mass matrix on a bounded priors-only target: reflection flips momenta between sub-steps
@@ -99,6 +101,13 @@ def make_inputs(name: str) -> dict:
         A = rng.normal(size=(N, N)) / np.sqrt(N)
         inp.update(G=rng.normal(size=(N, dims)) / np.sqrt(N), d=rng.normal(size=(N, 1)),
                    cov=A @ A.T + 0.5 * np.eye(N), mass=rng.uniform(0.5, 2.0, size=(dims, 1)))
+    elif name == "sparse_fullcov_lf":
+        dims, N = 40, 60
+        mask = rng.uniform(size=(N, dims)) < 0.12
+        band = rng.uniform(-0.2, 0.2, size=N - 1)
+        inp.update(G=np.where(mask, rng.uniform(0.1, 1.4, size=(N, dims)), 0.0),
+                   d=rng.normal(size=(N, 1)) + 2.0,
+                   cov=np.diag(rng.uniform(0.6, 1.4, size=N)) + np.diag(band, 1) + np.diag(band, -1))
     elif name == "dense_full_mass_3s":
         dims = 30
         A = rng.normal(size=(dims, dims)) / np.sqrt(dims)
@@ -212,6 +221,15 @@ def build(name: str, inp: dict, ns):
     elif name == "dense_fullcov_direct":
         post = D.BayesRule([D.Normal(np.zeros((dims, 1)), 2.0),
                             D.LinearMatrix(cp("G"), cp("d"), cp("cov"))])      # N < dims: direct form
+    elif name == "sparse_fullcov_lf":
+        import importlib
+        import scipy.sparse as sp
+        mod = importlib.import_module(D.LinearMatrix.__module__)
+        # inner class directly: the float64 sparse covariance is kept as given (through the public
+        # dispatcher it would be converted to float32 and solved in single precision)
+        lik = mod._LinearMatrix_sparse_forward_sparse_covariance(
+            sp.csr_matrix(cp("G")), cp("d"), sp.csr_matrix(cp("cov")))
+        post = D.BayesRule([D.Normal(np.zeros((dims, 1)), 2.0), lik])
     elif name == "dense_full_mass_3s":
         post = D.BayesRule([D.Normal(np.zeros((dims, 1)), 1.0),
                             D.LinearMatrix(cp("G"), cp("d"), cp("var"), premultiplication=False)])

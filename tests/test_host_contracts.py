@@ -86,8 +86,20 @@ def test_linear_matrix_dtype_quirks_are_inherited():
     inv32 = np.linalg.inv((np.eye(7) * 2.0).astype(np.float32))
     assert np.array_equal(node["Gt"], (G.astype(np.float32).T @ inv32).astype(np.float64))   # float32 product
     assert np.allclose(node["misfit_G"].T @ node["misfit_G"], G32.T @ G32 / 2.0, rtol=1e-6)
-    with pytest.raises(NotImplementedError, match="sparse data covariance|sparse LU"):
+    with pytest.raises(ValueError, match="data covariance"):     # like the reference's dispatcher (LinearMatrix.py:74-95)
         D.LinearMatrix(sp.csr_matrix(G), d, sp.eye(7).tocsr())
+    # sparse G + (N x N) covariance: the sparse-covariance class; lowered to the dense direct form
+    cov = np.eye(7) * 2.0 + np.diag(np.full(6, 0.3), 1) + np.diag(np.full(6, 0.3), -1)
+    spcov = D.LinearMatrix(sp.csr_matrix(G), d, cov)
+    assert type(spcov.Distribution).__name__ == "_LinearMatrix_sparse_forward_sparse_covariance"
+    assert spcov.Distribution.data_covariance.dtype == np.float32        # the dispatcher path rounds it
+    from hmclab_b200.Distributions.LinearMatrix import _LinearMatrix_sparse_forward_sparse_covariance as SpCov
+    node = describe(SpCov(sp.csr_matrix(G), d, sp.csr_matrix(cov)))
+    assert node["kind"] == "linear_dense" and not node["premult"] and node["cov_csc"][0].dtype == np.float64
+    assert np.allclose(node["Gt"], G32.T @ np.linalg.inv(cov), rtol=1e-12, atol=1e-14)
+    assert np.allclose(node["chol_upper"].T @ node["chol_upper"], np.linalg.inv(cov), rtol=1e-12, atol=1e-14)
+    with pytest.raises(ValueError, match="symmetric"):
+        describe(SpCov(sp.csr_matrix(G), d, sp.csr_matrix(cov + np.diag(np.full(6, 0.1), 1))))
     sparse = D.LinearMatrix(sp.csr_matrix(G), d, 0.5, premultiplication=False)
     node = describe(sparse)
     assert node["kind"] == "linear_csr" and node["indices"].dtype == np.int32
