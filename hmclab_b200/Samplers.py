@@ -620,7 +620,10 @@ class ParallelSampleSMP:
     by posterior object, every group is one batch on its own engine, and an exchange round
     evaluates each scheduled chain's posterior at its partner's model on the device
     (``hmcb_misfit``), applies the reference's acceptance test per pair and swaps the models
-    (``_sample_grouped``).
+    (``_sample_grouped``).  Under ``torchrun`` (an initialised ``torch.distributed`` group, one process
+    per GPU) the chains are sharded over the ranks and the exchange round is the one collective of the
+    path (``parallel.exchange_round``: NCCL all-gather of models and partner misfits); every rank
+    writes the files of its own chains, and the result does not depend on the number of GPUs.
     """
 
     def __init__(self, seed=None):
@@ -770,28 +773,49 @@ class ParallelSampleSMP:
         dev_index = kwargs.get("device")
         dev = torch.device("cuda", torch.cuda.current_device() if dev_index is None else int(dev_index))
 
-        # groups of chains sharing a posterior object: one engine each
-        groups = []
+        # groups of chains sharing a posterior object: one engine each.  The chains are laid out group
+        # after group ("positions"); a rank owns a contiguous range of positions (all of them without a
+        # process group), so a group's local part is a contiguous slice of it and the device random
+        # streams, keyed by position, do not depend on the number of GPUs.
+        all_groups = []
         for i, post in enumerate(posteriors):
-            for g in groups:
+            for g in all_groups:
                 if g["posterior"] is post:
                     g["chains"].append(i)
                     break
             else:
-                groups.append({"posterior": post, "chains": [i]})
-        offset = 0
+                all_groups.append({"posterior": post, "chains": [i]})
+        order = [i for g in all_groups for i in g["chains"]]          # position -> chain
+        position = _numpy.empty(n, dtype=_numpy.int64)                # chain -> position
+        position[order] = _numpy.arange(n)
+        rank, world = _parallel.world()
+        lo, hi = _parallel.shard_range(n, world, rank)
+        if world > 1:
+            import hashlib
+            import torch.distributed as dist
+
+            mine = hashlib.sha256(repr(self.rng.bit_generator.state).encode()).hexdigest()
+            states = [None] * world
+            dist.all_gather_object(states, mine)
+            if any(st != mine for st in states):
+                raise ValueError("ParallelSampleSMP(seed=...) must be seeded identically on every rank: the "
+                                 "exchange schedule and the device random streams derive from it")
+        groups, start = [], 0
+        for g in all_groups:
+            a, b = max(lo, start), min(hi, start + len(g["chains"]))
+            if a < b:
+                groups.append({"posterior": g["posterior"], "chains": g["chains"][a - start: b - start],
+                               "offset": a})
+            start += len(g["chains"])
         for g in groups:
             ids = g["chains"]
             g["engine"] = Engine(flatten(describe(g["posterior"])), describe_mass(mass), len(ids),
                                  integrator=integrator, amount_of_steps=steps, device=dev.index)
-            g["ids"] = torch.as_tensor(ids, device=dev)
             g["q"] = torch.as_tensor(q0[ids], dtype=torch.float64).to(dev).contiguous()
             g["x"] = g["engine"].misfit(g["q"])
             g["accepted"] = torch.zeros(len(ids), dtype=torch.int32, device=dev)
-            g["offset"] = offset
-            offset += len(ids)
             assert bool(torch.isfinite(g["x"]).all()), "The initial model has a non-finite misfit."
-        where = {i: (gi, l) for gi, g in enumerate(groups) for l, i in enumerate(g["chains"])}
+        local_chains = [i for g in groups for i in g["chains"]]       # = order[lo:hi]
 
         self.samplers = list(samplers)
         self.exchange_schedule = None
@@ -802,8 +826,17 @@ class ParallelSampleSMP:
                 _numpy.vstack([self.rng.choice(n, pairs * 2, replace=False) for _ in range(rounds)])
                 if pairs and rounds else _numpy.zeros((0, 0), dtype=int))
         device_seed = int(self.rng.integers(0, 2**63 - 1))
-        rows_host = [[] for _ in range(n)]       # stored rows per chain
+        rows_host = {i: [] for i in local_chains}       # stored rows per chain
         self.exchanges_accepted = 0
+
+        def misfit_at(models):       # chain i's own posterior at the model in row i, on the device
+            out, r = [], 0
+            for g in groups:
+                C = len(g["chains"])
+                out.append(g["engine"].misfit(models[r: r + C].contiguous()))
+                r += C
+            return torch.cat(out) if out else models.new_zeros(0)
+
         done = 0
         while done < proposals:
             if exchange:   # blocks end right after the proposals k with k % interval == 0
@@ -834,35 +867,32 @@ class ParallelSampleSMP:
                 bufs.append(buf)
             k = done + B - 1
             if exchange and k % exchange_interval == 0 and k // exchange_interval < self.exchange_schedule.shape[0]:
-                row = self.exchange_schedule[k // exchange_interval]
-                partner = _numpy.arange(n)
-                for a, b in row.reshape(-1, 2):
-                    partner[a], partner[b] = b, a
-                Q = torch.empty(n, d, dtype=torch.float64, device=dev)
-                X = torch.empty(n, dtype=torch.float64, device=dev)
-                for g in groups:
-                    Q[g["ids"]] = g["q"]
-                    X[g["ids"]] = g["x"]
-                Xex = torch.empty(n, dtype=torch.float64, device=dev)
-                for g in groups:     # chi_i(m_partner) for every chain of the group, on the device
-                    theirs = Q[torch.as_tensor(partner[g["chains"]], device=dev)].contiguous()
-                    Xex[g["ids"]] = g["engine"].misfit(theirs)
-                improvement = (X - Xex).cpu().numpy()
-                xex = Xex.cpu().numpy()
-                for a, b in row.reshape(-1, 2):          # a: even position, b: odd position = master
-                    u = samplers[b].rng.uniform(0, 1) if host_rng else self.rng.uniform(0, 1)
-                    with _numpy.errstate(all="ignore"):
-                        accept = _numpy.exp(improvement[a] + improvement[b]) > u
-                    if not accept:
-                        continue
-                    self.exchanges_accepted += 1
-                    (ga, la), (gb, lb) = where[a], where[b]
-                    ma, mb = groups[ga]["q"][la].clone(), groups[gb]["q"][lb].clone()
-                    groups[ga]["q"][la], groups[gb]["q"][lb] = mb, ma
-                    groups[ga]["x"][la], groups[gb]["x"][lb] = float(xex[a]), float(xex[b])
-                    if k % thin == 0:      # the stored row: exchanged model, misfit from before the exchange
-                        bufs[ga][-1, la, :d] = mb
-                        bufs[gb][-1, lb, :d] = ma
+                row = self.exchange_schedule[k // exchange_interval].reshape(-1, 2)
+                # a: even entry of the schedule row, b: odd entry = the pair's master, which draws the
+                # uniform -- from its sampler's generator with host_rng (the owner rank), else from the
+                # front end's generator (identical on every rank, drawn for all pairs up front)
+                shared_u = None if host_rng else self.rng.uniform(0, 1, size=len(row))
+                if host_rng:
+                    draw = lambda p, a, b: samplers[order[b]].rng.uniform(0, 1)
+                else:
+                    draw = lambda p, a, b: shared_u[p]
+                q_loc = torch.cat([g["q"] for g in groups]) if groups else torch.zeros(0, d, dtype=torch.float64, device=dev)
+                x_loc = torch.cat([g["x"] for g in groups]) if groups else torch.zeros(0, dtype=torch.float64, device=dev)
+                accepted, q_before = _parallel.exchange_round(position[row], n, q_loc, x_loc, misfit_at, draw)
+                self.exchanges_accepted += int(accepted.sum())
+                r = 0
+                for g, buf in zip(groups, bufs):
+                    C = len(g["chains"])
+                    g["q"].copy_(q_loc[r: r + C])
+                    g["x"].copy_(x_loc[r: r + C])
+                    r += C
+                if k % thin == 0:      # the stored row: exchanged model, misfit from before the exchange
+                    where = {i: (gi, l) for gi, g in enumerate(groups) for l, i in enumerate(g["chains"])}
+                    for (a, b), ok in zip(row, accepted):
+                        for mine, other in ((a, b), (b, a)):
+                            if ok and int(mine) in where:
+                                gi, l = where[int(mine)]
+                                bufs[gi][-1, l, :d] = q_before[position[other]]
             for g, buf in zip(groups, bufs):
                 if buf is not None:
                     host = buf.cpu().numpy()
@@ -880,7 +910,8 @@ class ParallelSampleSMP:
                 smp.current_model = qf[l][:, None].copy()
                 smp.current_x = float(xf[l])
             g["engine"].close()
-        for i, name in enumerate(filenames):
+        for i in local_chains:          # every rank writes the files of the chains it owns
+            name = filenames[i]
             rows = _numpy.concatenate(rows_host[i]) if rows_host[i] else _numpy.zeros((0, d + 1))
             out = _Samples(name, mode="w", overwrite=True)
             out.allocate(1, rows.shape[0], d)

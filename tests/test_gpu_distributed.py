@@ -54,3 +54,61 @@ def test_two_gpu_run_equals_single_gpu_run(tmp_path):
     acc = np.load(tmp_path / "acc0.npy")
     assert np.array_equal(acc, np.load(tmp_path / "acc1.npy"))
     assert np.array_equal(acc, single.accepted_proposals_per_chain)
+
+
+EXCHANGE_WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+sys.path.insert(0, os.path.join({root!r}, "tests"))
+from test_gpu_distributed import tempering_run
+local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+smp = tempering_run(os.path.join({out!r}, "dist"))
+np.save(os.path.join({out!r}, f"exacc{{dist.get_rank()}}.npy"), np.array([smp.exchanges_accepted]))
+dist.destroy_process_group()
+'''
+
+
+def tempering_run(prefix):
+    """Seven chains on a ladder of four posteriors (cold ... hot; the posteriors repeat, so the engines
+    hold groups of one or two chains), replica exchange every third proposal, device random streams."""
+    from hmclab_b200 import Distributions as D
+    from hmclab_b200.Samplers import HMC, ParallelSampleSMP
+
+    rng = np.random.default_rng(5)
+    d, n = 12, 7
+    mean, var = rng.normal(size=(d, 1)), rng.uniform(0.5, 1.5, size=(d, 1))
+    ladder = [D.Normal(mean + 0.1 * t, var * (1.0 + 0.7 * t)) for t in range(4)]
+    posts = [ladder[i % 4] for i in range(n)]
+    os.makedirs(prefix, exist_ok=True)
+    names = [os.path.join(prefix, f"chain{i}.npy") for i in range(n)]
+    smp = ParallelSampleSMP(seed=21)
+    smp.sample([HMC(seed=i) for i in range(n)], names, posts, overwrite_existing_files=True, proposals=30,
+               exchange=True, exchange_interval=3, initial_model=[q[:, None] for q in rng.normal(size=(n, d))],
+               kwargs=dict(stepsize=0.25, amount_of_steps=5, online_thinning=1, disable_progressbar=True))
+    return smp
+
+
+def test_replica_exchange_across_two_gpus_equals_single_gpu_run(tmp_path):
+    """ParallelSampleSMP under torchrun: chains sharded over two ranks, exchange rounds over NCCL
+    (parallel.exchange_round); every chain's file equals the one a single GPU writes, bit for bit."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "exchange_worker.py"
+    script.write_text(EXCHANGE_WORKER.format(root=ROOT, out=str(tmp_path)))
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                           "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                           "--master-port", "29543", str(script)], cwd=ROOT)
+    single = tempering_run(str(tmp_path / "single"))
+    assert single.exchanges_accepted > 0
+    assert int(np.load(tmp_path / "exacc0.npy")[0]) == single.exchanges_accepted
+    assert int(np.load(tmp_path / "exacc1.npy")[0]) == single.exchanges_accepted
+    for i in range(7):
+        one = np.load(tmp_path / "single" / f"chain{i}.npy")
+        two = np.load(tmp_path / "dist" / f"chain{i}.npy")
+        assert one.shape == (30, 13) and np.array_equal(one, two), i
