@@ -149,15 +149,25 @@ cudaError_t launch_oz_combine_residual(const int* C, long long plane_stride, int
                                        unsigned long long* maxbits_out, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(maxbits_out, 0, (size_t)ld * sizeof(unsigned long long), s);
   if (e != cudaSuccess) return e;
-  oz_combine_kernel<ResidualEpi, true, 16><<<dim3(ld / 128, (rows + 15) / 16), 128, 0, s>>>(
-      C, plane_stride, rows, ld, orders, ea, maxbits_in, epi, maxbits_out);
+  const dim3 grid(ld / 128, (rows + 15) / 16);
+  if (orders == 6)
+    oz_combine_kernel<ResidualEpi, true, 16, 6><<<grid, 128, 0, s>>>(C, plane_stride, rows, ld, orders, ea, maxbits_in,
+                                                                      epi, maxbits_out);
+  else
+    oz_combine_kernel<ResidualEpi, true, 16, 0><<<grid, 128, 0, s>>>(C, plane_stride, rows, ld, orders, ea, maxbits_in,
+                                                                      epi, maxbits_out);
   return cudaGetLastError();
 }
 
 cudaError_t launch_oz_combine_update(const int* C, long long plane_stride, int rows, int ld, int orders, const int* ea,
                                      const unsigned long long* maxbits_in, const UpdateEpi& epi, cudaStream_t s) {
-  oz_combine_kernel<UpdateEpi, false, 16><<<dim3(ld / 128, (rows + 15) / 16), 128, 0, s>>>(
-      C, plane_stride, rows, ld, orders, ea, maxbits_in, epi, nullptr);
+  const dim3 grid(ld / 128, (rows + 15) / 16);
+  if (orders == 6)
+    oz_combine_kernel<UpdateEpi, false, 16, 6><<<grid, 128, 0, s>>>(C, plane_stride, rows, ld, orders, ea, maxbits_in,
+                                                                     epi, nullptr);
+  else
+    oz_combine_kernel<UpdateEpi, false, 16, 0><<<grid, 128, 0, s>>>(C, plane_stride, rows, ld, orders, ea, maxbits_in,
+                                                                     epi, nullptr);
   return cudaGetLastError();
 }
 
@@ -165,8 +175,13 @@ cudaError_t launch_oz_combine_update(const int* C, long long plane_stride, int r
 // holds [rows / 128 x ld])
 cudaError_t launch_oz_combine_misfit(const int* C, long long plane_stride, int rows, int ld, int orders, const int* ea,
                                      const unsigned long long* maxbits_in, const MisfitEpi& epi, cudaStream_t s) {
-  oz_combine_kernel<MisfitEpi, false, 128><<<dim3(ld / 128, (rows + 127) / 128), 128, 0, s>>>(
-      C, plane_stride, rows, ld, orders, ea, maxbits_in, epi, nullptr);
+  const dim3 grid(ld / 128, (rows + 127) / 128);
+  if (orders == 6)
+    oz_combine_kernel<MisfitEpi, false, 128, 6><<<grid, 128, 0, s>>>(C, plane_stride, rows, ld, orders, ea, maxbits_in,
+                                                                      epi, nullptr);
+  else
+    oz_combine_kernel<MisfitEpi, false, 128, 0><<<grid, 128, 0, s>>>(C, plane_stride, rows, ld, orders, ea, maxbits_in,
+                                                                      epi, nullptr);
   return cudaGetLastError();
 }
 

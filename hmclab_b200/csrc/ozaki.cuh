@@ -275,8 +275,17 @@ oz_colmax_kernel(const double* __restrict__ X, int rows, int ld, unsigned long l
   if (m) atomicMax(maxbits + c, m);
 }
 
+// all balanced digits of X at once: with u_t = d_t + 128 in [0, 255], sum_t u_t 256^t = X + 128 sum_t 256^t, so the
+// bytes of X + 0x80...80 are the u_t and flipping their top bits gives the two's-complement d_t (byte 0 = the
+// least significant digit = digit S-1).  Same digits as oz_digits: the balanced representation is unique.
+__device__ __forceinline__ unsigned long long oz_digit_bytes(long long X, int S) {
+  const unsigned long long bias = 0x8080808080808080ull >> (8 * (8 - S));
+  return ((unsigned long long)X + bias) ^ bias;
+}
+
 // X [K x ld] (chains contiguous) -> SB int8 digit planes, chain-major [t][ld][K] (K contiguous): the B
-// operand of the tensor-core product.  Block = 128 k x 32 chains, transposed through shared memory.
+// operand of the tensor-core product.  Block = 128 k x 32 chains, transposed through shared memory: a thread
+// slices four consecutive k of its chain and packs each plane's four digits into one 32-bit word.
 __global__ void __launch_bounds__(256)
 oz_slice_chains_kernel(const double* __restrict__ X, int K, int ld, int SB, const unsigned long long* __restrict__ maxbits,
                        signed char* __restrict__ out) {
@@ -285,15 +294,34 @@ oz_slice_chains_kernel(const double* __restrict__ X, int K, int ld, int SB, cons
   const int tc = threadIdx.x & 31, tr = threadIdx.x >> 5;
   const int eb = oz_exponent(maxbits[c0 + tc]);
   const double up = oz_pow2(OZ_BITS * SB);
-#pragma unroll 4
-  for (int r = tr; r < 128; r += 8) {
-    long long Xi = 0;
-    if (k0 + r < K && eb != INT_MIN) Xi = __double2ll_rn(oz_scale_down(X[(size_t)(k0 + r) * ld + c0 + tc], eb) * up);
-    signed char digit[OZ_MAX_SLICES];
-    oz_digits(Xi, SB, digit);
+  double x[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (tr + 8 * j) * 4 + i;
+      x[j][i] = (k0 + r < K) ? __ldcs(X + (size_t)(k0 + r) * ld + c0 + tc) : 0.0;
+    }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    unsigned lo[4], hi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long Xi = eb != INT_MIN ? __double2ll_rn(oz_scale_down(x[j][i], eb) * up) : 0ll;
+      const unsigned long long y = oz_digit_bytes(Xi, SB);
+      lo[i] = (unsigned)y;
+      hi[i] = (unsigned)(y >> 32);
+    }
+    const int r = (tr + 8 * j) * 4;
 #pragma unroll
     for (int t = 0; t < OZ_MAX_SLICES; ++t)
-      if (t < SB) sl[t][tc][r] = digit[t];
+      if (t < SB) {
+        const int byte = SB - 1 - t;                       // digit t lives in byte S-1-t
+        const unsigned* w = byte < 4 ? lo : hi;
+        const unsigned sel = 0x4040u + (unsigned)(byte & 3) * 0x1111u;   // result bytes 0, 1 <- byte b of x, byte b of y
+        const unsigned p01 = __byte_perm(w[0], w[1], sel), p23 = __byte_perm(w[2], w[3], sel);
+        *reinterpret_cast<unsigned*>(&sl[t][tc][r]) = __byte_perm(p01, p23, 0x5410u);
+      }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -307,11 +335,15 @@ oz_slice_chains_kernel(const double* __restrict__ X, int K, int ld, int SB, cons
 // Y[i][c] = 2^(ea[i] + eb[c]) sum_o 256^-(o + 2) C_o[i][c]  -> epilogue functor (SpMM interface: tile_begin /
 // row / chunk_end; a block = 128 chains x ROWS rows); optionally the per-chain max |R| of what a ResidualEpi
 // stored (the scale of the next slicing pass)
-template <class Epi, bool TRACK_MAX, int ROWS>
+template <class Epi, bool TRACK_MAX, int ROWS, int ORD>
 __global__ void __launch_bounds__(128)
 oz_combine_kernel(const int* __restrict__ C, long long plane_stride, int rows, int ld, int orders,
                   const int* __restrict__ ea, const unsigned long long* __restrict__ maxbits_in, Epi epi,
                   unsigned long long* __restrict__ maxbits_out) {
+  // ORD > 0: the number of order planes at compile time (all loads of two rows are issued before the
+  // first use: the kernel streams 4 ORD bytes per element and lives on loads in flight); ORD = 0: `orders`
+  constexpr int NV = ORD > 0 ? ORD : OZ_MAX_ORDERS;
+  const int n_ord = ORD > 0 ? ORD : orders;
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= ld) return;
   const int eb = oz_exponent(maxbits_in[c]);
@@ -319,10 +351,11 @@ oz_combine_kernel(const int* __restrict__ C, long long plane_stride, int rows, i
   const int r1 = min(rows, ((int)blockIdx.y + 1) * ROWS);
   Epi fn = epi;
   fn.tile_begin(blockIdx.y, c);
-  for (int i = blockIdx.y * ROWS; i < r1; ++i) {
-    const int* p = C + (size_t)i * ld + c;
+  auto finish = [&](int i, const int (&v)[NV]) {
     double acc = 0.0;
-    for (int o = orders - 1; o >= 0; --o) acc = fma(acc, 0.00390625, (double)p[(size_t)o * plane_stride]);
+#pragma unroll
+    for (int o = NV - 1; o >= 0; --o)
+      if (o < n_ord) acc = fma(acc, 0.00390625, (double)v[o]);
     double y;
     if (eb == INT_MIN) y = CUDART_NAN;
     else {
@@ -340,6 +373,18 @@ oz_combine_kernel(const int* __restrict__ C, long long plane_stride, int rows, i
     } else {
       fn.row(i, c, y);
     }
+  };
+  for (int i = blockIdx.y * ROWS; i < r1; i += 2) {
+    const int* p = C + (size_t)i * ld + c;
+    const bool two = i + 1 < r1;
+    int v0[NV], v1[NV];
+#pragma unroll
+    for (int o = 0; o < NV; ++o) {
+      v0[o] = o < n_ord ? __ldcs(p + (size_t)o * plane_stride) : 0;
+      v1[o] = (o < n_ord && two) ? __ldcs(p + (size_t)o * plane_stride + ld) : 0;
+    }
+    finish(i, v0);
+    if (two) finish(i + 1, v1);
   }
   fn.chunk_end(blockIdx.y, c);
   if constexpr (TRACK_MAX) {
