@@ -202,15 +202,18 @@ def _split_events_2d(node, m):
     return x, z, T, v
 
 
-_MATRIX_CACHE = {}
+def _cache_of(node):
+    """Per-node cache of rebuilt matrices, stored IN the node (a global dict keyed by id(node) would hand
+    a recycled id the matrices of a tree that no longer exists)."""
+    return node.setdefault("_oracle_cache", {})
 
 
 def _sparse_cov_parts(node):
     """(G as CSR, solve(rhs) of the factorised covariance, d) of the sparse-covariance LinearMatrix:
     ``scipy.sparse.linalg.factorized`` of the CSC covariance, right-hand side cast to the
     covariance's dtype first (LinearMatrix.py:462-464, 476, 484)."""
-    key = (id(node), "sparse_cov")
-    if key not in _MATRIX_CACHE:
+    cache, key = _cache_of(node), "sparse_cov"
+    if key not in cache:
         import scipy.sparse as sp
         import scipy.sparse.linalg as spla
 
@@ -221,15 +224,15 @@ def _sparse_cov_parts(node):
         cov = sp.csc_matrix((cdata, cind, cptr), shape=(N, N))
         lu = spla.factorized(cov)
         dtype = cov.dtype
-        _MATRIX_CACHE[key] = (Gs, lambda rhs: lu(rhs.astype(dtype)), np.asarray(node["d_stored"]).reshape(N, 1))
-    return _MATRIX_CACHE[key]
+        cache[key] = (Gs, lambda rhs: lu(rhs.astype(dtype)), np.asarray(node["d_stored"]).reshape(N, 1))
+    return cache[key]
 
 
 def _matrix(node, name):
     """Dense ndarray or scipy CSR/CSC rebuilt from the plain arrays of the tree."""
-    key = (id(node), name)
-    if key in _MATRIX_CACHE:
-        return _MATRIX_CACHE[key]
+    cache, key = _cache_of(node), name
+    if key in cache:
+        return cache[key]
     if node["kind"] == "linear_dense":
         if name == "Gt":
             out = node["Gt"] if node.get("Gt") is not None else node["G"].T
@@ -248,7 +251,7 @@ def _matrix(node, name):
             out = sp.csr_matrix(
                 (node["t_data"], node["t_indices"], node["t_indptr"]), shape=(d, N)
             ).tocsc()
-    _MATRIX_CACHE[key] = out
+    cache[key] = out
     return out
 
 
