@@ -56,15 +56,21 @@ class _Evaluator:
 
 
 def _fingerprint(dist, depth=0):
-    """Cheap identity of everything `update_bounds`, `normalize`, `collapse_bounds` or
-    `add_distribution` can change on a distribution or any of its children (those methods
-    rebind the attributes, so object identities are enough; big operators are not hashed)."""
-    own = (id(dist), id(getattr(dist, "lower_bounds", None)), id(getattr(dist, "upper_bounds", None)),
-           repr(getattr(dist, "normalization_constant", None)))
+    """Everything `update_bounds`, `normalize`, `collapse_bounds` or `add_distribution` can change on a
+    distribution or any of its children: those methods rebind the attributes, so the OBJECTS are the
+    identity (big operators are not hashed).  The cache keeps these references, so a rebound array cannot
+    be mistaken for its predecessor through a recycled ``id``."""
+    own = [dist, getattr(dist, "lower_bounds", None), getattr(dist, "upper_bounds", None),
+           repr(getattr(dist, "normalization_constant", None))]
     children = getattr(dist, "separate_distributions", None) or ()
-    if depth > 16:
-        return own
-    return own + tuple(_fingerprint(c, depth + 1) for c in children)
+    if depth <= 16:
+        for c in children:
+            own.extend(_fingerprint(c, depth + 1))
+    return own
+
+
+def _same(a, b) -> bool:
+    return len(a) == len(b) and all(x is y or (isinstance(x, str) and x == y) for x, y in zip(a, b))
 
 
 def evaluator_for(dist) -> _Evaluator:
@@ -72,7 +78,7 @@ def evaluator_for(dist) -> _Evaluator:
 
     key = _fingerprint(dist)
     cached = dist.__dict__.get("_hmcb_evaluator")
-    if cached is None or cached[0] != key:
+    if cached is None or not _same(cached[0], key):
         plan = flatten(describe(dist))
         cached = (key, _Evaluator(plan, {"kind": "unit", "dims": plan["dims"]}))
         dist.__dict__["_hmcb_evaluator"] = cached

@@ -91,7 +91,7 @@ struct hmcb_engine {
   signed char *oz_AG = nullptr, *oz_AGt = nullptr, *oz_B = nullptr;   // int8 slices of G, G^T, the chain batch
   int *oz_eaG = nullptr, *oz_eaGt = nullptr, *oz_C = nullptr;         // row exponents, int32 order planes
   unsigned long long *oz_maxQ = nullptr, *oz_maxR = nullptr;          // per-chain max |.| (bit patterns)
-  CUtensorMap oz_mapAG, oz_mapAGt, oz_mapBq, oz_mapBr, oz_mapCq, oz_mapCr;
+  CUtensorMap oz_mapAG, oz_mapAGt, oz_mapBq, oz_mapBr, oz_mapBqh, oz_mapBrh, oz_mapCq, oz_mapCr;
   std::vector<double> h_vec, h_var, h_sigma;  // Gtd0 or d ; var ; sigma
   double dtd = 0.0;
   HostCsr csr, csr_t;
@@ -839,6 +839,8 @@ int oz_setup(hmcb_engine* e) {
   HMCB_CUDA(ozaki_slice_map(e->oz_AGt, e->npad, e->dpad, e->oz_saGt, 128, &e->oz_mapAGt));
   HMCB_CUDA(ozaki_slice_map(e->oz_B, e->dpad, e->ld, e->oz_sb, 256, &e->oz_mapBq));
   HMCB_CUDA(ozaki_slice_map(e->oz_B, e->npad, e->ld, e->oz_sb, 256, &e->oz_mapBr));
+  HMCB_CUDA(ozaki_slice_map(e->oz_B, e->dpad, e->ld, e->oz_sb, 128, &e->oz_mapBqh));   // half tiles: CTA pairs
+  HMCB_CUDA(ozaki_slice_map(e->oz_B, e->npad, e->ld, e->oz_sb, 128, &e->oz_mapBrh));
   HMCB_CUDA(ozaki_plane_map(e->oz_C, e->ld, e->npad, e->oz_orders, (long long)e->npad * e->ld, &e->oz_mapCq));
   HMCB_CUDA(ozaki_plane_map(e->oz_C, e->ld, e->dpad, e->oz_orders, (long long)e->dpad * e->ld, &e->oz_mapCr));
   e->oz = true;
@@ -850,7 +852,7 @@ int oz_setup(hmcb_engine* e) {
 int oz_forward_product(hmcb_engine* e, const double* q_in, cudaStream_t s) {
   HMCB_CUDA(launch_oz_colmax(q_in, e->dpad, e->ld, e->oz_maxQ, s));
   HMCB_CUDA(launch_oz_slice_chains(q_in, e->dpad, e->ld, e->oz_sb, e->oz_maxQ, e->oz_B, s));
-  HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAG, e->oz_mapBq, e->oz_mapCq, e->npad, e->ld, e->dpad, e->oz_saG, e->oz_sb,
+  HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAG, e->oz_mapBq, e->oz_mapBqh, e->oz_mapCq, e->npad, e->ld, e->dpad, e->oz_saG, e->oz_sb,
                                   e->oz_orders, e->ld, s));
   e->launches += 3;
   return 0;
@@ -907,7 +909,7 @@ int staged_gradient_pass(hmcb_engine* e, const double* q_in, UpdateEpi epi, cuda
         HMCB_CUDA(launch_oz_combine_residual(e->oz_C, plane_q, e->npad, e->ld, e->oz_orders, e->oz_eaG, e->oz_maxQ, r,
                                              e->oz_maxR, s));
         HMCB_CUDA(launch_oz_slice_chains(e->R, e->npad, e->ld, e->oz_sb, e->oz_maxR, e->oz_B, s));
-        HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAGt, e->oz_mapBr, e->oz_mapCr, e->dpad, e->ld, e->npad, e->oz_saGt,
+        HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAGt, e->oz_mapBr, e->oz_mapBrh, e->oz_mapCr, e->dpad, e->ld, e->npad, e->oz_saGt,
                                         e->oz_sb, e->oz_orders, e->ld, s));
         HMCB_CUDA(launch_oz_combine_update(e->oz_C, plane_r, e->dpad, e->ld, e->oz_orders, e->oz_eaGt, e->oz_maxR, epi,
                                            s));

@@ -124,8 +124,8 @@ cudaError_t launch_oz_combine_misfit(const int* C, long long plane_stride, int r
                                      const unsigned long long* maxbits_in, const MisfitEpi& epi, cudaStream_t s);
 cudaError_t ozaki_plane_map(const int* base, long long ldc, long long M, int orders, long long plane_stride,
                             CUtensorMap* out);
-cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapC,
-                                  long long M, long long N, long long K, int SA, int SB, int orders, int ldc,
-                                  cudaStream_t s);
+cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBh,
+                                  const CUtensorMap& mapC, long long M, long long N, long long K, int SA, int SB,
+                                  int orders, int ldc, cudaStream_t s);
 
 }  // namespace hmcb

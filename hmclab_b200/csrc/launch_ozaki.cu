@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "launch.cuh"
@@ -55,7 +56,17 @@ cudaError_t ozaki_plane_map(const int* base, long long ldc, long long M, int ord
 }
 
 cudaError_t ozaki_init() {
-  return cudaFuncSetAttribute(i8_gemm_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(i8_gemm_groups_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)OZ_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(i8_gemm_groups_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)OZ_SMEM_BYTES);
+}
+
+// CTA pairs (tcgen05 cta_group::2) unless HMCB_OZAKI_PAIR=0
+bool ozaki_pair_mode() {
+  const char* v = std::getenv("HMCB_OZAKI_PAIR");
+  return v ? std::atoi(v) != 0 : true;
 }
 
 // The dataflow program of the order group {orders[0], orders[1]}: walking the B digits t upward, B_t meets
@@ -117,17 +128,34 @@ bool oz_build_plan(int SA, int SB, int orders, long long M, long long N, OzPlan*
 }
 
 // C[o] (o < orders) = sum_{s+t=o} A_s B_t^T;  M % 128 == 0, K % 128 == 0, ldc = padded N (% 128 == 0);
+// mapB: box of 256 rows (one CTA per tile), mapBh: box of 128 rows (CTA pairs: each CTA loads half a B tile);
 // mapC = ozaki_plane_map of the order planes
-cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapC,
-                                  long long M, long long N, long long K, int SA, int SB, int orders, int ldc,
-                                  cudaStream_t s) {
+cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBh,
+                                  const CUtensorMap& mapC, long long M, long long N, long long K, int SA, int SB,
+                                  int orders, int ldc, cudaStream_t s) {
   if (M % OZ_BM || K % OZ_BK || N % 128) return cudaErrorInvalidValue;
   OzPlan plan;
   if (!oz_build_plan(SA, SB, orders, M, N, &plan)) return cudaErrorInvalidValue;
-  const long long ctas = (long long)plan.n_groups * plan.tiles_m * plan.tiles_n;
+  const bool pair = ozaki_pair_mode();
+  const long long rows_m = pair ? (plan.tiles_m + 1) / 2 : plan.tiles_m;
+  const long long ctas = (long long)plan.n_groups * rows_m * plan.tiles_n * (pair ? 2 : 1);
   if (ctas <= 0 || ctas > 0x7fffffffll) return cudaErrorInvalidValue;
-  i8_gemm_groups_kernel<<<(unsigned)ctas, OZ_THREADS, OZ_SMEM_BYTES, s>>>(mapA, mapB, mapC, plan, (int)(K / OZ_BK), ldc);
-  return cudaGetLastError();
+  if (!pair) {
+    i8_gemm_groups_kernel<false><<<(unsigned)ctas, OZ_THREADS, OZ_SMEM_BYTES, s>>>(mapA, mapB, mapC, plan,
+                                                                                  (int)(K / OZ_BK), ldc, (int)M);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(OZ_THREADS);
+  cfg.dynamicSmemBytes = OZ_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, i8_gemm_groups_kernel<true>, mapA, mapBh, mapC, plan, (int)(K / OZ_BK), ldc, (int)M);
 }
 
 cudaError_t launch_oz_colmax(const double* X, int rows, int ld, unsigned long long* maxbits, cudaStream_t s) {
@@ -227,12 +255,13 @@ extern "C" int hmcb_debug_i8_gemm(int device, int64_t M, int64_t N, int64_t K, i
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || SA < 1 || SB < 1) return -1;
   if (cudaSetDevice(device) != cudaSuccess) return -1;
   if (ozaki_init() != cudaSuccess) return -2;
-  CUtensorMap mapA, mapB, mapC;
+  CUtensorMap mapA, mapB, mapBh, mapC;
   if (ozaki_slice_map(A, K, M, SA, OZ_BM, &mapA) != cudaSuccess) return -3;
   if (ozaki_slice_map(B, K, N, SB, OZ_BN, &mapB) != cudaSuccess) return -3;
+  if (ozaki_slice_map(B, K, N, SB, OZ_BN / 2, &mapBh) != cudaSuccess) return -3;
   if (ozaki_plane_map(C, N, M, orders, M * N, &mapC) != cudaSuccess) return -3;
-  if (launch_i8_gemm_orders(mapA, mapB, mapC, M, N, K, SA, SB, orders, (int)N, static_cast<cudaStream_t>(stream)) !=
-      cudaSuccess)
+  if (launch_i8_gemm_orders(mapA, mapB, mapBh, mapC, M, N, K, SA, SB, orders, (int)N,
+                            static_cast<cudaStream_t>(stream)) != cudaSuccess)
     return -4;
   return 0;
 }

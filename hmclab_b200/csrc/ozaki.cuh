@@ -85,45 +85,76 @@ __device__ __forceinline__ void tma_load_3d_raw(unsigned dst, const CUtensorMap*
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::
           "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
+template <bool PAIR>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {   // arrives when the MMAs issued so far have completed
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::
-                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+  if constexpr (PAIR)   // ... on the barrier at this address in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::
+                     "r"((unsigned)__cvta_generic_to_shared(bar)), "h"((unsigned short)3) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::
+                     "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
 // C[o][m][n] = sum over slice pairs (s, t = o - s) of A_s[m][:] . B_t[n][:]   (int8 x int8 -> int32, exact)
-//   mapA: {K, M, SA} int8, box {128, 128, 1};  mapB: {K, N, SB} int8, box {128, 256, 1}; 128-byte swizzle
+//   mapA: {K, M, SA} int8, box {128, 128, 1};  mapB: {K, N, SB} int8, box {128, 256, 1} (PAIR: {128, 128, 1});
+//   128-byte swizzle
 // grid.x = groups x tiles: heaviest group first; inside a group panels of OZ_PANEL column tiles, row tiles
-// fastest inside a panel, so a wave of CTAs covers a near-square region and shares its operand tiles in L2
+// fastest inside a panel, so a wave of CTAs covers a near-square region and shares its operand tiles in L2.
+//
+// PAIR = true: the CTA PAIR version (cluster of two CTAs on one TPC, tcgen05 cta_group::2).  The pair owns a
+// 256 x 256 tile: CTA r holds rows m0 + 128 r of A and rows n0 + 128 r of B (HALF of the B tile), one thread of
+// the leader CTA issues 256 x 256 x 32 MMAs that read both CTAs' shared memory and write each CTA's half of the
+// accumulator into its own tensor memory.  Per CTA and slice product that is 16 KB + 16 KB of operand instead of
+// 16 KB + 32 KB: a third less L2 -> SM traffic (the path that caps the single-CTA kernel) and half the
+// shared-memory reads of B.  Both CTAs load (their TMA completes on the LEADER's full barrier, which expects the
+// bytes of both), the leader's commits arrive on the empty barriers of both.
+template <bool PAIR>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 i8_gemm_groups_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                       const __grid_constant__ CUtensorMap mapC, const __grid_constant__ OzPlan plan, int kblocks,
-                      int ldc) {
+                      int ldc, int m_rows) {
+  constexpr int NB = PAIR ? 2 * OZ_NB : OZ_NB, B_BYTES = PAIR ? OZ_B_BYTES / 2 : OZ_B_BYTES;
   extern __shared__ __align__(1024) unsigned char oz_smem[];
-  __shared__ uint64_t fullA[OZ_NA], emptyA[OZ_NA], fullB[OZ_NB], emptyB[OZ_NB], tmem_full_bar;
+  __shared__ uint64_t fullA[OZ_NA], emptyA[OZ_NA], fullB[NB], emptyB[NB], tmem_full_bar;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles = plan.tiles_m * plan.tiles_n;
-  const int gi = (int)blockIdx.x / tiles, tile = (int)blockIdx.x % tiles;
-  const int panel = tile / (OZ_PANEL * plan.tiles_m), within = tile % (OZ_PANEL * plan.tiles_m);
+  unsigned rank = 0;
+  if constexpr (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+  const int rows_m = PAIR ? (plan.tiles_m + 1) / 2 : plan.tiles_m;      // row tiles (pairs of row tiles)
+  const int tiles = rows_m * plan.tiles_n;
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int gi = unit / tiles, tile = unit % tiles;
+  const int panel = tile / (OZ_PANEL * rows_m), within = tile % (OZ_PANEL * rows_m);
   const int pw = min(OZ_PANEL, plan.tiles_n - panel * OZ_PANEL);
-  const int m0 = (within / pw) * OZ_BM, n0 = (panel * OZ_PANEL + within % pw) * OZ_BN;
+  const int m0 = ((within / pw) * (PAIR ? 2 : 1) + (int)rank) * OZ_BM, n0 = (panel * OZ_PANEL + within % pw) * OZ_BN;
   const OzProgram& P = plan.g[gi];
   const unsigned smemA = ((unsigned)__cvta_generic_to_shared(oz_smem) + 1023u) & ~1023u;
   const unsigned smemB = smemA + OZ_NA * OZ_A_BYTES;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < OZ_NA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
-    for (int s = 0; s < OZ_NB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    for (int s = 0; s < NB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     mbar_init(&tmem_full_bar, 1);
     fence_async_proxy();
+    if constexpr (PAIR) asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 2) {   // one warp allocates tensor memory: all 512 columns (two accumulators; one CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::
-                     "r"((unsigned)__cvta_generic_to_shared(&tmem_base_s)), "r"((unsigned)(OZ_MAX_ACC * OZ_BN)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::
+                       "r"((unsigned)__cvta_generic_to_shared(&tmem_base_s)), "r"((unsigned)(OZ_MAX_ACC * OZ_BN)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::
+                       "r"((unsigned)__cvta_generic_to_shared(&tmem_base_s)), "r"((unsigned)(OZ_MAX_ACC * OZ_BN)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  if constexpr (PAIR) {   // the peer's barriers and tensor memory exist before anything crosses the pair
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  }
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = tmem_base_s;
 
@@ -133,7 +164,8 @@ i8_gemm_groups_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       const CUtensorMap* map = is_b ? &mapB : &mapA;
       uint64_t* full = is_b ? fullB : fullA;
       uint64_t* empty = is_b ? emptyB : emptyA;
-      const int slots = is_b ? OZ_NB : OZ_NA, bytes = is_b ? OZ_B_BYTES : OZ_A_BYTES, row0 = is_b ? n0 : m0;
+      const int slots = is_b ? NB : OZ_NA, bytes = is_b ? B_BYTES : OZ_A_BYTES;
+      const int row0 = is_b ? n0 + (PAIR ? (int)rank * (OZ_BN / 2) : 0) : m0;
       const unsigned base = is_b ? smemB : smemA;
       int seq = 0;
       for (int kb = 0; kb < kblocks; ++kb)
@@ -141,40 +173,57 @@ i8_gemm_groups_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           if ((P.load_is_b[l] != 0) != is_b) continue;
           const int slot = seq % slots;
           if (seq >= slots) mbar_wait(&empty[slot], (unsigned)((seq / slots - 1) & 1));
-          mbar_expect_tx(&full[slot], (unsigned)bytes);
-          tma_load_3d_raw(base + (unsigned)slot * bytes, map, kb * OZ_BK, row0, P.load_slice[l],
-                          (unsigned)__cvta_generic_to_shared(&full[slot]));
+          const unsigned bar = (unsigned)__cvta_generic_to_shared(&full[slot]);
+          if constexpr (PAIR) {
+            // the leader's barrier counts the bytes of both CTAs; the peer bit of the address is cleared so
+            // that the peer's copy completes there too
+            if (rank == 0) mbar_expect_tx(&full[slot], (unsigned)(2 * bytes));
+            asm volatile(
+                "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+                "[%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(base + (unsigned)slot * bytes), "l"(map), "r"(kb * OZ_BK),
+                "r"(row0), "r"((int)P.load_slice[l]), "r"(bar & 0xFEFFFFFFu) : "memory");
+          } else {
+            mbar_expect_tx(&full[slot], (unsigned)bytes);
+            tma_load_3d_raw(base + (unsigned)slot * bytes, map, kb * OZ_BK, row0, P.load_slice[l], bar);
+          }
           ++seq;
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ---- MMA issuer: one thread drives the tensor core
-      constexpr unsigned idesc = umma_idesc_i8(OZ_BM, OZ_BN);
+    if (lane == 0 && rank == 0) {   // ---- MMA issuer: one thread (of the leader CTA) drives the tensor core
+      constexpr unsigned idesc = umma_idesc_i8(PAIR ? 2 * OZ_BM : OZ_BM, OZ_BN);
       for (int kb = 0; kb < kblocks; ++kb)
         for (int m = 0; m < P.n_mma; ++m) {
           const int a_seq = kb * P.nA + P.mma_a[m], b_seq = kb * P.nB + P.mma_b[m];
-          const int sa = a_seq % OZ_NA, sb = b_seq % OZ_NB;
+          const int sa = a_seq % OZ_NA, sb = b_seq % NB;
           const unsigned flags = P.mma_flags[m];
           mbar_wait(&fullA[sa], (unsigned)((a_seq / OZ_NA) & 1));
-          mbar_wait(&fullB[sb], (unsigned)((b_seq / OZ_NB) & 1));
+          mbar_wait(&fullB[sb], (unsigned)((b_seq / NB) & 1));
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const uint64_t a_desc = umma_desc_k_major_sw128(smemA + (unsigned)sa * OZ_A_BYTES);
-          const uint64_t b_desc = umma_desc_k_major_sw128(smemB + (unsigned)sb * OZ_B_BYTES);
+          const uint64_t b_desc = umma_desc_k_major_sw128(smemB + (unsigned)sb * B_BYTES);
           const unsigned d_tmem = tmem + (unsigned)P.mma_acc[m] * OZ_BN;
           const bool fresh = kb == 0 && (flags & 4u);
 #pragma unroll
           for (int k = 0; k < OZ_BK / 32; ++k) {     // K = 32 int8 per instruction: 32 bytes further along the row
             const unsigned accumulate = (fresh && k == 0) ? 0u : 1u;
-            asm volatile(
-                "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::
-                    "r"(d_tmem), "l"(a_desc + (uint64_t)(2 * k)), "l"(b_desc + (uint64_t)(2 * k)), "r"(idesc),
-                "r"(accumulate), "r"(0u) : "memory");
+            if constexpr (PAIR)
+              asm volatile(
+                  "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                  "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}\n" ::
+                      "r"(d_tmem), "l"(a_desc + (uint64_t)(2 * k)), "l"(b_desc + (uint64_t)(2 * k)), "r"(idesc),
+                  "r"(accumulate), "r"(0u) : "memory");
+            else
+              asm volatile(
+                  "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::
+                      "r"(d_tmem), "l"(a_desc + (uint64_t)(2 * k)), "l"(b_desc + (uint64_t)(2 * k)), "r"(idesc),
+                  "r"(accumulate), "r"(0u) : "memory");
           }
-          if (flags & 1u) umma_commit(&emptyA[sa]);
-          if (flags & 2u) umma_commit(&emptyB[sb]);
+          if (flags & 1u) umma_commit<PAIR>(&emptyA[sa]);
+          if (flags & 2u) umma_commit<PAIR>(&emptyB[sb]);
         }
-      umma_commit(&tmem_full_bar);
+      umma_commit<PAIR>(&tmem_full_bar);
     }
   } else if (warp >= 4) {
     // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 = rows m0 + 32 (w - 4) + lane, 32 columns at a
@@ -187,7 +236,7 @@ i8_gemm_groups_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     const int row0 = m0 + (warp - 4) * 32;
     const unsigned stage0 = smemA + (unsigned)(warp - 4) * 8192u;
     int it = 0;
-    for (int a = 0; a < P.n_acc; ++a) {
+    for (int a = 0; a < P.n_acc && row0 < m_rows; ++a) {
       const uint32_t taddr = tmem + ((uint32_t)((warp - 4) * 32) << 16) + (uint32_t)(a * OZ_BN);
 #pragma unroll 1
       for (int c = 0; c < OZ_BN && n0 + c < ldc; c += 32, ++it) {
@@ -223,8 +272,16 @@ i8_gemm_groups_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
-  if (warp == 2)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"((unsigned)(OZ_MAX_ACC * OZ_BN)));
+  if constexpr (PAIR) {   // neither CTA leaves (or frees tensor memory) while the other may still touch it
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  }
+  if (warp == 2) {
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"((unsigned)(OZ_MAX_ACC * OZ_BN)));
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"((unsigned)(OZ_MAX_ACC * OZ_BN)));
+  }
 }
 
 

@@ -28,11 +28,16 @@ def _i8_gemm(A, B, orders):
     (128, 256, 128, 1, 1, 1), (256, 512, 384, 2, 3, 4), (384, 384, 1152, 3, 2, 4),
     (256, 1280, 640, 5, 6, 6),      # the default scheme: digits 5 x 6, orders 0..5 in three groups of two
     (128, 2304, 256, 6, 6, 6), (256, 256, 2048, 7, 7, 7), (128, 128, 256, 5, 6, 3), (2560, 256, 128, 4, 7, 5)])
-def test_i8_slice_products_are_exact(M, N, K, SA, SB, orders):
+@pytest.mark.parametrize("pair", ["1", "0"])
+def test_i8_slice_products_are_exact(monkeypatch, pair, M, N, K, SA, SB, orders):
     """Every order plane equals the integer sum of its slice products, over the full int8 range; the
     grouped kernel (two orders per CTA sharing operand tiles) with odd and even order counts, column
-    panels that do not fill (N / 256 not a multiple of 8) and a half-empty last column tile."""
+    panels that do not fill (N / 256 not a multiple of 8) and a half-empty last column tile.  Both
+    launch modes: CTA pairs (tcgen05 cta_group::2, the default; an odd number of row tiles leaves the last
+    pair's second CTA without rows) and one CTA per tile (HMCB_OZAKI_PAIR=0)."""
     import torch
+
+    monkeypatch.setenv("HMCB_OZAKI_PAIR", pair)
 
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randint(-128, 128, (SA, M, K), generator=g, device="cuda", dtype=torch.int8)
