@@ -65,6 +65,9 @@ SIGNATURES = {
     "hmcb_set_mass_full": (C.c_int, [C.c_void_p, _c_double_p, _c_double_p]),
     "hmcb_debug_i8_gemm": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmcb_debug_i8_gather_gemm": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                            C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]),
     "hmcb_debug_oz_slice_rows": (C.c_double, [_c_double_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "hmcb_clear_target": (C.c_int, [C.c_void_p]),
     "hmcb_add_prior": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, _c_double_p,

@@ -128,4 +128,14 @@ cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& ma
                                   const CUtensorMap& mapC, long long M, long long N, long long K, int SA, int SB,
                                   int orders, int ldc, cudaStream_t s);
 
+struct OzBundle;
+struct OzPlan;
+bool oz_build_plan(int SA, int SB, int orders, long long M, long long N, OzPlan* plan);
+cudaError_t ozaki_sparse_init();
+cudaError_t launch_i8_gather_gemm(const CUtensorMap& mapA, const CUtensorMap& mapC, int n_bundles, int SA, int SB,
+                                  int orders, const OzBundle* bundles, const int* list, const signed char* Bg,
+                                  long long bg_plane, int ld, cudaStream_t s);
+cudaError_t launch_oz_slice_plain(const double* X, int K, int ld, int SB, const unsigned long long* maxbits,
+                                  signed char* out, long long plane, cudaStream_t s);
+
 }  // namespace hmcb

@@ -8,6 +8,7 @@
 
 #include "launch.cuh"
 #include "ozaki.cuh"
+#include "ozaki_sparse.cuh"
 
 namespace hmcb {
 
@@ -271,4 +272,60 @@ extern "C" double hmcb_debug_oz_slice_rows(const double* A, int64_t rows, int64_
                                            int32_t* ea) {
   if (!A || !ea || rows <= 0 || cols <= 0 || S < 1 || S > hmcb::OZ_MAX_SLICES) return -1.0;
   return hmcb::oz_slice_rows_host(A, rows, cols, rows, cols, S, slices, ea);
+}
+
+// ---- gathered (block-sparse) slice products (ozaki_sparse.cuh) ------------------------------------------
+namespace hmcb {
+
+cudaError_t ozaki_sparse_init() {
+  return cudaFuncSetAttribute(i8_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES);
+}
+
+// C[o] (o < orders), rows = bundles x 128: the slice products of every bundle's dense tile (mapA: the digits of
+// all bundles end to end on the K axis, 128 rows) with the B rows its list names, gathered from the digit
+// planes Bg [SB][rows_b x ld] (chains contiguous).  ld % 128 == 0.
+cudaError_t launch_i8_gather_gemm(const CUtensorMap& mapA, const CUtensorMap& mapC, int n_bundles, int SA, int SB,
+                                  int orders, const OzBundle* bundles, const int* list, const signed char* Bg,
+                                  long long bg_plane, int ld, cudaStream_t s) {
+  if (ld % 128 || n_bundles < 1) return cudaErrorInvalidValue;
+  OzPlan plan;
+  if (!oz_build_plan(SA, SB, orders, (long long)n_bundles * OZ_BM, ld, &plan)) return cudaErrorInvalidValue;
+  const long long ctas = (long long)plan.n_groups * plan.tiles_m * plan.tiles_n;
+  if (ctas <= 0 || ctas > 0x7fffffffll) return cudaErrorInvalidValue;
+  // column tiles per panel: the digit planes of a panel's chains (all B rows x 256 chains x SB digits per tile)
+  // should stay in L2 next to the model tiles and the order planes streaming through
+  const char* pv = std::getenv("HMCB_OZAKI_SPARSE_PANEL");
+  const int panel = std::max(1, pv ? std::atoi(pv) : 3);
+  i8_gather_gemm_kernel<<<(unsigned)ctas, OZS_THREADS, OZ_SMEM_BYTES, s>>>(mapA, mapC, plan, bundles, list, Bg, bg_plane,
+                                                                            ld, ld, panel);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_oz_slice_plain(const double* X, int K, int ld, int SB, const unsigned long long* maxbits,
+                                  signed char* out, long long plane, cudaStream_t s) {
+  if (ld % 128 || SB < 1 || SB > OZ_MAX_SLICES) return cudaErrorInvalidValue;
+  oz_slice_plain_kernel<<<dim3((ld / 4 + 255) / 256, (K + 7) / 8), 256, 0, s>>>(X, K, ld, SB, maxbits, out, plane);
+  return cudaGetLastError();
+}
+
+}  // namespace hmcb
+
+// Test / measurement entry: gathered int8 slice products.  A: [SA][128][Ktot] digits of the bundles' tiles,
+// bundles: n_bundles x {koff, kblocks}, list: [Ktot] B-row index per list entry, B: [SB][rows_b][N] digit
+// planes (chains contiguous), C: [orders][n_bundles * 128][N].
+extern "C" int hmcb_debug_i8_gather_gemm(int device, int64_t n_bundles, int64_t N, int64_t Ktot, int64_t rows_b, int SA,
+                                         int SB, int orders, const signed char* A, const int32_t* bundles,
+                                         const int32_t* list, const signed char* B, int32_t* C, void* stream) {
+  using namespace hmcb;
+  if (!A || !B || !C || !bundles || !list || n_bundles <= 0 || N <= 0 || Ktot <= 0 || Ktot % OZ_BK) return -1;
+  if (cudaSetDevice(device) != cudaSuccess) return -1;
+  if (ozaki_sparse_init() != cudaSuccess) return -2;
+  CUtensorMap mapA, mapC;
+  if (ozaki_slice_map(A, Ktot, OZ_BM, SA, OZ_BM, &mapA) != cudaSuccess) return -3;
+  if (ozaki_plane_map(C, N, n_bundles * OZ_BM, orders, n_bundles * OZ_BM * N, &mapC) != cudaSuccess) return -3;
+  static_assert(sizeof(OzBundle) == 2 * sizeof(int32_t), "OzBundle layout");
+  if (launch_i8_gather_gemm(mapA, mapC, (int)n_bundles, SA, SB, orders, reinterpret_cast<const OzBundle*>(bundles), list, B,
+                            rows_b * N, (int)N, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return -4;
+  return 0;
 }

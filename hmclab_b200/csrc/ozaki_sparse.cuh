@@ -13,12 +13,10 @@
 //
 // Kernel = ozaki.cuh's slice-product kernel (dataflow program per order group, tile rings, one MMA
 // thread, TMEM accumulators, TMA-stored order planes) with one change: the B tiles are GATHERED.  Eight
-// producer warps replace the B TMA lane: warp w owns chains 32 w .. 32 w + 31 of the tile, lane g the
-// four list entries 4 g .. 4 g + 3 of the k-block; a lane loads 32 bytes (32 chains) of each of its
-// four B rows, transposes 4 x 4 byte blocks with byte permutes and stores, per chain, one 32-bit word
-// (four consecutive k) into the K-major 128-byte-swizzled tile the MMA descriptor expects -- the 32
-// lanes of a store hit 32 different banks.  ~1 warp instruction per clock and SM, 28 % of the issue
-// slots, next to a tensor pipe that needs 128 clocks per instruction.
+// producer warps replace the B TMA lane: they load the listed B rows (coalesced: 128 contiguous bytes of
+// a row per 8 lanes), transpose 4 x 4 byte blocks with byte permutes and store, per chain, one 32-bit
+// word (four consecutive k) into the K-major 128-byte-swizzled tile the MMA descriptor expects (details
+// at the producer code).
 #pragma once
 #include "ozaki.cuh"
 
@@ -41,24 +39,24 @@ __device__ __forceinline__ void oz_transpose4(const unsigned (&w)[4], unsigned (
 // C[o][b * 128 + r][n] = sum over slice pairs (s, o - s) of sum_j A_s[r][koff_b + j] * Bg_(o-s)[list[koff_b + j]][n]
 //   mapA: {Ktot, 128, SA} int8, box {128, 128, 1}, 128-byte swizzle;  Bg: [SB][rows_b x ld] int8, chains contiguous
 //   mapC: order planes [orders][n_bundles * 128 x ldc]
-// grid.x = groups x (bundles x column tiles): heaviest group first; panels of OZ_PANEL column tiles, bundles
+// grid.x = groups x (bundles x column tiles): heaviest group first; panels of `panel_tiles` column tiles, bundles
 // (sorted by length) fastest inside a panel: a wave works on few column tiles (their B rows stay in L2) and
 // on neighbouring bundles
 __global__ void __launch_bounds__(OZS_THREADS, 1)
 i8_gather_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapC,
                       const __grid_constant__ OzPlan plan, const OzBundle* __restrict__ bundles,
                       const int* __restrict__ list, const signed char* __restrict__ Bg, long long bg_plane, int ld,
-                      int ldc) {
+                      int ldc, int panel_tiles) {
   extern __shared__ __align__(1024) unsigned char oz_smem[];
   __shared__ uint64_t fullA[OZ_NA], emptyA[OZ_NA], fullB[OZ_NB], emptyB[OZ_NB], tmem_full_bar;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_bundles = plan.tiles_m;
-  const int tiles = n_bundles * plan.tiles_n;
-  const int gi = (int)blockIdx.x / tiles, tile = (int)blockIdx.x % tiles;
-  const int panel = tile / (OZ_PANEL * n_bundles), within = tile % (OZ_PANEL * n_bundles);
-  const int pw = min(OZ_PANEL, plan.tiles_n - panel * OZ_PANEL);
-  const int b = within / pw, n0 = (panel * OZ_PANEL + within % pw) * OZ_BN;
+  // the order groups of a (bundle, column tile) run next to each other: they read the same operands
+  const int gi = (int)blockIdx.x % plan.n_groups, tile = (int)blockIdx.x / plan.n_groups;
+  const int panel = tile / (panel_tiles * n_bundles), within = tile % (panel_tiles * n_bundles);
+  const int pw = min(panel_tiles, plan.tiles_n - panel * panel_tiles);
+  const int b = within / pw, n0 = (panel * panel_tiles + within % pw) * OZ_BN;
   const int m0 = b * OZ_BM;
   const OzBundle bun = bundles[b];
   const int kblocks = bun.kblocks;
@@ -97,51 +95,75 @@ i8_gather_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         }
     }
   } else if (warp >= 8) {
-    // ---- gather producers of the chain digits: warp w -> chains n0 + 32 w .., lane g -> list entries 4 g ..
-    const int w = warp - 8, chain0 = n0 + 32 * w;
-    const bool live = chain0 < ld;
+    // ---- gather producers of the chain digits.  Warp w owns the list entries 16 w .. 16 w + 15 of every
+    // k-block (four k-quads), lane (q, h) = (lane >> 3, lane & 7) the k-quad 4 w + q and 16 bytes of each
+    // 128-chain half of its four B rows: one warp-level load touches 4 rows x 128 contiguous bytes = four
+    // lines (a lane-per-row mapping costs the L1 tag stage a lookup per 16 bytes and runs 4x slower).  The
+    // digit planes hold the chains of a 128-chain block PERMUTED -- byte 16 h + m <-> chain h + 8 m -- so
+    // that the four bytes of a loaded word are chains 8 apart: after the 4 x 4 byte transpose the 32 lanes
+    // of a store write rows with 8 different swizzle phases x 4 different words = 32 different banks.
+    // The loads of the NEXT tile are in flight while the current one is transposed and stored.
+    const int w = warp - 8, q = lane >> 3, h = lane & 7;
+    unsigned long long bsl = 0ull;   // slice of the i-th B load of a k-block, 4 bits each
+    {
+      int i = 0;
+      for (int l = 0; l < P.n_loads; ++l)
+        if (P.load_is_b[l]) bsl |= (unsigned long long)P.load_slice[l] << (4 * i++);
+    }
+    const int nB = P.nB;
+    const bool live0 = n0 < ld, live1 = n0 + 128 < ld;
+    const int4* lst = reinterpret_cast<const int4*>(list + bun.koff) + 4 * w + q;   // + 32 per k-block
+    auto load_tile = [&](int4 (&v)[4][2], int slice, const int4& r4) {
+      const signed char* plane = Bg + (size_t)slice * bg_plane + n0 + 16 * h;
+      const int rows[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const signed char* p = plane + (size_t)rows[c] * ld;
+        v[c][0] = live0 ? __ldg(reinterpret_cast<const int4*>(p)) : make_int4(0, 0, 0, 0);
+        v[c][1] = live1 ? __ldg(reinterpret_cast<const int4*>(p + 128)) : make_int4(0, 0, 0, 0);
+      }
+    };
+    int4 rows_cur = __ldg(lst), rows_nxt = kblocks > 1 ? __ldg(lst + 32) : rows_cur;
+    int4 v[4][2];
+    load_tile(v, (int)(bsl & 15ull), rows_cur);
+    // byte offset of (row h of a swizzle atom, k-quad 4 w + q): the row adds 1024 (row >> 3) per atom
+    const unsigned lane_off = (unsigned)h * 128u + ((unsigned)(w ^ h) << 4) + (unsigned)q * 4u;
     int seq = 0;
     for (int kb = 0; kb < kblocks; ++kb) {
-      const int4 rows4 = __ldg(reinterpret_cast<const int4*>(list + bun.koff + kb * OZ_BK) + lane);
-      const int rows[4] = {rows4.x, rows4.y, rows4.z, rows4.w};
-      for (int l = 0; l < P.n_loads; ++l) {
-        if (!P.load_is_b[l]) continue;
+      const int4 rows_n2 = kb + 2 < kblocks ? __ldg(lst + 32 * (kb + 2)) : rows_nxt;
+      for (int i = 0; i < nB; ++i) {
+        int4 vn[4][2];
+        const bool last_of_kb = i + 1 == nB;
+        if (!(last_of_kb && kb + 1 == kblocks))
+          load_tile(vn, (int)((bsl >> (4 * (last_of_kb ? 0 : i + 1))) & 15ull), last_of_kb ? rows_nxt : rows_cur);
         const int slot = seq % OZ_NB;
         if (seq >= OZ_NB) mbar_wait(&emptyB[slot], (unsigned)((seq / OZ_NB - 1) & 1));
-        const signed char* plane = Bg + (size_t)P.load_slice[l] * bg_plane + chain0;
-        int4 v[4][2];
+        const unsigned tileB = smemB + (unsigned)slot * OZ_B_BYTES + lane_off;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (live) {
-            const int4* p = reinterpret_cast<const int4*>(plane + (size_t)rows[c] * ld);
-            v[c][0] = __ldg(p); v[c][1] = __ldg(p + 1);
-          } else {
-            v[c][0] = make_int4(0, 0, 0, 0); v[c][1] = make_int4(0, 0, 0, 0);
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {   // word u of the 16 bytes: chains h + 8 (4 u + j), j = 0..3, of the half
+            unsigned in[4], out[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int4 x = v[c][half];
+              in[c] = (unsigned)(u == 0 ? x.x : u == 1 ? x.y : u == 2 ? x.z : x.w);
+            }
+            oz_transpose4(in, out);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)   // row 128 half + h + 8 (4 u + j): atom 16 half + 4 u + j
+              asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(tileB + (unsigned)(16 * half + 4 * u + j) * 1024u),
+                           "r"(out[j]) : "memory");
           }
-        }
-        const unsigned tileB = smemB + (unsigned)slot * OZ_B_BYTES;
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {   // chains 4 a .. 4 a + 3 of the warp's 32
-          unsigned in[4], out[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int4 q = v[c][a >> 2];
-            in[c] = (unsigned)((a & 3) == 0 ? q.x : (a & 3) == 1 ? q.y : (a & 3) == 2 ? q.z : q.w);
-          }
-          oz_transpose4(in, out);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const unsigned row = (unsigned)(32 * w + 4 * a + j);      // chain row of the tile
-            const unsigned addr = tileB + (row >> 3) * 1024u + (row & 7u) * 128u +
-                                  ((((unsigned)lane >> 2) ^ (row & 7u)) << 4) + ((unsigned)lane & 3u) * 4u;
-            asm volatile("st.shared.b32 [%0], %1;\n" ::"r"(addr), "r"(out[j]) : "memory");
-          }
-        }
         fence_async_proxy();
         __syncwarp();
         if (lane == 0) mbar_arrive(&fullB[slot]);
         ++seq;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { v[c][0] = vn[c][0]; v[c][1] = vn[c][1]; }
       }
+      rows_cur = rows_nxt;
+      rows_nxt = rows_n2;
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ---- MMA issuer
@@ -219,25 +241,29 @@ i8_gather_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"((unsigned)(OZ_MAX_ACC * OZ_BN)));
 }
 
-// X [K x ld] (chains contiguous) -> SB digit planes [t][K x ld], chains contiguous (the layout the gather
-// producers read); a thread slices four consecutive chains of a row and writes one word per plane
+// position of chain n inside its digit-plane row: the chains of a 128-chain block are permuted, byte
+// 16 h + m <-> chain h + 8 m (see the gather producers)
+__host__ __device__ __forceinline__ int oz_plane_pos(int n) { return (n & ~127) + 16 * (n & 7) + ((n & 127) >> 3); }
+
+// X [K x ld] (chains contiguous) -> SB digit planes [t][K x ld] in the gather layout (oz_plane_pos); a thread
+// slices the four chains of one plane word (8 apart) of a row and writes one word per plane.  ld % 128 == 0.
 __global__ void __launch_bounds__(256)
 oz_slice_plain_kernel(const double* __restrict__ X, int K, int ld, int SB, const unsigned long long* __restrict__ maxbits,
                       signed char* __restrict__ out, long long plane) {
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
-  if (c >= ld) return;
-  int eb[4];
+  const int word = blockIdx.x * 256 + threadIdx.x;       // word of a plane row: bytes 4 word .. 4 word + 3
+  if (4 * word >= ld) return;
+  const int blk = (4 * word) & ~127, p = (4 * word) & 127, h = p >> 4, m0 = p & 15;   // chains h + 8 (m0 + j)
+  int eb[4], col[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) eb[j] = oz_exponent(maxbits[c + j]);
+  for (int j = 0; j < 4; ++j) { col[j] = blk + h + 8 * (m0 + j); eb[j] = oz_exponent(maxbits[col[j]]); }
   const double up = oz_pow2(OZ_BITS * SB);
   const int r1 = min(K, ((int)blockIdx.y + 1) * 8);
   for (int r = blockIdx.y * 8; r < r1; ++r) {
-    const double4 x = *reinterpret_cast<const double4*>(X + (size_t)r * ld + c);
-    const double xs[4] = {x.x, x.y, x.z, x.w};
     unsigned lo[4], hi[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const long long Xi = eb[j] != INT_MIN ? __double2ll_rn(oz_scale_down(xs[j], eb[j]) * up) : 0ll;
+      const double x = __ldcs(X + (size_t)r * ld + col[j]);
+      const long long Xi = eb[j] != INT_MIN ? __double2ll_rn(oz_scale_down(x, eb[j]) * up) : 0ll;
       const unsigned long long y = oz_digit_bytes(Xi, SB);
       lo[j] = (unsigned)y;
       hi[j] = (unsigned)(y >> 32);
@@ -249,7 +275,7 @@ oz_slice_plain_kernel(const double* __restrict__ X, int K, int ld, int SB, const
         const unsigned* w = byte < 4 ? lo : hi;
         const unsigned sel = 0x4040u + (unsigned)(byte & 3) * 0x1111u;
         const unsigned p01 = __byte_perm(w[0], w[1], sel), p23 = __byte_perm(w[2], w[3], sel);
-        *reinterpret_cast<unsigned*>(out + (size_t)t * plane + (size_t)r * ld + c) = __byte_perm(p01, p23, 0x5410u);
+        *reinterpret_cast<unsigned*>(out + (size_t)t * plane + (size_t)r * ld + 4 * word) = __byte_perm(p01, p23, 0x5410u);
       }
   }
 }

@@ -103,6 +103,14 @@ int hmcb_set_mass_full(hmcb_engine *e, const double *cholesky_lower, const doubl
  * multiples of 128), C [orders][M x N] int32 DEVICE: C[o] = sum over s + t = o of A_s B_t^T. */
 int hmcb_debug_i8_gemm(int device, int64_t M, int64_t N, int64_t K, int SA, int SB, int orders,
                        const signed char *A, const signed char *B, int32_t *C, void *stream);
+/* Gathered (block-sparse) slice products (csrc/ozaki_sparse.cuh): the building block of the sparse
+ * LinearMatrix products on tcgen05.  A [SA][128 x Ktot]: the dense int8 tiles of `n_bundles` row bundles end to
+ * end on the K axis; bundles [n_bundles] = {offset on that axis, k-blocks of 128}; list [Ktot]: the row of B every
+ * list entry multiplies; B [SB][rows_b x N] digit planes with the N chains contiguous (N % 128 == 0);
+ * C [orders][n_bundles * 128 x N] int32.  All DEVICE arrays. */
+int hmcb_debug_i8_gather_gemm(int device, int64_t n_bundles, int64_t N, int64_t Ktot, int64_t rows_b, int SA,
+                              int SB, int orders, const signed char *A, const int32_t *bundles,
+                              const int32_t *list, const signed char *B, int32_t *C, void *stream);
 /* Host side of the slicing (no GPU needed): balanced radix-256 digits of a HOST matrix [rows x cols],
  * a[i][k] = 2^ea[i] * sum_s slices[s][i][k] 256^-(s+1) + rounding; slices [S][rows x cols] int8 (may be
  * NULL), ea [rows].  Returns max over rows of sum_k |rounding| / sum_k |a[i][k]|, or -1 on bad input. */

@@ -129,3 +129,44 @@ def test_ozaki_gradient_follows_chain_scales_over_many_magnitudes():
     ref = (Gt @ r).T
     scale = (np.abs(Gt) @ np.abs(r)).T + (np.abs(Gt) @ ((np.abs(G32) @ np.abs(q.T)) / v32)).T
     assert np.all(np.abs(got - ref) <= 1e-12 * scale)
+
+
+@pytest.mark.parametrize("N,kblocks,SA,SB,orders", [(256, (1,), 1, 1, 1), (384, (2, 1, 3), 3, 4, 5),
+                                                     (1280, (3, 3, 2, 1), 5, 6, 6)])
+def test_gathered_slice_products_are_exact(N, kblocks, SA, SB, orders):
+    """The block-sparse building block (csrc/ozaki_sparse.cuh): every bundle's dense int8 tile times the B rows
+    its list names, gathered by the producer warps into the swizzled operand tile -- against integer
+    arithmetic; bundles of different lengths, repeated list entries, a half-empty last column tile."""
+    import torch
+
+    from hmclab_b200._engine import load_library
+
+    lib = load_library()
+    g = torch.Generator(device="cuda").manual_seed(N + sum(kblocks))
+    nb, rows_b = len(kblocks), 700
+    Ktot = 128 * sum(kblocks)
+    koff = np.concatenate([[0], np.cumsum(kblocks)[:-1]]) * 128
+    bundles = torch.as_tensor(np.stack([koff, kblocks], axis=1).astype(np.int32)).cuda().contiguous()
+    lst = torch.randint(0, rows_b, (Ktot,), generator=g, device="cuda", dtype=torch.int32)
+    A = torch.randint(-128, 128, (SA, 128, Ktot), generator=g, device="cuda", dtype=torch.int8)
+    B = torch.randint(-128, 128, (SB, rows_b, N), generator=g, device="cuda", dtype=torch.int8)
+    # the digit planes hold the chains of every 128-chain block permuted: chain h + 8 m sits at byte 16 h + m
+    n = np.arange(N)
+    pos = torch.as_tensor((n & ~127) + 16 * (n & 7) + ((n & 127) >> 3)).cuda()
+    planes = torch.empty_like(B)
+    planes[:, :, pos] = B
+    out = torch.full((orders, nb * 128, N), -7, dtype=torch.int32, device="cuda")
+    rc = lib.hmcb_debug_i8_gather_gemm(torch.cuda.current_device(), nb, N, Ktot, rows_b, SA, SB, orders, A.data_ptr(),
+                                       bundles.data_ptr(), lst.data_ptr(), planes.data_ptr(), out.data_ptr(),
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    ref = torch.zeros(orders, nb * 128, N, dtype=torch.float64, device="cuda")
+    for b in range(nb):
+        sl = slice(int(koff[b]), int(koff[b]) + 128 * kblocks[b])
+        rows = lst[sl].long()
+        for s in range(SA):
+            for t in range(SB):
+                if s + t < orders:
+                    ref[s + t, b * 128:(b + 1) * 128] += A[s][:, sl].double() @ B[t][rows].double()
+    assert torch.equal(out.double(), ref)
