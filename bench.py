@@ -540,8 +540,11 @@ def bench_workload(ctx, name, steps, warmup, block=0, chains=0):
             # section 4) over the duration of the WHOLE launch group (slicing + products + recombination);
             # the fp64 view of the same launches (4 N d flop per gradient evaluation against the DGEMM peak
             # measured in this run) is kept next to it -- its ratio may exceed 1, which is the point.
-            pairs = oz_pairs                      # slice products of G q and G^T r together
-            i8_ops = pairs * flops / 2.0 * C      # 2 N d int8 operations per slice product and chain
+            pairs = oz_pairs                      # slice products of G q and G^T r together (premultiplied: of GtG q)
+            # int8 operations per slice product and chain: 2 N d (half the 4 N d flops of the direct form's two
+            # products), or 2 d^2 = all the flops of the premultiplied form's single product
+            per_product = flops if w.extra.get("form") == "premultiplied" else flops / 2.0
+            i8_ops = pairs * per_product * C
             measured = committed_json("../MEASURED_PEAKS.json")
             sustained = measured.get("bf16_tflops_sustained") if ms_per_step > 50 else measured.get("bf16_tflops")
             i8_peak = 2.0 * sustained if sustained else 4500.0
@@ -552,7 +555,7 @@ def bench_workload(ctx, name, steps, warmup, block=0, chains=0):
                                  "path's measured peak: > 1 means faster than any DMMA/DGEMM kernel could be"}
             roofline = {"bound": "tensor", "achieved": i8_ops / (kernel_ms * 1e-3) / 1e12, "peak": i8_peak,
                         "unit": "TFLOP/s", "traffic": traffic, "kernel": kernel, "dtype_of_peak": "int8 (dense, TOP/s)",
-                        "slice_pairs": pairs, "algorithmic_int8_ops_per_grad_eval": pairs * flops / 2.0,
+                        "slice_pairs": pairs, "algorithmic_int8_ops_per_grad_eval": pairs * per_product,
                         "peak_source": ("2 x the driver-measured %s bf16 rate (MEASURED_PEAKS.json): tcgen05 kind::i8 "
                                         "runs at twice the bf16 rate" % ("sustained" if ms_per_step > 50 else "burst")
                                         if sustained else "nominal dense int8"),

@@ -88,6 +88,7 @@ struct hmcb_engine {
   bool oz = false;
   int oz_saG = 0, oz_saGt = 0;         // int8 digits of G / G^T (what their rows need, at most the orders kept)
   int oz_sb = OZ_SLICES_B, oz_orders = OZ_NUM_ORDERS;   // digits of the chain batch, orders kept
+  int64_t oz_rows = 0;                                  // padded rows of the forward operator (npad, or dpad when premultiplied)
   signed char *oz_AG = nullptr, *oz_AGt = nullptr, *oz_B = nullptr;   // int8 slices of G, G^T, the chain batch
   int *oz_eaG = nullptr, *oz_eaGt = nullptr, *oz_C = nullptr;         // row exponents, int32 order planes
   unsigned long long *oz_maxQ = nullptr, *oz_maxR = nullptr;          // per-chain max |.| (bit patterns)
@@ -814,46 +815,54 @@ int oz_upload_matrix(hmcb_engine* e, const double* A, int64_t rows, int64_t cols
   return 0;
 }
 
-// Sets up the Ozaki-sliced tcgen05 path for the dense direct products when it is valid and pays:
-// int32 accumulation must not overflow (K * pairs * 128^2 < 2^31) and the products must be large.
+// Sets up the Ozaki-sliced tcgen05 path for the dense products (direct: G q and G^T r; premultiplied: GtG q)
+// when it is valid and pays: int32 accumulation must not overflow (K * pairs * 128^2 < 2^31) and the
+// products must be large.
 int oz_setup(hmcb_engine* e) {
   const int want = env_int("HMCB_OZAKI", -1);   // -1: when it pays, 0: never, 1: whenever valid
   if (want == 0) return 0;
+  const bool premult = e->lik == LK_DENSE_PREMULT;
   e->oz_orders = std::min(std::max(env_int("HMCB_OZAKI_ORDERS", OZ_NUM_ORDERS), 4), OZ_SLICES_MAX);
   e->oz_sb = e->oz_orders;
-  const int64_t Kmax = std::max<int64_t>(e->dpad, e->npad);
+  e->oz_rows = premult ? e->dpad : e->npad;     // rows of the forward operator (padded)
+  const int64_t Kmax = std::max<int64_t>(e->dpad, premult ? 0 : e->npad);
   if (Kmax * e->oz_orders * 128 * 128 >= (1ll << 31)) return 0;
-  if (want < 0 && ((int64_t)e->dpad * e->npad < (1ll << 20) || e->C < 1024)) return 0;
+  if (want < 0 && ((int64_t)e->dpad * e->oz_rows < (1ll << 20) || e->C < 1024)) return 0;
+  if (premult && e->dpad == 128) return 0;      // the whole-proposal kernel with GtG in shared memory owns that size
   for (double v : e->h_A) if (!std::isfinite(v)) return 0;
   for (double v : e->h_At) if (!std::isfinite(v)) return 0;
   const int d = (int)e->d;
-  if (oz_upload_matrix(e, e->h_A.data(), e->N, d, e->npad, e->dpad, e->oz_orders, &e->oz_saG, &e->oz_AG, &e->oz_eaG) ||
-      oz_upload_matrix(e, e->h_At.data(), d, e->N, e->dpad, e->npad, e->oz_orders, &e->oz_saGt, &e->oz_AGt,
-                       &e->oz_eaGt))
+  if (oz_upload_matrix(e, e->h_A.data(), premult ? d : e->N, d, e->oz_rows, e->dpad, e->oz_orders, &e->oz_saG, &e->oz_AG,
+                       &e->oz_eaG))
+    return -1;
+  if (!premult && oz_upload_matrix(e, e->h_At.data(), d, e->N, e->dpad, e->npad, e->oz_orders, &e->oz_saGt, &e->oz_AGt,
+                                   &e->oz_eaGt))
     return -1;
   if (dev_alloc(e, (size_t)e->oz_sb * e->ld * Kmax, &e->oz_B) ||
-      dev_alloc(e, (size_t)e->oz_orders * e->npad * e->ld, &e->oz_C) ||
+      dev_alloc(e, (size_t)e->oz_orders * e->oz_rows * e->ld, &e->oz_C) ||
       dev_alloc(e, (size_t)e->ld, &e->oz_maxQ) || dev_alloc(e, (size_t)e->ld, &e->oz_maxR)) return -1;
   HMCB_CUDA(ozaki_init());
-  HMCB_CUDA(ozaki_slice_map(e->oz_AG, e->dpad, e->npad, e->oz_saG, 128, &e->oz_mapAG));
-  HMCB_CUDA(ozaki_slice_map(e->oz_AGt, e->npad, e->dpad, e->oz_saGt, 128, &e->oz_mapAGt));
+  HMCB_CUDA(ozaki_slice_map(e->oz_AG, e->dpad, e->oz_rows, e->oz_saG, 128, &e->oz_mapAG));
   HMCB_CUDA(ozaki_slice_map(e->oz_B, e->dpad, e->ld, e->oz_sb, 256, &e->oz_mapBq));
-  HMCB_CUDA(ozaki_slice_map(e->oz_B, e->npad, e->ld, e->oz_sb, 256, &e->oz_mapBr));
   HMCB_CUDA(ozaki_slice_map(e->oz_B, e->dpad, e->ld, e->oz_sb, 128, &e->oz_mapBqh));   // half tiles: CTA pairs
-  HMCB_CUDA(ozaki_slice_map(e->oz_B, e->npad, e->ld, e->oz_sb, 128, &e->oz_mapBrh));
-  HMCB_CUDA(ozaki_plane_map(e->oz_C, e->ld, e->npad, e->oz_orders, (long long)e->npad * e->ld, &e->oz_mapCq));
-  HMCB_CUDA(ozaki_plane_map(e->oz_C, e->ld, e->dpad, e->oz_orders, (long long)e->dpad * e->ld, &e->oz_mapCr));
+  HMCB_CUDA(ozaki_plane_map(e->oz_C, e->ld, e->oz_rows, e->oz_orders, (long long)e->oz_rows * e->ld, &e->oz_mapCq));
+  if (!premult) {
+    HMCB_CUDA(ozaki_slice_map(e->oz_AGt, e->npad, e->dpad, e->oz_saGt, 128, &e->oz_mapAGt));
+    HMCB_CUDA(ozaki_slice_map(e->oz_B, e->npad, e->ld, e->oz_sb, 256, &e->oz_mapBr));
+    HMCB_CUDA(ozaki_slice_map(e->oz_B, e->npad, e->ld, e->oz_sb, 128, &e->oz_mapBrh));
+    HMCB_CUDA(ozaki_plane_map(e->oz_C, e->ld, e->dpad, e->oz_orders, (long long)e->dpad * e->ld, &e->oz_mapCr));
+  }
   e->oz = true;
   return 0;
 }
 
-// Y = G q as int8 slice products on the tcgen05 tensor cores (ozaki.cuh): per-chain scale, digits of the
+// Y = G q (premultiplied: GtG q) as int8 slice products on the tcgen05 tensor cores (ozaki.cuh): per-chain scale, digits of the
 // chain batch, the exact slice products in int32 order planes -> oz_C (recombined by the caller's epilogue)
 int oz_forward_product(hmcb_engine* e, const double* q_in, cudaStream_t s) {
   HMCB_CUDA(launch_oz_colmax(q_in, e->dpad, e->ld, e->oz_maxQ, s));
   HMCB_CUDA(launch_oz_slice_chains(q_in, e->dpad, e->ld, e->oz_sb, e->oz_maxQ, e->oz_B, s));
-  HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAG, e->oz_mapBq, e->oz_mapBqh, e->oz_mapCq, e->npad, e->ld, e->dpad, e->oz_saG, e->oz_sb,
-                                  e->oz_orders, e->ld, s));
+  HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAG, e->oz_mapBq, e->oz_mapBqh, e->oz_mapCq, e->oz_rows, e->ld, e->dpad, e->oz_saG,
+                                  e->oz_sb, e->oz_orders, e->ld, s));
   e->launches += 3;
   return 0;
 }
@@ -894,6 +903,13 @@ int staged_gradient_pass(hmcb_engine* e, const double* q_in, UpdateEpi epi, cuda
     }
     case LK_DENSE_PREMULT: {
       epi.sub = e->dvec;
+      if (e->oz) {   // GtG q as int8 slice products on tcgen05, the update fused into the recombination
+        if (oz_forward_product(e, q_in, s)) return -1;
+        HMCB_CUDA(launch_oz_combine_update(e->oz_C, (long long)e->oz_rows * e->ld, e->dpad, e->ld, e->oz_orders, e->oz_eaG,
+                                           e->oz_maxQ, epi, s));
+        e->launches += 1;
+        break;
+      }
       HMCB_CUDA(launch_gemm_update(e->dA, e->dpad, e->dpad, q_in, e->ld, e->dpad, epi, s));
       e->launches += 1;
       break;
@@ -955,6 +971,12 @@ int staged_misfit_pass(hmcb_engine* e, const double* q, cudaStream_t s) {
     case LK_NONE: return 0;
     case LK_DENSE_PREMULT:
       m.rows = (int)e->d; m.vec = e->dvec;
+      if (e->oz) {
+        if (oz_forward_product(e, q, s)) return -1;
+        HMCB_CUDA(launch_oz_combine_misfit(e->oz_C, (long long)e->oz_rows * e->ld, e->dpad, e->ld, e->oz_orders, e->oz_eaG,
+                                           e->oz_maxQ, m, s));
+        break;
+      }
       HMCB_CUDA(launch_gemm_misfit(e->dA, e->dpad, e->dpad, q, e->ld, e->dpad, m, s));
       break;
     case LK_DENSE_DIRECT:
@@ -1699,6 +1721,7 @@ int hmcb_finalize(hmcb_engine* e) {
         if (e->dpad == 128 && dev_upload_padded(e, e->h_A.data(), d, d, 128, 128, &e->dA_rowmajor)) return -1;
         if (dev_upload(e, e->h_vec, &tmp)) return -1;
         e->dvec = const_cast<double*>(tmp);
+        if (oz_setup(e)) return -1;
         e->ltiles = e->dpad / GEMM_BM;
         break;
       case LK_DENSE_DIRECT:
@@ -1770,9 +1793,9 @@ int hmcb_path(const hmcb_engine* e) {
 }
 int hmcb_dense_products_on_tcgen05(const hmcb_engine* e) {
   if (!e || !e->oz) return 0;
-  // slice pairs of the two products of one gradient evaluation: digits s of the matrix, t of the batch, s + t < orders
+  // slice pairs of the products of one gradient evaluation (two in the direct form, one premultiplied): digits s of the matrix, t of the batch, s + t < orders
   int pairs = 0;
-  for (int sa : {e->oz_saG, e->oz_saGt})
+  for (int sa : {e->oz_saG, e->lik == LK_DENSE_PREMULT ? 0 : e->oz_saGt})
     for (int a = 0; a < sa; ++a)
       for (int b = 0; b < e->oz_sb; ++b) pairs += (a + b < e->oz_orders) ? 1 : 0;
   return pairs;

@@ -170,3 +170,18 @@ def test_gathered_slice_products_are_exact(N, kblocks, SA, SB, orders):
                 if s + t < orders:
                     ref[s + t, b * 128:(b + 1) * 128] += A[s][:, sl].double() @ B[t][rows].double()
     assert torch.equal(out.double(), ref)
+
+
+@pytest.mark.parametrize("premult", [False, True])
+def test_ozaki_path_at_config3_shape_vs_oracle(monkeypatch, premult):
+    """A scaled config-3 problem (333 parameters x 700 data, 130 chains, 4-stage) with the tcgen05 path
+    forced on, both forms of the dense LinearMatrix: the direct products G q / G^T r and the premultiplied
+    GtG q (an fp64-valued operator: six digits), checked against the oracle like the full-size tests."""
+    from hmclab_b200 import workloads
+    from test_gpu_fullsize import _compare_with_oracle
+
+    monkeypatch.setenv("HMCB_OZAKI", "1")
+    w = workloads.dense_large(dims=333, data=700, chains=130, premultiplication=premult)
+    eng, _ = _compare_with_oracle(w, K=2)
+    assert eng.path == "staged" and eng.tcgen05_slice_pairs > 0
+    assert (eng.tcgen05_slice_pairs <= 21) == premult       # one product premultiplied, two in the direct form
