@@ -543,7 +543,7 @@ def bench_workload(ctx, name, steps, warmup, block=0, chains=0):
             pairs = oz_pairs                      # slice products of G q and G^T r together (premultiplied: of GtG q)
             # int8 operations per slice product and chain: 2 N d (half the 4 N d flops of the direct form's two
             # products), or 2 d^2 = all the flops of the premultiplied form's single product
-            per_product = flops if w.extra.get("form") == "premultiplied" else flops / 2.0
+            per_product = flops if w.extra.get("form") == "premult" else flops / 2.0
             i8_ops = pairs * per_product * C
             measured = committed_json("../MEASURED_PEAKS.json")
             sustained = measured.get("bf16_tflops_sustained") if ms_per_step > 50 else measured.get("bf16_tflops")
