@@ -11,9 +11,12 @@ import argparse
 import os
 import tempfile
 
+import sys
+
 import numpy as np
 
-import hmclab_b200 as hmclab
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # run from a checkout
+import hmclab_b200 as hmclab  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--chains", type=int, default=4096)
