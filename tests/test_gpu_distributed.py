@@ -112,3 +112,62 @@ def test_replica_exchange_across_two_gpus_equals_single_gpu_run(tmp_path):
         one = np.load(tmp_path / "single" / f"chain{i}.npy")
         two = np.load(tmp_path / "dist" / f"chain{i}.npy")
         assert one.shape == (30, 13) and np.array_equal(one, two), i
+
+
+GOLDEN_EXCHANGE_WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+sys.path.insert(0, os.path.join({root!r}, "tests"))
+from test_gpu_distributed import reference_exchange_run
+local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+reference_exchange_run({out!r})
+dist.destroy_process_group()
+'''
+
+
+def reference_exchange_run(out_dir):
+    """The reference's own ParallelSampleSMP run of tests/golden/exchange_runs.npz (two posteriors, four
+    chains, host random streams in the reference's order) on whatever process group is initialised."""
+    from hmclab_b200 import Distributions as D
+    from hmclab_b200.Samplers import HMC, ParallelSampleSMP
+
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "exchange_runs.npz"))
+    st = {k[len("setting_"):]: gold[k] for k in gold.files if k.startswith("setting_")}
+    n = int(st["chains"])
+    mean, var = gold["mean"][:, None], gold["var"][:, None]
+    cold, hot = D.Normal(mean, var), D.Normal(mean + 0.3, 3.0 * var)
+    names = [os.path.join(out_dir, f"gold_chain{i}.npy") for i in range(n)]
+    smp = ParallelSampleSMP(seed=int(st["smp_seed"]))
+    smp.sample([HMC(seed=int(s)) for s in st["sampler_seeds"]], names, [cold, hot, cold, hot],
+               overwrite_existing_files=True, proposals=int(st["proposals"]), exchange=True,
+               exchange_interval=int(st["exchange_interval"]), initial_model=[q[:, None] for q in gold["q0"]],
+               kwargs=dict(stepsize=float(st["stepsize"]), amount_of_steps=int(st["amount_of_steps"]),
+                           integrator=str(st["integrator"]), randomize_stepsize=bool(st["randomize_stepsize"]),
+                           online_thinning=int(st["online_thinning"]), disable_progressbar=True, host_rng=True))
+    return gold, names
+
+
+def test_reference_exchange_run_is_reproduced_across_two_gpus(tmp_path):
+    """The unmodified reference's multi-process replica-exchange run (golden) reproduced with the cold chains
+    on one GPU and the hot chains on the other: every swap crosses the NVLink, the masters' acceptance
+    uniforms come from the owning rank's sampler generators (all-reduced), and every file matches the
+    reference's to 1e-10."""
+    import torch
+
+    from helpers import rel_err
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "gold_exchange_worker.py"
+    script.write_text(GOLDEN_EXCHANGE_WORKER.format(root=ROOT, out=str(tmp_path)))
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                           "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                           "--master-port", "29545", str(script)], cwd=ROOT)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "exchange_runs.npz"))
+    for i in range(int(gold["setting_chains"])):
+        got, ref = np.load(tmp_path / f"gold_chain{i}.npy"), gold[f"samples{i}"]
+        assert got.shape == ref.shape and rel_err(got, ref) < 1e-10, i
