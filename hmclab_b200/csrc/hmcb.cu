@@ -831,6 +831,16 @@ int oz_setup(hmcb_engine* e) {
   if (premult && e->dpad == 128) return 0;      // the whole-proposal kernel with GtG in shared memory owns that size
   for (double v : e->h_A) if (!std::isfinite(v)) return 0;
   for (double v : e->h_At) if (!std::isfinite(v)) return 0;
+  if (want < 0) {
+    // The digits of a chain are cut 48 bits below the CHAIN's largest |value|.  With a fully populated
+    // operator every output mixes all coordinates and that is far below its own rounding; an operator with
+    // structural zeros (block structure) can have rows that only see coordinates many orders of magnitude
+    // below the chain's largest one, which the native fp64 path keeps and this one would lose: such
+    // operators stay on DMMA unless the path is forced.
+    size_t zeros = 0;
+    for (double v : e->h_A) zeros += v == 0.0;
+    if (zeros * 100 > e->h_A.size()) return 0;
+  }
   const int d = (int)e->d;
   if (oz_upload_matrix(e, e->h_A.data(), premult ? d : e->N, d, e->oz_rows, e->dpad, e->oz_orders, &e->oz_saG, &e->oz_AG,
                        &e->oz_eaG))
