@@ -65,6 +65,8 @@ SIGNATURES = {
     "hmcb_set_mass_full": (C.c_int, [C.c_void_p, _c_double_p, _c_double_p]),
     "hmcb_debug_i8_gemm": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmcb_debug_crt_product": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, _c_double_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
     "hmcb_debug_i8_gather_gemm": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p]),

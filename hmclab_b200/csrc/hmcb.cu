@@ -89,6 +89,11 @@ struct hmcb_engine {
   int oz_saG = 0, oz_saGt = 0;         // int8 digits of G / G^T (what their rows need, at most the orders kept)
   int oz_sb = OZ_SLICES_B, oz_orders = OZ_NUM_ORDERS;   // digits of the chain batch, orders kept
   int64_t oz_rows = 0;                                  // padded rows of the forward operator (npad, or dpad when premultiplied)
+  // modular variant for G^T r (long contraction): residue planes of G^T, of the chain batch, of the product
+  bool oz_crt = false;
+  signed char *oz_crtA = nullptr, *oz_crtB = nullptr, *oz_crtC = nullptr;
+  int* oz_crt_ea = nullptr;
+  CUtensorMap oz_mapCrtA, oz_mapCrtB, oz_mapCrtBh;
   signed char *oz_AG = nullptr, *oz_AGt = nullptr, *oz_B = nullptr;   // int8 slices of G, G^T, the chain batch
   int *oz_eaG = nullptr, *oz_eaGt = nullptr, *oz_C = nullptr;         // row exponents, int32 order planes
   unsigned long long *oz_maxQ = nullptr, *oz_maxR = nullptr;          // per-chain max |.| (bit patterns)
@@ -856,6 +861,25 @@ int oz_setup(hmcb_engine* e) {
   HMCB_CUDA(ozaki_slice_map(e->oz_B, e->dpad, e->ld, e->oz_sb, 256, &e->oz_mapBq));
   HMCB_CUDA(ozaki_slice_map(e->oz_B, e->dpad, e->ld, e->oz_sb, 128, &e->oz_mapBqh));   // half tiles: CTA pairs
   HMCB_CUDA(ozaki_plane_map(e->oz_C, e->ld, e->oz_rows, e->oz_orders, (long long)e->oz_rows * e->ld, &e->oz_mapCq));
+  // G^T r as 13 modular products + Chinese-remainder reconstruction instead of 21 digit products: opt-in
+  // (HMCB_OZAKI_CRT=1).  Measured at config 3: 2.14 ms against 2.39 ms for the products, but no two modular
+  // products share an operand tile (2 tile loads per product instead of 1.1: the L2 -> SM feed binds, tensor
+  // pipe 48 % active) and reducing the chain batch modulo 13 moduli costs 0.73 ms against 0.21 ms of digit
+  // slicing -- 3.1 ms against 2.8 ms for the whole G^T r side.
+  e->oz_crt = !premult && env_int("HMCB_OZAKI_CRT", 0) > 0 && e->npad * 128ll * 128ll < (1ll << 31) && e->npad < 40000;
+  if (e->oz_crt) {
+    std::vector<signed char> res((size_t)OZ_NUM_MODULI * e->dpad * e->npad);
+    std::vector<int> ea((size_t)e->dpad);
+    oz_residue_rows_host(e->h_At.data(), d, e->N, e->dpad, e->npad, res.data(), ea.data());
+    const signed char* pa = nullptr; const int* pe = nullptr;
+    if (dev_upload(e, res, &pa) || dev_upload(e, ea, &pe)) return -1;
+    e->oz_crtA = const_cast<signed char*>(pa); e->oz_crt_ea = const_cast<int*>(pe);
+    if (dev_alloc(e, (size_t)OZ_NUM_MODULI * e->ld * e->npad, &e->oz_crtB) ||
+        dev_alloc(e, (size_t)OZ_NUM_MODULI * e->dpad * e->ld, &e->oz_crtC)) return -1;
+    HMCB_CUDA(ozaki_slice_map(e->oz_crtA, e->npad, e->dpad, OZ_NUM_MODULI, 128, &e->oz_mapCrtA));
+    HMCB_CUDA(ozaki_slice_map(e->oz_crtB, e->npad, e->ld, OZ_NUM_MODULI, 256, &e->oz_mapCrtB));
+    HMCB_CUDA(ozaki_slice_map(e->oz_crtB, e->npad, e->ld, OZ_NUM_MODULI, 128, &e->oz_mapCrtBh));
+  }
   if (!premult) {
     HMCB_CUDA(ozaki_slice_map(e->oz_AGt, e->npad, e->dpad, e->oz_saGt, 128, &e->oz_mapAGt));
     HMCB_CUDA(ozaki_slice_map(e->oz_B, e->npad, e->ld, e->oz_sb, 256, &e->oz_mapBr));
@@ -934,6 +958,15 @@ int staged_gradient_pass(hmcb_engine* e, const double* q_in, UpdateEpi epi, cuda
         if (oz_forward_product(e, q_in, s)) return -1;
         HMCB_CUDA(launch_oz_combine_residual(e->oz_C, plane_q, e->npad, e->ld, e->oz_orders, e->oz_eaG, e->oz_maxQ, r,
                                              e->oz_maxR, s));
+        if (e->oz_crt) {   // residues of R, 13 modular products, Chinese-remainder reconstruction + update
+          HMCB_CUDA(launch_oz_residue_chains(e->R, (int)e->npad, e->ld, e->oz_maxR, e->oz_crtB, s));
+          HMCB_CUDA(launch_i8_gemm_moduli(e->oz_mapCrtA, e->oz_mapCrtB, e->oz_mapCrtBh, e->dpad, e->ld, e->npad, e->ld,
+                                          e->oz_crtC, s));
+          HMCB_CUDA(launch_oz_crt_update(e->oz_crtC, (long long)e->dpad * e->ld, (int)e->dpad, e->ld, e->oz_crt_ea,
+                                         e->oz_maxR, epi, s));
+          e->launches += 4;
+          break;
+        }
         HMCB_CUDA(launch_oz_slice_chains(e->R, e->npad, e->ld, e->oz_sb, e->oz_maxR, e->oz_B, s));
         HMCB_CUDA(launch_i8_gemm_orders(e->oz_mapAGt, e->oz_mapBr, e->oz_mapBrh, e->oz_mapCr, e->dpad, e->ld, e->npad, e->oz_saGt,
                                         e->oz_sb, e->oz_orders, e->ld, s));
@@ -1805,10 +1838,10 @@ int hmcb_dense_products_on_tcgen05(const hmcb_engine* e) {
   if (!e || !e->oz) return 0;
   // slice pairs of the products of one gradient evaluation (two in the direct form, one premultiplied): digits s of the matrix, t of the batch, s + t < orders
   int pairs = 0;
-  for (int sa : {e->oz_saG, e->lik == LK_DENSE_PREMULT ? 0 : e->oz_saGt})
+  for (int sa : {e->oz_saG, (e->lik == LK_DENSE_PREMULT || e->oz_crt) ? 0 : e->oz_saGt})
     for (int a = 0; a < sa; ++a)
       for (int b = 0; b < e->oz_sb; ++b) pairs += (a + b < e->oz_orders) ? 1 : 0;
-  return pairs;
+  return pairs + (e->oz_crt ? OZ_NUM_MODULI : 0);   // G^T r as modular products
 }
 int64_t hmcb_grads_per_proposal(const hmcb_engine* e) { return e ? e->S.grads_per_proposal : -1; }
 int64_t hmcb_launch_count(const hmcb_engine* e) { return e ? e->launches : -1; }

@@ -129,6 +129,15 @@ cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& ma
                                   int orders, int ldc, cudaStream_t s);
 
 struct OzBundle;
+cudaError_t launch_i8_gemm_moduli(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBh,
+                                  long long M, long long N, long long K, int ldc, signed char* res, cudaStream_t s);
+void oz_residue_rows_host(const double* A, long long rows, long long cols, long long rows_pad, long long cols_pad,
+                          signed char* res, int* ea);
+cudaError_t launch_oz_residue_chains(const double* X, int K, int ld, const unsigned long long* maxbits, signed char* out,
+                                     cudaStream_t s);
+cudaError_t launch_oz_crt_update(const signed char* res, long long plane, int rows, int ld, const int* ea,
+                                 const unsigned long long* maxbits_in, const UpdateEpi& epi, cudaStream_t s);
+constexpr int OZ_NUM_MODULI = 13;
 struct OzPlan;
 bool oz_build_plan(int SA, int SB, int orders, long long M, long long N, OzPlan* plan);
 cudaError_t ozaki_sparse_init();

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "launch.cuh"
 #include "ozaki.cuh"
@@ -57,11 +58,18 @@ cudaError_t ozaki_plane_map(const int* base, long long ldc, long long M, int ord
 }
 
 cudaError_t ozaki_init() {
-  cudaError_t e = cudaFuncSetAttribute(i8_gemm_groups_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(i8_gemm_groups_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)OZ_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(i8_gemm_groups_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)OZ_SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(i8_gemm_groups_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)OZ_SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(i8_gemm_groups_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)OZ_SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(i8_gemm_groups_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)OZ_SMEM_BYTES);
+  return e;
 }
 
 // CTA pairs (tcgen05 cta_group::2) unless HMCB_OZAKI_PAIR=0
@@ -128,22 +136,17 @@ bool oz_build_plan(int SA, int SB, int orders, long long M, long long N, OzPlan*
   return true;
 }
 
-// C[o] (o < orders) = sum_{s+t=o} A_s B_t^T;  M % 128 == 0, K % 128 == 0, ldc = padded N (% 128 == 0);
-// mapB: box of 256 rows (one CTA per tile), mapBh: box of 128 rows (CTA pairs: each CTA loads half a B tile);
-// mapC = ozaki_plane_map of the order planes
-cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBh,
-                                  const CUtensorMap& mapC, long long M, long long N, long long K, int SA, int SB,
-                                  int orders, int ldc, cudaStream_t s) {
-  if (M % OZ_BM || K % OZ_BK || N % 128) return cudaErrorInvalidValue;
-  OzPlan plan;
-  if (!oz_build_plan(SA, SB, orders, M, N, &plan)) return cudaErrorInvalidValue;
+template <bool RESIDUES>
+static cudaError_t launch_i8_plan(const OzPlan& plan, const CUtensorMap& mapA, const CUtensorMap& mapB,
+                                  const CUtensorMap& mapBh, const CUtensorMap& mapC, long long M, long long K, int ldc,
+                                  signed char* res, long long res_plane, cudaStream_t s) {
   const bool pair = ozaki_pair_mode();
   const long long rows_m = pair ? (plan.tiles_m + 1) / 2 : plan.tiles_m;
   const long long ctas = (long long)plan.n_groups * rows_m * plan.tiles_n * (pair ? 2 : 1);
   if (ctas <= 0 || ctas > 0x7fffffffll) return cudaErrorInvalidValue;
   if (!pair) {
-    i8_gemm_groups_kernel<false><<<(unsigned)ctas, OZ_THREADS, OZ_SMEM_BYTES, s>>>(mapA, mapB, mapC, plan,
-                                                                                  (int)(K / OZ_BK), ldc, (int)M);
+    i8_gemm_groups_kernel<false, RESIDUES><<<(unsigned)ctas, OZ_THREADS, OZ_SMEM_BYTES, s>>>(
+        mapA, mapB, mapC, plan, (int)(K / OZ_BK), ldc, (int)M, res, res_plane);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg = {};
@@ -156,7 +159,46 @@ cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& ma
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, i8_gemm_groups_kernel<true>, mapA, mapBh, mapC, plan, (int)(K / OZ_BK), ldc, (int)M);
+  return cudaLaunchKernelEx(&cfg, i8_gemm_groups_kernel<true, RESIDUES>, mapA, mapBh, mapC, plan, (int)(K / OZ_BK), ldc,
+                            (int)M, res, res_plane);
+}
+
+// C[o] (o < orders) = sum_{s+t=o} A_s B_t^T;  M % 128 == 0, K % 128 == 0, ldc = padded N (% 128 == 0);
+// mapB: box of 256 rows (one CTA per tile), mapBh: box of 128 rows (CTA pairs: each CTA loads half a B tile);
+// mapC = ozaki_plane_map of the order planes
+cudaError_t launch_i8_gemm_orders(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBh,
+                                  const CUtensorMap& mapC, long long M, long long N, long long K, int SA, int SB,
+                                  int orders, int ldc, cudaStream_t s) {
+  if (M % OZ_BM || K % OZ_BK || N % 128) return cudaErrorInvalidValue;
+  OzPlan plan;
+  if (!oz_build_plan(SA, SB, orders, M, N, &plan)) return cudaErrorInvalidValue;
+  return launch_i8_plan<false>(plan, mapA, mapB, mapBh, mapC, M, K, ldc, nullptr, 0, s);
+}
+
+// Modular products: res[m] = (A_m B_m^T) mod p_m for the OZ_NMOD residue planes of A (mapA: {K, M, OZ_NMOD}) and
+// B; two moduli per CTA (two accumulators; no tile is shared between moduli).  res: [OZ_NMOD][M x ldc] int8.
+cudaError_t launch_i8_gemm_moduli(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapBh,
+                                  long long M, long long N, long long K, int ldc, signed char* res, cudaStream_t s) {
+  if (M % OZ_BM || K % OZ_BK || N % 128 || K * 128 * 128 >= (1ll << 31)) return cudaErrorInvalidValue;
+  OzPlan plan;
+  std::memset(&plan, 0, sizeof(plan));
+  plan.tiles_m = (int)(M / OZ_BM);
+  plan.tiles_n = (int)((N + OZ_BN - 1) / OZ_BN);
+  for (int m = 0; m < OZ_NMOD; m += 2) {
+    OzProgram& P = plan.g[plan.n_groups++];
+    P.n_acc = m + 1 < OZ_NMOD ? 2 : 1;
+    for (int a = 0; a < P.n_acc; ++a) {
+      P.order[a] = m + a;                                   // the plane / modulus of accumulator a
+      P.load_is_b[P.n_loads] = 1; P.load_slice[P.n_loads++] = (unsigned char)(m + a);
+      P.load_is_b[P.n_loads] = 0; P.load_slice[P.n_loads++] = (unsigned char)(m + a);
+      P.mma_a[P.n_mma] = (unsigned char)a; P.mma_b[P.n_mma] = (unsigned char)a; P.mma_acc[P.n_mma] = (unsigned char)a;
+      P.mma_flags[P.n_mma++] = 1 | 2 | 4;                   // last use of both tiles, first product of its accumulator
+    }
+    P.nA = P.nB = P.n_acc;
+  }
+  CUtensorMap unused;
+  std::memset(&unused, 0, sizeof(unused));
+  return launch_i8_plan<true>(plan, mapA, mapB, mapBh, unused, M, K, ldc, res, M * (long long)ldc, s);
 }
 
 cudaError_t launch_oz_colmax(const double* X, int rows, int ld, unsigned long long* maxbits, cudaStream_t s) {
@@ -272,6 +314,128 @@ extern "C" double hmcb_debug_oz_slice_rows(const double* A, int64_t rows, int64_
                                            int32_t* ea) {
   if (!A || !ea || rows <= 0 || cols <= 0 || S < 1 || S > hmcb::OZ_MAX_SLICES) return -1.0;
   return hmcb::oz_slice_rows_host(A, rows, cols, rows, cols, S, slices, ea);
+}
+
+// ---- modular variant: host side -----------------------------------------------------------------------
+namespace hmcb {
+
+static const int kOzMod[OZ_NMOD] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211};
+
+// the reconstruction constants: f_m = y_m / p_m in three 40-bit chunks, y_m = (P / p_m)^-1 mod p_m; P as a double
+OzCrt oz_crt_constants() {
+  OzCrt c;
+  c.P = 1.0;
+  for (int m = 0; m < OZ_NMOD; ++m) c.P *= (double)kOzMod[m];
+  for (int m = 0; m < OZ_NMOD; ++m) {
+    const int p = kOzMod[m];
+    int Mm = 1;
+    for (int j = 0; j < OZ_NMOD; ++j)
+      if (j != m) Mm = (int)(((long long)Mm * (kOzMod[j] % p)) % p);
+    int y = 1;
+    while ((Mm * y) % p != 1) ++y;
+    long long rem = y;
+    for (int j = 0; j < 3; ++j) {
+      const long long num = rem << 40;          // rem < 256
+      c.F[m][j] = (double)(num / p);
+      rem = num % p;
+    }
+  }
+  return c;
+}
+
+static int sym_mod(long long X, int p) {
+  int r = (int)(X % p);
+  if (r < 0) r += p;
+  return r > 127 ? r - p : r;
+}
+
+// Residue planes of a row-major HOST matrix [rows x cols], zero padded to [rows_pad x cols_pad]: every row scaled
+// to 44-bit integers (exponent ea[i] as in oz_slice_rows_host), res[m][i][k] = that integer modulo p_m in [-128, 127].
+void oz_residue_rows_host(const double* A, long long rows, long long cols, long long rows_pad, long long cols_pad,
+                          signed char* res, int* ea) {
+  std::memset(res, 0, (size_t)OZ_NMOD * rows_pad * cols_pad);
+  std::memset(ea, 0, sizeof(int) * (size_t)rows_pad);
+  const double up = std::ldexp(1.0, OZ_CRT_BITS);
+  for (long long i = 0; i < rows; ++i) {
+    const double* a = A + (size_t)i * cols;
+    double mx = 0.0;
+    for (long long k = 0; k < cols; ++k) mx = std::max(mx, std::fabs(a[k]));
+    unsigned long long bits;
+    std::memcpy(&bits, &mx, sizeof(bits));
+    const int e = oz_exponent(bits);
+    if (e == INT_MIN || !(mx > 0.0)) continue;
+    ea[i] = e;
+    for (long long k = 0; k < cols; ++k) {
+      const long long X = (long long)std::nearbyint(oz_scale_down(a[k], e) * up);
+      for (int m = 0; m < OZ_NMOD; ++m) res[((size_t)m * rows_pad + i) * cols_pad + k] = (signed char)sym_mod(X, kOzMod[m]);
+    }
+  }
+}
+
+cudaError_t launch_oz_residue_chains(const double* X, int K, int ld, const unsigned long long* maxbits, signed char* out,
+                                     cudaStream_t s) {
+  if (K % 128 || ld % 16) return cudaErrorInvalidValue;
+  oz_residue_chains_kernel<<<dim3(ld / 16, K / 128), 256, 0, s>>>(X, K, ld, maxbits, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_oz_crt_update(const signed char* res, long long plane, int rows, int ld, const int* ea,
+                                 const unsigned long long* maxbits_in, const UpdateEpi& epi, cudaStream_t s) {
+  static const OzCrt crt = oz_crt_constants();
+  oz_crt_combine_kernel<UpdateEpi, 16><<<dim3((ld / 4 + 127) / 128, (rows + 15) / 16), 128, 0, s>>>(
+      res, plane, rows, ld, ea, maxbits_in, crt, epi);
+  return cudaGetLastError();
+}
+
+struct RawStoreEpi {     // Y -> out[i][c] (tests)
+  double* out; int ld;
+  __device__ __forceinline__ void row(int i, int c, double y) const { out[(size_t)i * ld + c] = y; }
+};
+
+}  // namespace hmcb
+
+// Test entry of the modular variant: Y = A X for HOST A [M x K] (row-major) and DEVICE chain batch X [K x N]
+// (chains contiguous): residues of A on the host, of X on the device, 13 modular int8 products on tcgen05,
+// Chinese-remainder reconstruction -> DEVICE Y [M x N] fp64.  M, K % 128 == 0, N % 128 == 0.
+extern "C" int hmcb_debug_crt_product(int device, int64_t M, int64_t N, int64_t K, const double* A_host,
+                                      const double* X_dev, double* Y_dev, void* stream) {
+  using namespace hmcb;
+  if (!A_host || !X_dev || !Y_dev || M <= 0 || N <= 0 || K <= 0 || M % 128 || K % 128 || N % 128) return -1;
+  if (cudaSetDevice(device) != cudaSuccess) return -1;
+  if (ozaki_init() != cudaSuccess) return -2;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::vector<signed char> resA((size_t)OZ_NMOD * M * K);
+  std::vector<int> ea((size_t)M);
+  oz_residue_rows_host(A_host, M, K, M, K, resA.data(), ea.data());
+  signed char *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  int* dea = nullptr;
+  unsigned long long* dmax = nullptr;
+  int rc = 0;
+  if (cudaMalloc(&dA, resA.size()) != cudaSuccess || cudaMalloc(&dB, (size_t)OZ_NMOD * N * K) != cudaSuccess ||
+      cudaMalloc(&dC, (size_t)OZ_NMOD * M * N) != cudaSuccess || cudaMalloc(&dea, sizeof(int) * M) != cudaSuccess ||
+      cudaMalloc(&dmax, sizeof(unsigned long long) * N) != cudaSuccess)
+    rc = -3;
+  CUtensorMap mapA, mapB, mapBh;
+  if (!rc && (cudaMemcpyAsync(dA, resA.data(), resA.size(), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+              cudaMemcpyAsync(dea, ea.data(), sizeof(int) * M, cudaMemcpyHostToDevice, s) != cudaSuccess))
+    rc = -3;
+  if (!rc && (ozaki_slice_map(dA, K, M, OZ_NMOD, OZ_BM, &mapA) != cudaSuccess ||
+              ozaki_slice_map(dB, K, N, OZ_NMOD, OZ_BN, &mapB) != cudaSuccess ||
+              ozaki_slice_map(dB, K, N, OZ_NMOD, OZ_BN / 2, &mapBh) != cudaSuccess))
+    rc = -3;
+  if (!rc && (launch_oz_colmax(X_dev, (int)K, (int)N, dmax, s) != cudaSuccess ||
+              launch_oz_residue_chains(X_dev, (int)K, (int)N, dmax, dB, s) != cudaSuccess ||
+              launch_i8_gemm_moduli(mapA, mapB, mapBh, M, N, K, (int)N, dC, s) != cudaSuccess))
+    rc = -4;
+  if (!rc) {
+    static const OzCrt crt = oz_crt_constants();
+    RawStoreEpi st{Y_dev, (int)N};
+    oz_crt_combine_kernel<RawStoreEpi, 16><<<dim3((unsigned)((N / 4 + 127) / 128), (unsigned)((M + 15) / 16)), 128, 0, s>>>(
+        dC, M * N, (int)M, (int)N, dea, dmax, crt, st);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) rc = -5;
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dea); cudaFree(dmax);
+  return rc;
 }
 
 // ---- gathered (block-sparse) slice products (ozaki_sparse.cuh) ------------------------------------------

@@ -48,7 +48,21 @@ constexpr size_t OZ_SMEM_BYTES = (size_t)OZ_NA * OZ_A_BYTES + (size_t)OZ_NB * OZ
 constexpr int OZ_THREADS = 256;    // warp 0: TMA (A), warp 1: MMA, warp 2: TMEM allocation, warp 3: TMA (B), warps 4-7: epilogue
 constexpr int OZ_BITS = 8;         // bits per slice (balanced digits in [-128, 127])
 constexpr int OZ_MAX_SLICES = 7, OZ_MAX_ORDERS = 7;
-constexpr int OZ_MAX_ACC = 2, OZ_MAX_OPS = 16, OZ_MAX_GROUPS = 4, OZ_PANEL = 8;
+constexpr int OZ_MAX_ACC = 2, OZ_MAX_OPS = 16, OZ_MAX_GROUPS = 8, OZ_PANEL = 8;
+
+// Modular variant ("Ozaki II") for products with a long contraction: the operands are scaled to 44-bit
+// integers, multiplied modulo 13 pairwise coprime moduli <= 256 (one exact int8 product each, residues in
+// [-128, 127]) and the integer product is rebuilt from its residues (Chinese remainder theorem): 13 slice
+// products instead of 21 for 2^-44 instead of 2^-48 of the row / chain maximum.  P = prod p = 2^102.5 must
+// exceed 2 K 2^86: K < 46 000.
+constexpr int OZ_NMOD = 13, OZ_CRT_BITS = 44;
+__constant__ int c_oz_mod[OZ_NMOD] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211};
+// symmetric residue of an integer-valued double |x| < 2^52 modulo p (any representative in [-128, 127])
+__device__ __forceinline__ int oz_residue(double x, int p) {
+  const double q = rint(x * (1.0 / (double)p));
+  int r = (int)fma(-q, (double)p, x);         // |r| <= (p + 1) / 2: the quotient may be off by one
+  return r > 127 ? r - p : r;
+}
 
 // The dataflow program of one order group, the same for every k-block (built by oz_build_plan)
 struct OzProgram {
@@ -108,11 +122,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {   // arrives when t
 // 16 KB + 32 KB: a third less L2 -> SM traffic (the path that caps the single-CTA kernel) and half the
 // shared-memory reads of B.  Both CTAs load (their TMA completes on the LEADER's full barrier, which expects the
 // bytes of both), the leader's commits arrive on the empty barriers of both.
-template <bool PAIR>
+// RESIDUES = true: the accumulators hold products modulo c_oz_mod[P.order[a]]; the epilogue reduces them and
+// stores int8 residue planes res[modulus][m_rows x ldc] directly (mapC unused).
+template <bool PAIR, bool RESIDUES>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 i8_gemm_groups_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                       const __grid_constant__ CUtensorMap mapC, const __grid_constant__ OzPlan plan, int kblocks,
-                      int ldc, int m_rows) {
+                      int ldc, int m_rows, signed char* __restrict__ res, long long res_plane) {
   constexpr int NB = PAIR ? 2 * OZ_NB : OZ_NB, B_BYTES = PAIR ? OZ_B_BYTES / 2 : OZ_B_BYTES;
   extern __shared__ __align__(1024) unsigned char oz_smem[];
   __shared__ uint64_t fullA[OZ_NA], emptyA[OZ_NA], fullB[NB], emptyB[NB], tmem_full_bar;
@@ -249,6 +265,26 @@ i8_gemm_groups_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
               "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr + (uint32_t)c));
+        if constexpr (RESIDUES) {
+          // lane = row: its 32 columns reduced modulo the accumulator's modulus, packed into 32 bytes
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+          const int pm = c_oz_mod[P.order[a]];
+          unsigned w[8];
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            unsigned word = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              word |= ((unsigned)oz_residue((double)(int)r[4 * v + j], pm) & 255u) << (8 * j);
+            w[v] = word;
+          }
+          if (row0 + lane < m_rows) {
+            uint4* dst = reinterpret_cast<uint4*>(res + (size_t)P.order[a] * res_plane + (size_t)(row0 + lane) * ldc + n0 + c);
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+          continue;
+        }
         if (it >= 2) {   // the buffer written two blocks ago must have been read by its store
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
           __syncwarp();
@@ -386,6 +422,95 @@ oz_slice_chains_kernel(const double* __restrict__ X, int K, int ld, int SB, cons
     const int t = row >> 5, ch = row & 31;
     const unsigned v = *reinterpret_cast<const unsigned*>(&sl[t][ch][lane * 4]);
     *reinterpret_cast<unsigned*>(out + ((size_t)t * ld + c0 + ch) * K + k0 + lane * 4) = v;
+  }
+}
+
+// ---- modular variant: residues of the chain batch, reconstruction from the residue planes -------------
+
+// X [K x ld] (chains contiguous) -> OZ_NMOD residue planes, chain-major [m][ld][K] (K contiguous): every value
+// scaled to a 44-bit integer (per-chain exponent as above) and reduced modulo each modulus.  Block = 128 k x 16
+// chains, transposed through shared memory (a thread reduces four consecutive k of its chain and packs each
+// plane's four residues into one word).
+__global__ void __launch_bounds__(256)
+oz_residue_chains_kernel(const double* __restrict__ X, int K, int ld, const unsigned long long* __restrict__ maxbits,
+                         signed char* __restrict__ out) {
+  __shared__ __align__(16) signed char sl[OZ_NMOD][16][132];
+  const int k0 = blockIdx.y * 128, c0 = blockIdx.x * 16;
+  const int tc = threadIdx.x & 15, tr = threadIdx.x >> 4;
+  const int eb = oz_exponent(maxbits[c0 + tc]);
+  const double up = oz_pow2(OZ_CRT_BITS);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = (tr + 16 * h) * 4;
+    double xi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double x = (k0 + r + i < K) ? __ldcs(X + (size_t)(k0 + r + i) * ld + c0 + tc) : 0.0;
+      xi[i] = eb != INT_MIN ? rint(oz_scale_down(x, eb) * up) : 0.0;      // |xi| < 2^43, an integer
+    }
+#pragma unroll
+    for (int m = 0; m < OZ_NMOD; ++m) {
+      unsigned word = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int res = m == 0 ? (int)(signed char)(__double2ll_rn(xi[i]) & 255ll) : oz_residue(xi[i], c_oz_mod[m]);
+        word |= ((unsigned)res & 255u) << (8 * i);
+      }
+      *reinterpret_cast<unsigned*>(&sl[m][tc][r]) = word;
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = warp; row < OZ_NMOD * 16; row += 8) {
+    const int m = row >> 4, ch = row & 15;
+    const unsigned v = *reinterpret_cast<const unsigned*>(&sl[m][ch][lane * 4]);
+    *reinterpret_cast<unsigned*>(out + ((size_t)m * ld + c0 + ch) * K + k0 + lane * 4) = v;
+  }
+}
+
+// Chinese remainder reconstruction.  x = sum_m c_m W_m mod P with W_m / P = y_m / p_m (y_m the inverse of P / p_m
+// modulo p_m): x / P = frac(sum_m c_m f_m), f_m = y_m / p_m held as three 40-bit chunks, so that the three sums
+// of at most 13 products |c| 2^40 are exact in fp64 and the fractional part is good to 2^-109.
+struct OzCrt { double F[OZ_NMOD][3]; double P; };
+
+// Y[i][c] = 2^(ea[i] + eb[c] - 88) x[i][c], x rebuilt from the residue planes res[m][rows x ld] -> epilogue
+// functor (row interface as oz_combine_kernel); a thread handles four neighbouring chains (one word per plane)
+template <class Epi, int ROWS>
+__global__ void __launch_bounds__(128)
+oz_crt_combine_kernel(const signed char* __restrict__ res, long long plane, int rows, int ld,
+                      const int* __restrict__ ea, const unsigned long long* __restrict__ maxbits_in,
+                      const __grid_constant__ OzCrt crt, Epi epi) {
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (c >= ld) return;
+  int eb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) eb[j] = oz_exponent(maxbits_in[c + j]);
+  const int r1 = min(rows, ((int)blockIdx.y + 1) * ROWS);
+  Epi fn = epi;
+  for (int i = blockIdx.y * ROWS; i < r1; ++i) {
+    unsigned w[OZ_NMOD];
+#pragma unroll
+    for (int m = 0; m < OZ_NMOD; ++m)
+      w[m] = __ldcs(reinterpret_cast<const unsigned*>(res + (size_t)m * plane + (size_t)i * ld + c));
+    const int ei = ea[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int m = 0; m < OZ_NMOD; ++m) {
+        const double cm = (double)(int)(signed char)((w[m] >> (8 * j)) & 255u);
+        s0 = fma(cm, crt.F[m][0], s0); s1 = fma(cm, crt.F[m][1], s1); s2 = fma(cm, crt.F[m][2], s2);
+      }
+      const double u = s0 * 0x1p-40;                       // exact; its fractional part is a multiple of 2^-40
+      const double frac = (u - rint(u)) + (s1 * 0x1p-80 + s2 * 0x1p-120);
+      double y;
+      if (eb[j] == INT_MIN) y = CUDART_NAN;
+      else {
+        const int e = ei + eb[j] - 2 * OZ_CRT_BITS, h = e / 2;
+        y = (frac - rint(frac)) * crt.P * oz_pow2(h) * oz_pow2(e - h);
+      }
+      fn.row(i, c + j, y);
+    }
   }
 }
 

@@ -103,6 +103,12 @@ int hmcb_set_mass_full(hmcb_engine *e, const double *cholesky_lower, const doubl
  * multiples of 128), C [orders][M x N] int32 DEVICE: C[o] = sum over s + t = o of A_s B_t^T. */
 int hmcb_debug_i8_gemm(int device, int64_t M, int64_t N, int64_t K, int SA, int SB, int orders,
                        const signed char *A, const signed char *B, int32_t *C, void *stream);
+/* The modular variant of the sliced products ("Ozaki II", csrc/ozaki.cuh): Y = A X for a HOST matrix A [M x K]
+ * (row-major) and a DEVICE chain batch X [K x N] (chains contiguous; M, K, N multiples of 128): operands scaled to
+ * 44-bit integers, 13 exact int8 products modulo 13 coprime moduli on tcgen05, Chinese-remainder reconstruction
+ * -> DEVICE Y [M x N] fp64 (2^-44 of |A|_row-max |X|_chain-max per term). */
+int hmcb_debug_crt_product(int device, int64_t M, int64_t N, int64_t K, const double *A_host,
+                           const double *X_dev, double *Y_dev, void *stream);
 /* Gathered (block-sparse) slice products (csrc/ozaki_sparse.cuh): the building block of the sparse
  * LinearMatrix products on tcgen05.  A [SA][128 x Ktot]: the dense int8 tiles of `n_bundles` row bundles end to
  * end on the K axis; bundles [n_bundles] = {offset on that axis, k-blocks of 128}; list [Ktot]: the row of B every

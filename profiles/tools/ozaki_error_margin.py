@@ -38,8 +38,11 @@ print(json.dumps({"slice_products": eng.tcgen05_slice_pairs,
                   "decisions_equal": bool(np.array_equal(got["out_accept"][:, sel].astype(bool), ref["accept"]))}))
 ''' % (ROOT, ROOT, ROOT)
 res = {}
-for name, env in {"DMMA (HMCB_OZAKI=0)": {"HMCB_OZAKI": "0"}, "orders 0..4 (5 digits)": {"HMCB_OZAKI_ORDERS": "5"},
-                  "orders 0..5 (6 digits, default)": {}, "orders 0..6 (7 digits)": {"HMCB_OZAKI_ORDERS": "7"}}.items():
+for name, env in {"DMMA (HMCB_OZAKI=0)": {"HMCB_OZAKI": "0"},
+                  "orders 0..4 (5 digits)": {"HMCB_OZAKI_ORDERS": "5"},
+                  "orders 0..5 (6 digits, default)": {},
+                  "orders 0..6 (7 digits)": {"HMCB_OZAKI_ORDERS": "7"},
+                  "G q 6 digits, G^T r 13 modular products (HMCB_OZAKI_CRT=1)": {"HMCB_OZAKI_CRT": "1"}}.items():
     p = subprocess.run([sys.executable, "-c", WORKER], env={**os.environ, **env}, capture_output=True, text=True)
     res[name] = json.loads(p.stdout.strip().splitlines()[-1]) if p.returncode == 0 else {"error": p.stderr[-400:]}
 print(json.dumps(res, indent=1))

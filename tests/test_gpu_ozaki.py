@@ -51,10 +51,12 @@ def test_i8_slice_products_are_exact(monkeypatch, pair, M, N, K, SA, SB, orders)
     assert torch.equal(got.double(), ref)
 
 
+@pytest.mark.parametrize("crt", ["0", "1"])
 @pytest.mark.parametrize("name", ["dense_direct_4s", "dense_direct_f64", "dense_full_mass_3s"])
-def test_ozaki_path_reproduces_the_golden_trajectories(monkeypatch, name):
+def test_ozaki_path_reproduces_the_golden_trajectories(monkeypatch, name, crt):
     """The dense direct products on tcgen05 (int8 slices, exact int32 accumulation, fp64 recombination)
-    forced on for the small golden cases: same 1e-10 / identical-decision bar as the DMMA path."""
+    forced on for the small golden cases: same 1e-10 / identical-decision bar as the DMMA path.  With
+    HMCB_OZAKI_CRT=1 the second product G^T r runs as 13 modular products + Chinese-remainder reconstruction."""
     import torch
 
     import cases
@@ -63,11 +65,13 @@ def test_ozaki_path_reproduces_the_golden_trajectories(monkeypatch, name):
     from hmclab_b200._lowering import describe, describe_mass, flatten
 
     monkeypatch.setenv("HMCB_OZAKI", "1")
+    monkeypatch.setenv("HMCB_OZAKI_CRT", crt)
     inp, ref = load_golden(name)
     s = cases.SETTINGS[name]
     K, C_, d = inp["z"].shape
     post, mass = build_mirror(name, inp)
     eng = Engine(flatten(describe(post)), describe_mass(mass), C_, integrator=s["integrator"], amount_of_steps=s["steps"])
+    assert (eng.tcgen05_slice_pairs in (20 + 13, 21 + 13)) == (crt == "1") and eng.tcgen05_slice_pairs >= 33
     G = eng.grads_per_proposal
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda()   # noqa: E731
     q = dev(inp["q0"])
@@ -172,8 +176,8 @@ def test_gathered_slice_products_are_exact(N, kblocks, SA, SB, orders):
     assert torch.equal(out.double(), ref)
 
 
-@pytest.mark.parametrize("premult", [False, True])
-def test_ozaki_path_at_config3_shape_vs_oracle(monkeypatch, premult):
+@pytest.mark.parametrize("premult,crt", [(False, "0"), (False, "1"), (True, "0")])
+def test_ozaki_path_at_config3_shape_vs_oracle(monkeypatch, premult, crt):
     """A scaled config-3 problem (333 parameters x 700 data, 130 chains, 4-stage) with the tcgen05 path
     forced on, both forms of the dense LinearMatrix: the direct products G q / G^T r and the premultiplied
     GtG q (an fp64-valued operator: six digits), checked against the oracle like the full-size tests."""
@@ -181,7 +185,47 @@ def test_ozaki_path_at_config3_shape_vs_oracle(monkeypatch, premult):
     from test_gpu_fullsize import _compare_with_oracle
 
     monkeypatch.setenv("HMCB_OZAKI", "1")
+    monkeypatch.setenv("HMCB_OZAKI_CRT", crt)
     w = workloads.dense_large(dims=333, data=700, chains=130, premultiplication=premult)
     eng, _ = _compare_with_oracle(w, K=2)
     assert eng.path == "staged" and eng.tcgen05_slice_pairs > 0
     assert (eng.tcgen05_slice_pairs <= 21) == premult       # one product premultiplied, two in the direct form
+    assert (eng.tcgen05_slice_pairs == 20 + 13) == (crt == "1")
+
+
+@pytest.mark.parametrize("pair", ["1", "0"])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (384, 640, 1152), (256, 256, 10112)])
+def test_modular_products_rebuild_the_exact_integer_product(monkeypatch, pair, M, N, K):
+    """The modular variant (13 int8 products modulo coprime moduli + Chinese-remainder reconstruction): for
+    integer operands the result is the integer product to fp64 rounding; for real operands it is within 2^-42
+    of sum |a| |x| (operands cut at 44 bits below the row / chain maximum)."""
+    import torch
+
+    from hmclab_b200._engine import load_library
+
+    monkeypatch.setenv("HMCB_OZAKI_PAIR", pair)
+    lib = load_library()
+    rng = np.random.default_rng(M + N + K)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def product(A, X):
+        Xd = torch.as_tensor(X).cuda().contiguous()
+        Y = torch.full((M, N), np.nan, dtype=torch.float64, device="cuda")
+        rc = lib.hmcb_debug_crt_product(torch.cuda.current_device(), M, N, K,
+                                        np.ascontiguousarray(A).ctypes.data_as(C.POINTER(C.c_double)), Xd.data_ptr(),
+                                        Y.data_ptr(), st)
+        assert rc == 0, rc
+        return Y.cpu().numpy()
+
+    Ai = rng.integers(-2**15, 2**15, size=(M, K)).astype(np.float64)
+    Xi = rng.integers(-2**15, 2**15, size=(K, N)).astype(np.float64)
+    Ai[3] = 0.0                       # an all-zero row and an all-zero chain
+    Xi[:, 5] = 0.0
+    exact = (Ai.astype(np.int64) @ Xi.astype(np.int64)).astype(np.float64)
+    got = product(Ai, Xi)            # the integer product is rebuilt exactly; the conversion to fp64 rounds once or twice
+    assert np.max(np.abs(got - exact)) <= 4e-16 * np.max(np.abs(exact)) and np.all(got[3] == 0) and np.all(got[:, 5] == 0)
+    A = rng.normal(size=(M, K)) * np.exp(rng.normal(size=(M, 1)) * 3)      # row scales over orders of magnitude
+    X = rng.normal(size=(K, N)) * np.exp(rng.normal(size=(1, N)) * 3)
+    got = product(A, X)
+    bound = np.abs(A) @ np.abs(X)
+    assert np.max(np.abs(got - A @ X) / bound) < 2.0**-42
